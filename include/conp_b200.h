@@ -1,0 +1,218 @@
+/* conp_b200.h -- C ABI of the B200 (sm_100a) electrode charge solve.
+ *
+ * This is the drop-in boundary for USER-CONP2's per-step path.  The LAMMPS
+ * shim classes (lammps-user-conp2_b200/shim/: FixConp, FixConq, FixCond,
+ * PPPMCONP) keep the reference's deck syntax and hook order and forward to
+ * these entry points; the Python host mirror (conp_b200/fix_conp.py) and the
+ * tests bind the same symbols through ctypes.
+ *
+ * Each entry point names the reference interface it replaces (file:line
+ * relative to the upstream USER-CONP2 tree).
+ *
+ * Conventions
+ *  - every function returns CONP_OK (0) or a CONP_ERR_* code; nothing aborts
+ *    or throws across the boundary.  conp_last_error() gives the message; the
+ *    shim turns a non-zero code into a collective error->all(FLERR, msg)
+ *    (the reference's only error mechanism, e.g. fix_conp.cpp:956).
+ *  - pointer arguments are HOST memory borrowed for the duration of the call
+ *    (pinned memory recommended) unless the name says `_device`.
+ *  - one context per GPU / MPI rank, not thread-safe; all ranks call the
+ *    collective entry points (marked [collective]) in the same order.
+ *  - all floating point is FP64, all indices are 32-bit int (LAMMPS tagint in
+ *    default builds, fix_conp.cpp:474).
+ *  - there is NO CPU fallback: without a CUDA device conp_create() fails.
+ */
+#ifndef CONP_B200_H
+#define CONP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CONP_ABI_VERSION 1
+#define CONP_UNIQUE_ID_BYTES 128
+
+typedef struct conp_ctx conp_ctx;
+
+enum conp_status {
+  CONP_OK = 0,
+  CONP_ERR_ARG = 1,      /* "Illegal fix conp command ..." class of errors            */
+  CONP_ERR_STATE = 2,    /* entry points called out of order                          */
+  CONP_ERR_CUDA = 3,     /* CUDA / cuFFT / cuSOLVER failure                           */
+  CONP_ERR_NUMERIC = 4,  /* "Inversion failed!"                   fix_conp.cpp:956    */
+  CONP_ERR_RANGE = 5,    /* "Out of range atoms - cannot compute PPPM" pppm_conp.cpp:167 */
+  CONP_ERR_COMM = 6,     /* NCCL failure                                              */
+  CONP_ERR_NOMEM = 7
+};
+
+enum { CONP_FF_NORMAL = 0, CONP_FF_FFIELD = 1, CONP_FF_NOSLAB = 2 }; /* fix_conp.cpp:68 */
+enum { CONP_PAIR_ETA = 0, CONP_PAIR_EHGO = 1 };                      /* fix_conp.cpp:69 */
+enum { CONP_KSPACE_EWALD = 0, CONP_KSPACE_PPPM = 1 };                /* `pppm` keyword, fix_conp.cpp:164, 401-408 */
+enum { CONP_VARIANT_CONP = 0, CONP_VARIANT_CONQ = 1, CONP_VARIANT_COND = 2 };
+
+/* sizes and counters, filled by conp_get_info() */
+typedef struct conp_info {
+  int abi_version;
+  int device, rank, nranks;
+  int n_ele;              /* elenum_all                                   */
+  int row_begin, row_end; /* this GPU's row block of A / S                */
+  int n_elyte;            /* charged+uncharged non-electrode atoms, all ranks */
+  int kxmax, kymax, kzmax;
+  int kcount, kcount_flat, kcount_expand; /* km_ewald.cpp:360-361           */
+  int mesh[3], order;
+  long long matrix_pitch; /* doubles per stored row of S                  */
+  long long launches;     /* kernels launched by this library so far      */
+  double setup_build_ms, setup_invert_ms; /* last conp_build_A / conp_invert_project */
+  double ee, dd;          /* "<e,e>" and "<d,d>" log values, fix_conp.cpp:1006-1009, 458-461 */
+  double totsetq;
+} conp_info;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+int conp_abi_version(void);
+
+/* Rank 0 creates the NCCL unique id; the host broadcasts the 128 bytes to
+ * the other ranks (MPI_Bcast on LAMMPS' `world`) before conp_create(). */
+int conp_get_unique_id(void *id_out /* CONP_UNIQUE_ID_BYTES */);
+
+/* One context per GPU.  unique_id may be NULL when nranks == 1.
+ * Replaces the constructors FixConp::FixConp (fix_conp.cpp:79-201) and
+ * KSpaceModuleEwald::KSpaceModuleEwald (km_ewald.cpp:41-54). [collective] */
+int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *unique_id);
+void conp_destroy(conp_ctx *ctx);
+const char *conp_last_error(const conp_ctx *ctx); /* ctx may be NULL: last conp_create failure */
+int conp_get_info(const conp_ctx *ctx, conp_info *out);
+
+/* ---- one-time setup (FixConp::linalg_init / linalg_setup) --------------- */
+
+/* domain->boxlo/prd/periodicity, force->kspace->slabflag/slab_volfactor and
+ * the fix's ffield/noslab keyword (km_ewald.cpp:66-89, fix_conp.cpp:120-133). */
+int conp_set_cell(conp_ctx *ctx, const double boxlo[3], const double prd[3], const int periodic[3],
+                  int slabflag, double slab_volfactor, int ff_flag);
+
+/* KSpaceModuleEwald::conp_setup (km_ewald.cpp:63-132): k-vector enumeration
+ * from LAMMPS' absolute accuracy, q2 = qqrd2e*sum(q^2)/dielectric over all
+ * atoms at setup, natoms = atom->natoms.  Needed in both KSpace modes: the A
+ * matrix always comes from the Ewald module (pppm_conp.cpp:91-101).
+ * lowmem is accepted for deck compatibility (`himem` keyword,
+ * fix_conp.cpp:167); it selects a CPU table layout in the reference and does
+ * not change results. */
+int conp_set_ewald(conp_ctx *ctx, double g_ewald, double accuracy_abs, double q2, long long natoms,
+                   int lowmem);
+
+/* Pair-potential data of the Coulomb pair style + the fix (fix_conp.cpp:252-258,
+ * 1232-1238, 1300-1305): cutsq is (ntypes+1)^2 row-major; eta_ij/fo_ij/u0_i
+ * are the EHGO tables (fix_conp.cpp:1517-1559; may be NULL in ETA mode);
+ * is_eletype[ntypes+1] holds the `etypes` keyword (NULL / smartlist 0 = all
+ * pairs listed, fix_conp.cpp:304-361). */
+int conp_set_pair(conp_ctx *ctx, int pairmode, double eta, double cut_coul, int ntypes,
+                  const double *cutsq, const double *eta_ij, const double *fo_ij, const double *u0_i,
+                  int smartlist, const int *is_eletype);
+
+/* Global electrode description in eleall order (FixConp::post_neighbor,
+ * fix_conp.cpp:468-539): side = electrode_check() (+1 fix group, -1 group2;
+ * fix_conp.cpp:599-605); xyz is N x 3.  The library splits the rows into
+ * nranks contiguous equal blocks (conp_info.row_begin/row_end). [collective] */
+int conp_set_electrodes(conp_ctx *ctx, int n_ele, const int *tag, const int *type, const int *side,
+                        const double *xyz);
+
+/* Host PPPM tables for `kspace_style pppm/conp` (PPPMCONP inherits them from
+ * LAMMPS PPPM: rho_coeff [order][order] with the k index shifted by -nlower,
+ * greensfn on the full mesh [nz][ny][nx] x-fastest, shift/shiftone;
+ * pppm_conp.cpp:146-148, 199-203, 245-249).  Also caches the electrode
+ * stencils (aaa_map_rho, pppm_conp.cpp:318-344) and allocates the bricks
+ * (setup_allocate :346-356). */
+int conp_pppm_setup(conp_ctx *ctx, const int mesh[3], int order, const double *rho_coeff,
+                    const double *greensfn, double shift, double shiftone);
+
+/* FixConp::a_cal (fix_conp.cpp:777-861) = KSpaceModuleEwald::a_cal
+ * (km_ewald.cpp:147-151, 426-666) + self term + alist_coul_cal (:1209-1279)
+ * + symmetrisation, for this GPU's row block. [collective] */
+int conp_build_A(conp_ctx *ctx);
+
+/* `org <file>` / `inv <file>` keywords (FixConp::a_read, fix_conp.cpp:721-773):
+ * full n_ele x n_ele row-major matrix; is_inverse != 0 skips the inversion. */
+int conp_load_matrix(conp_ctx *ctx, const double *full_matrix, int is_inverse);
+/* `matout` keyword (fix_conp.cpp:833-849, 960-977): this rank's row block of
+ * the current matrix (A before conp_invert_project, S after), n_rows x n_ele. */
+int conp_get_matrix(conp_ctx *ctx, double *rows_out);
+
+/* FixConp::inv + inv_project (fix_conp.cpp:932-1067): in-place inverse, then
+ * (unless one_electrode) the electroneutrality projection(s).
+ * ee_out receives "<e,e>" (may be NULL). [collective] */
+int conp_invert_project(conp_ctx *ctx, int nullneutral, int zneutr, int one_electrode, double *ee_out);
+
+/* b_setq_cal + cond_setup + get_setq (fix_conp.cpp:609-637, 1071-1116,
+ * fix_cond.cpp:46-55): d vector, elesetq = S.d, totsetq; q_init (may be NULL)
+ * is the `qinit` snapshot in eleall order; with one_electrode the projection
+ * is applied afterwards (:1115). [collective] */
+int conp_set_unit_voltage(conp_ctx *ctx, double evscale, const double *q_init, int one_electrode,
+                          int nullneutral, int zneutr, double *totsetq_out);
+
+/* ---- per-step path ------------------------------------------------------ */
+
+/* FixConp::post_neighbor (fix_conp.cpp:468-539) for the atoms this rank
+ * owns: static per-atom data until the next reneighbouring.  mask/groupbits
+ * as in LAMMPS (atom->mask, groupbit | jgroupbit): atoms with
+ * (mask & ele_bits) != 0 are electrode atoms and are skipped; mask may be
+ * NULL when only non-electrode atoms are passed.  counts[nranks] = nlocal of
+ * every rank (NULL when nranks == 1). */
+int conp_post_neighbor(conp_ctx *ctx, int nlocal, const double *q, const int *type, const int *mask,
+                       int ele_bits, const int *counts);
+
+/* FixConp::pre_force (fix_conp.cpp:543-573) = b_cal (:677-695: k-space part
+ * km_ewald.cpp:153-167 or pppm_conp.cpp:269-316, real-space part
+ * fix_conp.cpp:1281-1365) + update_charge of the chosen variant
+ * (fix_conp.cpp:1120-1161, fix_conq.cpp:41-90, fix_cond.cpp:70-126).
+ * x = atom->x[0] (nlocal x 3).  value = dV [V] for conp, right-electrode
+ * charge for conq, D for cond.  q_ele_out[n_ele] = new electrode charges in
+ * eleall order; scalar_out = the fix's compute_scalar(). [collective] */
+int conp_pre_force(conp_ctx *ctx, const double *x, int kspace_mode, int variant, double value,
+                   double *q_ele_out, double *scalar_out);
+
+/* Same solve with the positions already in device memory (x_device: nlocal x 3
+ * on this context's GPU) and no device->host copy: the device-resident timing
+ * leg of bench.py.  Results are fetched with conp_get_charges(). [collective] */
+int conp_solve_device(conp_ctx *ctx, const double *x_device, int kspace_mode, int variant,
+                      double value);
+int conp_get_charges(conp_ctx *ctx, double *q_ele_out, double *scalar_out);
+
+/* b vector of the last solve (bbb_all, fix_conp.cpp:694) and its k-space-only
+ * part (kspmod->b_cal output incl. slab term). */
+int conp_get_b(conp_ctx *ctx, double *b_out, double *b_kspace_out);
+
+/* PPPMCONP::ele_make_rho / make_rho overrides (pppm_conp.cpp:385-450): bricks
+ * on the global periodic mesh [nz][ny][nx]; which = 0 electrolyte, 1 electrode,
+ * 2 sum (what the host PPPM force pass consumes). */
+int conp_get_density(conp_ctx *ctx, int which, double *brick_out);
+/* u_brick (pppm_conp.cpp:260-266) for potential probes. */
+int conp_get_potential_brick(conp_ctx *ctx, double *brick_out);
+
+/* FixConp::post_force -> force_cal (fix_conp.cpp:1163-1201, 1368-1444).
+ * f_out (nlocal x 3, may be NULL) receives the Gaussian-correction force on
+ * this rank's non-electrode atoms (zero rows for electrode atoms);
+ * energies_out[8] = { pair ecoul tally, self energy added to kspace->energy,
+ * virial xx yy zz xy xz yz }, summed over ranks. [collective] */
+int conp_post_force(conp_ctx *ctx, double qqrd2e, double *f_out, double *energies_out);
+
+/* ---- instrumentation ------------------------------------------------------ */
+
+void *conp_stream(conp_ctx *ctx); /* cudaStream_t all kernels are launched on */
+int conp_sync(conp_ctx *ctx);
+/* CUDA events on the context's stream (slots 0..15) */
+int conp_timer_record(conp_ctx *ctx, int slot);
+int conp_timer_elapsed_ms(conp_ctx *ctx, int slot_begin, int slot_end, float *ms_out);
+/* per-stage event timing of the solves since the last reset:
+ * out[0..7] = mean ms of {upload/pack, bin, pair, kspace, gather/extract,
+ * exchange, gemv, epilogue+electrode spread}; returns number of solves. */
+int conp_stage_times(conp_ctx *ctx, int enable, double *out8);
+/* stand-alone kernels for roofline measurement (bench.py):
+ *   conp_bench_gemv: one q = S.b pass on the resident row block.
+ *   conp_bench_dgemm_tflops: cuBLAS DGEMM n^3 ceiling for the Gram. */
+int conp_bench_gemv(conp_ctx *ctx, int reps, float *ms_per_rep_out);
+int conp_bench_dgemm_tflops(conp_ctx *ctx, int n, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONP_B200_H */

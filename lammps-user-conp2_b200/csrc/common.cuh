@@ -1,0 +1,262 @@
+// Internal declarations shared by the translation units of libconp_b200.so.
+// Public boundary: include/conp_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/conp_b200.h"
+
+namespace conp {
+
+// ---------------------------------------------------------------------------
+// error plumbing: nothing throws across the C ABI
+// ---------------------------------------------------------------------------
+struct Error {
+  int code;
+  std::string msg;
+};
+
+#define CONP_THROW(code_, ...)                                   \
+  do {                                                           \
+    char buf_[512];                                              \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);                   \
+    throw ::conp::Error{(code_), std::string(buf_)};             \
+  } while (0)
+
+#define CUDA_CHECK(expr)                                                                     \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      CONP_THROW(CONP_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_),       \
+                 __FILE__, __LINE__, #expr);                                                 \
+  } while (0)
+
+#define CUFFT_CHECK(expr)                                                                    \
+  do {                                                                                       \
+    cufftResult r_ = (expr);                                                                 \
+    if (r_ != CUFFT_SUCCESS)                                                                 \
+      CONP_THROW(CONP_ERR_CUDA, "cuFFT error %d at %s:%d (%s)", (int)r_, __FILE__, __LINE__, \
+                 #expr);                                                                     \
+  } while (0)
+
+#define CUSOLVER_CHECK(expr)                                                                 \
+  do {                                                                                       \
+    cusolverStatus_t r_ = (expr);                                                            \
+    if (r_ != CUSOLVER_STATUS_SUCCESS)                                                       \
+      CONP_THROW(CONP_ERR_CUDA, "cuSOLVER error %d at %s:%d (%s)", (int)r_, __FILE__,        \
+                 __LINE__, #expr);                                                           \
+  } while (0)
+
+#define CUBLAS_CHECK(expr)                                                                   \
+  do {                                                                                       \
+    cublasStatus_t r_ = (expr);                                                              \
+    if (r_ != CUBLAS_STATUS_SUCCESS)                                                         \
+      CONP_THROW(CONP_ERR_CUDA, "cuBLAS error %d at %s:%d (%s)", (int)r_, __FILE__,          \
+                 __LINE__, #expr);                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// device buffer with RAII; grows, never shrinks
+// ---------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    release();
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess)
+      CONP_THROW(CONP_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    p = (T *)q;
+    cap = n;
+  }
+  void upload(const T *h, size_t n, cudaStream_t s) {
+    reserve(n);
+    if (n) CUDA_CHECK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T> &h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void zero(size_t n, cudaStream_t s) {
+    reserve(n);
+    if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFreeHost(p);
+    void *q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, n * sizeof(T));
+    if (e != cudaSuccess) CONP_THROW(CONP_ERR_NOMEM, "cudaMallocHost of %zu bytes failed", n * sizeof(T));
+    p = (T *)q;
+    cap = n;
+  }
+};
+
+// 32-byte packed point charge: position (wrapped into the box along periodic
+// dimensions) and charge.  One 2x LDG.128 per atom in the pair/spread kernels.
+struct __align__(32) PosQ {
+  double x, y, z, q;
+};
+
+// ---------------------------------------------------------------------------
+// geometry of the uniform cell grid used to bin point charges
+// ---------------------------------------------------------------------------
+struct CellGrid {
+  int nc[3];
+  int periodic[3];
+  int smax[3];  // periodic image shifts searched: -smax..smax
+  double lo[3], prd[3], cinv[3];
+  double rc;    // search radius the grid was sized for
+  int ncells;
+};
+
+// per-type-pair tables for the real-space kernels (device pointers)
+struct PairTables {
+  int ntypes;
+  int pairmode;
+  double g_ewald, eta;
+  const double *cuteff;  // (ntypes+1)^2: min(cutsq, cut_coulsq) if the pair is listed else 0
+  const double *eta_ij;  // EHGO
+  const double *fo_ij;   // EHGO
+};
+
+struct EwaldHost {
+  int kxmax = 0, kymax = 0, kzmax = 0, kcount = 0, kcount_flat = 0, kcount_expand = 0;
+  int dims[7] = {0, 0, 0, 0, 0, 0, 0};
+  double unitk[3] = {0, 0, 0}, gsqmx = 0, volume = 0, ug_tot = 0;
+  // device ordering: grouped by (kx, ky) with kz fastest
+  std::vector<short> kx, ky, kz;
+  std::vector<double> ug;
+};
+
+struct PPPMGeom {
+  int nx, ny, nz, order, nlower;
+  double boxlo[3], delinv[3], delvolinv, shift, shiftone;
+};
+
+// ---------------------------------------------------------------------------
+// NCCL, loaded at run time (comm.cu)
+// ---------------------------------------------------------------------------
+struct Comm;
+Comm *comm_create(int rank, int nranks, const void *unique_id);
+void comm_destroy(Comm *);
+int comm_get_unique_id(void *out);
+void comm_allgather(Comm *, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t);
+void comm_allgatherv(Comm *, const void *send, void *recv, const size_t *bytes, const size_t *offsets,
+                     int rank, int nranks, cudaStream_t);
+void comm_allreduce_sum_f64(Comm *, double *buf, size_t n, cudaStream_t);
+
+// ---------------------------------------------------------------------------
+// kernel launchers (one .cu per group); all take the context's stream and
+// return the number of kernels they launched
+// ---------------------------------------------------------------------------
+
+// gemv.cu ------------------------------------------------------------------
+// out[r] = sum_c S[r*pitch + c] * b[c], r < nrows, c < ncols_pad (pad columns of S and b are zero).
+int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int ncols_pad, const double *b,
+                double *out, int num_sms);
+// conp/conq/cond epilogue over the full eleallq vector (single block)
+int launch_update_charge(cudaStream_t s, int variant, int n, const double *sb, const double *setq,
+                         const double *qinit, const int *side, const double *setz, double totsetq,
+                         double value, int one_electrode, const double *dipole_dev, double lz, double vmult,
+                         double *q_out, double *scalar_out /* [0]=scalar, [1]=potdiff */);
+
+// pair.cu ------------------------------------------------------------------
+CellGrid make_cell_grid(const double lo[3], const double prd[3], const int periodic[3], double rc);
+// pack: gather raw positions -> wrapped PosQ, accumulate sum(q z) [slab/cond dipole], count per cell
+int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
+                      const double *q, const int *type, PosQ *packed, int *packed_type, int *cell_of, int *slot,
+                      int *cell_count, double *qz_sum);
+int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, int *cell_of, int *slot,
+                         int *cell_count);
+int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start);
+int launch_cell_scatter(cudaStream_t s, int m, const PosQ *packed, const int *type, const int *cell_of,
+                        const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type, int *sorted_src);
+int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
+                  const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
+                  const int *sorted_type, const int *cell_start, double *b_real /* indexed by global row */);
+int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
+                  const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
+                  const int *sorted_type, const int *sorted_src, const int *cell_start, double *A_rows,
+                  size_t pitch);
+int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e, int row_begin,
+                          int row_end, const double *ex, const double *ey, const double *ez, const int *etype,
+                          const double *q_ele, const PosQ *sorted, const int *sorted_type, const int *sorted_src,
+                          const int *cell_start, const double *cutsq_listed, double *f_packed /* m x 3 */,
+                          double *energies /* 8 */);
+
+// pppm.cu ------------------------------------------------------------------
+int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m, const PosQ *atoms,
+                       double *brick, int *range_flag);
+int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
+int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
+                            const double *ey, const double *ez, int *part2grid, double *weights);
+int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *part2grid,
+                         const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
+                         double slab_pref /* 4 pi / V or 0 */, const double *b_real, double *b_kspace, double *b);
+int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, const double *weights,
+                           const double *q_ele, double *brick);
+int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out);
+
+// ewald.cu -----------------------------------------------------------------
+void ewald_setup_host(EwaldHost &e, double g_ewald, double accuracy, double q2, long long natoms,
+                      const double prd[3], double slab_volfactor);
+// axis tables E[a][i][m] = exp(i m unitk_a r_a), m = 0..kmax_a; layout per atom: (kxmax+1)+(kymax+1)+(kzmax+1) double2
+int launch_axis_tables(cudaStream_t s, int n, const double *x, const double *y, const double *z,
+                       const PosQ *packed /* or null */, const double unitk[3], int kxmax, int kymax, int kzmax,
+                       double2 *tab);
+int launch_ewald_sfac(cudaStream_t s, int m, const PosQ *atoms, const double2 *tab, int kxmax, int kymax,
+                      int kzmax, int kcount, const short *kx, const short *ky, const short *kz,
+                      double *sfac /* 2*kcount, zeroed by the launcher */);
+int launch_ewald_bextract(cudaStream_t s, int row_begin, int row_end, const double2 *etab, int kxmax, int kymax,
+                          int kzmax, int kcount, const short *kx, const short *ky, const short *kz,
+                          const double *ug, const double *sfac, const double *ez, const double *qz_sum,
+                          double slab_pref, const double *b_real, double *b_kspace, double *b);
+// k-major panel Pt[2*kc][ld]: rows kk / kc+kk = sqrt(2 u_k) {cos, sin}(k.r_i), k = k0+kk; segs = runs of
+// consecutive k with equal (kx,ky) inside the chunk
+int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, int kymax, int kzmax, int k0,
+                       int kc, int nseg, const int2 *segs, const short *kx, const short *ky, const short *kz,
+                       const double *ug, double *panel, size_t ld);
+
+// gram.cu ------------------------------------------------------------------
+// C[i][j] += sum_k Pt[k][row_begin+i] * Pt[k][j] (k-major panel, ld doubles per k-row); FP64 tensor cores
+int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
+                           const double *panel_all, size_t ld, double *C, size_t pitch);
+
+// linalg.cu ----------------------------------------------------------------
+int launch_a_finish(cudaStream_t s, int row_begin, int row_end, int n, double *A_rows, size_t pitch,
+                    double diag_kspace, int pairmode, double self_eta, const double *u0_i, const int *etype,
+                    double slab_pref, const double *ez);
+int launch_project(cudaStream_t s, int n, double *S, size_t pitch, const int *subset /* or null */,
+                   double *rowsum_tmp, double *tot_out /* device scalar */, int apply);
+int launch_d_vector(cudaStream_t s, int n, const double *ez, const int *side, int ff_flag, double evscale,
+                    double zlo, double zprd, double *d, double *setz);
+int launch_pad_identity(cudaStream_t s, int n, double *B, size_t ld);
+
+}  // namespace conp

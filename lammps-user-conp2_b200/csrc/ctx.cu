@@ -1,0 +1,1055 @@
+// C-ABI entry points (include/conp_b200.h) and the host-side orchestration of
+// the setup and per-step pipelines.  No numerical work happens on the host
+// besides O(N) bookkeeping; there is no CPU fallback.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace conp;
+
+namespace {
+constexpr double MY_PI = 3.14159265358979323846;
+constexpr double MY_PIS = 1.77245385090551602729;
+constexpr double ERFC_MAX = 5.8;
+constexpr int NSTAGE = 8;
+std::string g_create_error;
+
+size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+}  // namespace
+
+struct conp_ctx {
+  int device = 0, rank = 0, nranks = 1, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  Comm *comm = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  bool have_cell = false, have_ewald = false, have_pair = false, have_ele = false, have_pppm = false;
+  bool have_A = false, inverted = false, have_setq = false, have_atoms = false, solved = false;
+
+  // cell ---------------------------------------------------------------
+  double boxlo[3] = {0, 0, 0}, prd[3] = {1, 1, 1};
+  int periodic[3] = {1, 1, 1};
+  int slabflag = 0, ff_flag = 0;
+  double slab_volfactor = 1.0;
+
+  // ewald ----------------------------------------------------------------
+  double g_ewald = 0;
+  EwaldHost ew;
+  DevBuf<short> d_kx, d_ky, d_kz;
+  DevBuf<double> d_ug, d_sfac;
+  DevBuf<double2> d_etab, d_jtab;
+
+  // pair -----------------------------------------------------------------
+  int pairmode = 0, ntypes = 0, smartlist = 0;
+  double eta = 0, cut_coul = 0;
+  std::vector<double> h_cutsq, h_u0;
+  DevBuf<double> d_cuteff_b, d_cuteff_a, d_cutsq_listed, d_eta_ij, d_fo_ij, d_u0;
+  double rc_b = 0, rc_a = 0, rc_f = 0;
+
+  // electrodes -------------------------------------------------------------
+  int N = 0, rpr = 0, r0 = 0, r1 = 0, ncols_pad = 0;
+  size_t pitch = 0, vlen = 0;
+  std::vector<int> h_tag, h_type, h_side;
+  std::vector<double> h_xyz;
+  DevBuf<double> d_ex, d_ey, d_ez, d_exyz;
+  DevBuf<int> d_etype, d_eside;
+
+  // matrix / vectors ---------------------------------------------------------
+  DevBuf<double> d_mat, d_fullS;
+  DevBuf<double> d_b, d_bk, d_breal, d_sb, d_q, d_setq, d_dvec, d_setz, d_qinit, d_scal;
+  bool have_qinit = false;
+  double totsetq = 0, vmult = 0, evscale = 0, ee = 0, dd = 0;
+  int one_electrode = 0;
+  double build_ms = 0, invert_ms = 0;
+
+  // atoms ------------------------------------------------------------------------
+  int nlocal = 0, m_local = 0, m_total = 0;
+  std::vector<int> h_idx, m_counts, m_offsets;
+  DevBuf<double> d_xraw, d_qraw;
+  DevBuf<int> d_typeraw, d_idx;
+  DevBuf<PosQ> d_packed, d_sorted;
+  DevBuf<int> d_ptype, d_stype, d_ssrc, d_cellof, d_slot, d_cellcount, d_cellstart;
+  CellGrid grid_b;
+  DevBuf<double> d_fpacked;
+
+  // pppm ---------------------------------------------------------------------------
+  PPPMGeom pg;
+  size_t ngrid = 0, nhalf = 0;
+  DevBuf<double> d_rho, d_ghalf, d_brick, d_ubrick, d_ebrick, d_weights, d_tmpbrick;
+  DevBuf<int> d_part2grid, d_flag;
+  DevBuf<cufftDoubleComplex> d_work;
+  cufftHandle plan_f = 0, plan_b = 0;
+  bool plans = false;
+
+  cusolverDnHandle_t solver = nullptr;
+  cublasHandle_t blas = nullptr;
+
+  // timing ----------------------------------------------------------------------------
+  cudaEvent_t ev[16];
+  cudaEvent_t sev[NSTAGE + 1];
+  bool stage_timing = false;
+  double stage_ms[NSTAGE] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int stage_n = 0;
+
+  // scalars in d_scal: [0] scalar_output [1] potdiff [2] qz_sum [3] projection total [4..11] energies
+  double *scal(int i) { return d_scal.p + i; }
+};
+
+namespace {
+
+template <class F>
+int guard(conp_ctx *c, F &&f) {
+  if (!c) return CONP_ERR_ARG;
+  try {
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) CONP_THROW(CONP_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    f();
+    return CONP_OK;
+  } catch (const Error &e) {
+    c->err = e.msg;
+    return e.code;
+  } catch (const std::exception &e) {
+    c->err = e.what();
+    return CONP_ERR_CUDA;
+  }
+}
+
+void need(bool cond, const char *what) {
+  if (!cond) CONP_THROW(CONP_ERR_STATE, "%s", what);
+}
+
+PairTables pair_tables(conp_ctx *c, const double *cuteff) {
+  PairTables pt;
+  pt.ntypes = c->ntypes;
+  pt.pairmode = c->pairmode;
+  pt.g_ewald = c->g_ewald;
+  pt.eta = c->eta;
+  pt.cuteff = cuteff;
+  pt.eta_ij = c->d_eta_ij.p;
+  pt.fo_ij = c->d_fo_ij.p;
+  return pt;
+}
+
+double slab_pref(const conp_ctx *c) {
+  if (!c->slabflag) return 0.0;
+  const double volume = c->prd[0] * c->prd[1] * c->prd[2] * c->slab_volfactor;
+  return 4.0 * MY_PI / volume;  // km_ewald.cpp:839, pppm_conp.cpp:307
+}
+
+// bin an arbitrary packed set (positions already wrapped) into grid g
+void bin_sorted(conp_ctx *c, const CellGrid &g, int m) {
+  c->d_cellcount.zero((size_t)g.ncells + 1, c->stream);
+  c->d_cellstart.reserve((size_t)g.ncells + 1);
+  c->d_cellof.reserve(m);
+  c->d_slot.reserve(m);
+  c->d_sorted.reserve(m);
+  c->d_stype.reserve(m);
+  c->d_ssrc.reserve(m);
+  c->launches += launch_bin_positions(c->stream, g, m, c->d_packed.p, c->d_cellof.p, c->d_slot.p, c->d_cellcount.p);
+  c->launches += launch_cell_scan(c->stream, g.ncells, c->d_cellcount.p, c->d_cellstart.p);
+  c->launches += launch_cell_scatter(c->stream, m, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
+                                     c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p);
+}
+
+void stage_mark(conp_ctx *c, int i) {
+  if (c->stage_timing) CUDA_CHECK(cudaEventRecord(c->sev[i], c->stream));
+}
+
+// --------------------------------------------------------------------------
+// the per-step pipeline (device side, asynchronous on c->stream)
+// --------------------------------------------------------------------------
+void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant, double value) {
+  need(c->have_setq, "conp_pre_force: setup incomplete (conp_set_unit_voltage not called)");
+  need(c->have_atoms, "conp_pre_force: conp_post_neighbor not called");
+  if (kspace_mode == CONP_KSPACE_PPPM) need(c->have_pppm, "conp_pre_force: PPPM mode needs conp_pppm_setup");
+  if (variant < 0 || variant > 2) CONP_THROW(CONP_ERR_ARG, "conp_pre_force: unknown variant %d", variant);
+  cudaStream_t s = c->stream;
+  const int nr = c->r1 - c->r0;
+  const bool multi = c->nranks > 1;
+
+  stage_mark(c, 0);
+  // ---- pack (+ bin when single rank) ---------------------------------
+  CUDA_CHECK(cudaMemsetAsync(c->scal(2), 0, sizeof(double), s));
+  const CellGrid &g = c->grid_b;
+  c->d_cellcount.zero((size_t)g.ncells + 1, s);
+  PosQ *packed_local = c->d_packed.p + c->m_offsets[c->rank];
+  int *ptype_local = c->d_ptype.p + c->m_offsets[c->rank];
+  if (!multi) {
+    c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
+                                     ptype_local, c->d_cellof.p, c->d_slot.p, c->d_cellcount.p, c->scal(2));
+  } else {
+    c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
+                                     ptype_local, nullptr, nullptr, nullptr, c->scal(2));
+  }
+  stage_mark(c, 1);
+  if (multi) {
+    std::vector<size_t> bytes(c->nranks), offs(c->nranks);
+    for (int r = 0; r < c->nranks; ++r) {
+      bytes[r] = (size_t)c->m_counts[r] * sizeof(PosQ);
+      offs[r] = (size_t)c->m_offsets[r] * sizeof(PosQ);
+    }
+    comm_allgatherv(c->comm, packed_local, c->d_packed.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
+    for (int r = 0; r < c->nranks; ++r) {
+      bytes[r] = (size_t)c->m_counts[r] * sizeof(int);
+      offs[r] = (size_t)c->m_offsets[r] * sizeof(int);
+    }
+    comm_allgatherv(c->comm, ptype_local, c->d_ptype.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
+    comm_allreduce_sum_f64(c->comm, c->scal(2), 1, s);
+    c->launches += launch_bin_positions(s, g, c->m_total, c->d_packed.p, c->d_cellof.p, c->d_slot.p,
+                                        c->d_cellcount.p);
+  }
+  c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p);
+  c->launches += launch_cell_scatter(s, c->m_total, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
+                                     c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p);
+  stage_mark(c, 2);
+
+  // ---- real-space part of b (blist_coul_cal) ---------------------------------
+  if (c->rc_b > 0.0 && c->m_total > 0) {
+    c->launches += launch_pair_b(s, g, pair_tables(c, c->d_cuteff_b.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
+                                 c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_cellstart.p,
+                                 c->d_breal.p);
+  } else {
+    CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * nr, s));
+  }
+  stage_mark(c, 3);
+
+  // ---- k-space part of b --------------------------------------------------------
+  const double spref = slab_pref(c);
+  if (kspace_mode == CONP_KSPACE_PPPM) {
+    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * c->ngrid, s));
+    CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
+    c->launches += launch_pppm_spread(s, c->pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_brick.p, c->d_flag.p);
+    CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_work.p));
+    c->launches += launch_pppm_green_mul(s, c->nhalf, c->d_work.p, c->d_ghalf.p);
+    CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_work.p, c->d_ubrick.p));
+    c->launches += 2;  // at least one kernel per cuFFT exec (library)
+    stage_mark(c, 4);
+    c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_part2grid.p, c->d_weights.p, c->d_ubrick.p,
+                                        c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
+  } else {
+    const EwaldHost &e = c->ew;
+    const size_t T = (size_t)e.kxmax + e.kymax + e.kzmax + 3;
+    c->d_jtab.reserve(T * (size_t)std::max(c->m_total, 1));
+    c->launches += launch_axis_tables(s, c->m_total, nullptr, nullptr, nullptr, c->d_sorted.p, e.unitk, e.kxmax,
+                                      e.kymax, e.kzmax, c->d_jtab.p);
+    c->launches += launch_ewald_sfac(s, c->m_total, c->d_sorted.p, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
+                                     c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
+    stage_mark(c, 4);
+    c->launches += launch_ewald_bextract(s, c->r0, c->r1, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
+                                         c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, c->d_sfac.p, c->d_ez.p,
+                                         c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
+  }
+  stage_mark(c, 5);
+
+  // ---- exchange b, GEMV, exchange S.b --------------------------------------------
+  if (multi) comm_allgather(c->comm, c->d_b.p + c->r0, c->d_b.p, sizeof(double) * c->rpr, s);
+  stage_mark(c, 6);
+  c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms);
+  if (multi) comm_allgather(c->comm, c->d_sb.p + c->r0, c->d_sb.p, sizeof(double) * c->rpr, s);
+  stage_mark(c, 7);
+
+  // ---- epilogue -------------------------------------------------------------------
+  c->launches += launch_update_charge(s, variant, c->N, c->d_sb.p, c->d_setq.p,
+                                      c->have_qinit ? c->d_qinit.p : nullptr, c->d_eside.p, c->d_setz.p,
+                                      c->totsetq, value, c->one_electrode, c->scal(2), c->prd[2], c->vmult,
+                                      c->d_q.p, c->scal(0));
+  if (kspace_mode == CONP_KSPACE_PPPM) {  // kspmod->update_charge() -> ele_make_rho
+    CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * c->ngrid, s));
+    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_part2grid.p, c->d_weights.p, c->d_q.p,
+                                          c->d_ebrick.p);
+  }
+  stage_mark(c, 8);
+  c->solved = true;
+  if (c->stage_timing) {
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int i = 0; i < NSTAGE; ++i) {
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, c->sev[i], c->sev[i + 1]));
+      c->stage_ms[i] += ms;
+    }
+    c->stage_n++;
+  }
+}
+
+void check_range_flag(conp_ctx *c) {
+  if (!c->have_pppm) return;
+  int flag = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (flag) CONP_THROW(CONP_ERR_RANGE, "Out of range atoms - cannot compute PPPM");
+}
+
+// full-matrix projection(s) of inv_project on S (ld = N)
+void project_full(conp_ctx *c, double *S, int nullneutral, int zneutr) {
+  const int N = c->N;
+  DevBuf<double> w;
+  w.reserve(N);
+  // first pass always evaluates e^T S e (reported even without neutralisation, fix_conp.cpp:986-1009)
+  c->launches += launch_project(c->stream, N, S, N, nullptr, w.p, c->scal(3), nullneutral);
+  double tot = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&tot, c->scal(3), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->ee = tot;
+  if (nullneutral && zneutr) {
+    const double zhalf = 0.5 * c->prd[2] + c->boxlo[2];
+    std::vector<int> pos(N);
+    for (int i = 0; i < N; ++i) pos[i] = c->h_xyz[3 * i + 2] > zhalf;  // :1039
+    DevBuf<int> dpos;
+    dpos.upload(pos, c->stream);
+    c->launches += launch_project(c->stream, N, S, N, dpos.p, w.p, c->scal(3), 1);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+}
+
+void store_rows_from_full(conp_ctx *c, const double *full) {
+  const int nr = c->r1 - c->r0;
+  c->d_mat.zero((size_t)std::max(nr, 1) * c->pitch, c->stream);
+  if (nr > 0)
+    CUDA_CHECK(cudaMemcpy2DAsync(c->d_mat.p, c->pitch * sizeof(double), full + (size_t)c->r0 * c->N,
+                                 (size_t)c->N * sizeof(double), (size_t)c->N * sizeof(double), nr,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int conp_abi_version(void) { return CONP_ABI_VERSION; }
+
+int conp_get_unique_id(void *id_out) {
+  try {
+    return comm_get_unique_id(id_out);
+  } catch (const Error &e) {
+    g_create_error = e.msg;
+    return e.code;
+  }
+}
+
+int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *unique_id) {
+  if (!out || nranks < 1 || rank < 0 || rank >= nranks) {
+    g_create_error = "conp_create: bad arguments";
+    return CONP_ERR_ARG;
+  }
+  *out = nullptr;
+  conp_ctx *c = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      CONP_THROW(CONP_ERR_CUDA, "conp_create: no CUDA device (%s); this library has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) CONP_THROW(CONP_ERR_ARG, "conp_create: device %d of %d", device, ndev);
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      CONP_THROW(CONP_ERR_CUDA, "conp_create: device %s is sm_%d%d; kernels are built for sm_100a only", prop.name,
+                 prop.major, prop.minor);
+    c = new conp_ctx;
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &ev : c->ev) CUDA_CHECK(cudaEventCreate(&ev));
+    for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
+    c->d_scal.zero(16, c->stream);
+    c->comm = comm_create(rank, nranks, unique_id);
+    CUSOLVER_CHECK(cusolverDnCreate(&c->solver));
+    CUSOLVER_CHECK(cusolverDnSetStream(c->solver, c->stream));
+    CUBLAS_CHECK(cublasCreate(&c->blas));
+    CUBLAS_CHECK(cublasSetStream(c->blas, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return CONP_OK;
+  } catch (const Error &e) {
+    g_create_error = e.msg;
+    if (c) conp_destroy(c);
+    return e.code;
+  }
+}
+
+void conp_destroy(conp_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->plans) {
+    cufftDestroy(c->plan_f);
+    cufftDestroy(c->plan_b);
+  }
+  if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->blas) cublasDestroy(c->blas);
+  comm_destroy(c->comm);
+  for (auto &ev : c->ev) cudaEventDestroy(ev);
+  for (auto &ev : c->sev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *conp_last_error(const conp_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int conp_get_info(const conp_ctx *c, conp_info *o) {
+  if (!c || !o) return CONP_ERR_ARG;
+  std::memset(o, 0, sizeof(*o));
+  o->abi_version = CONP_ABI_VERSION;
+  o->device = c->device; o->rank = c->rank; o->nranks = c->nranks;
+  o->n_ele = c->N; o->row_begin = c->r0; o->row_end = c->r1; o->n_elyte = c->m_total;
+  o->kxmax = c->ew.kxmax; o->kymax = c->ew.kymax; o->kzmax = c->ew.kzmax;
+  o->kcount = c->ew.kcount; o->kcount_flat = c->ew.kcount_flat; o->kcount_expand = c->ew.kcount_expand;
+  if (c->have_pppm) { o->mesh[0] = c->pg.nx; o->mesh[1] = c->pg.ny; o->mesh[2] = c->pg.nz; o->order = c->pg.order; }
+  o->matrix_pitch = (long long)c->pitch;
+  o->launches = c->launches;
+  o->setup_build_ms = c->build_ms; o->setup_invert_ms = c->invert_ms;
+  o->ee = c->ee; o->dd = c->dd; o->totsetq = c->totsetq;
+  return CONP_OK;
+}
+
+// ---- setup -----------------------------------------------------------------
+
+int conp_set_cell(conp_ctx *c, const double boxlo[3], const double prd[3], const int periodic[3], int slabflag,
+                  double slab_volfactor, int ff_flag) {
+  return guard(c, [&] {
+    for (int a = 0; a < 3; ++a) {
+      if (!(prd[a] > 0.0) || !std::isfinite(boxlo[a]))
+        CONP_THROW(CONP_ERR_ARG, "Non-numeric box dimensions - simulation unstable");  // pppm_conp.cpp:136-137
+      c->boxlo[a] = boxlo[a]; c->prd[a] = prd[a]; c->periodic[a] = periodic[a] ? 1 : 0;
+    }
+    if (ff_flag < 0 || ff_flag > 2) CONP_THROW(CONP_ERR_ARG, "conp_set_cell: bad ff_flag");
+    c->slabflag = slabflag ? 1 : 0;
+    c->slab_volfactor = c->slabflag ? slab_volfactor : 1.0;
+    c->ff_flag = ff_flag;
+    c->have_cell = true;
+  });
+}
+
+int conp_set_ewald(conp_ctx *c, double g_ewald, double accuracy_abs, double q2, long long natoms, int lowmem) {
+  return guard(c, [&] {
+    need(c->have_cell, "conp_set_ewald: call conp_set_cell first");
+    (void)lowmem;
+    c->g_ewald = g_ewald;
+    ewald_setup_host(c->ew, g_ewald, accuracy_abs, q2, natoms, c->prd, c->slab_volfactor);
+    c->d_kx.upload(c->ew.kx, c->stream);
+    c->d_ky.upload(c->ew.ky, c->stream);
+    c->d_kz.upload(c->ew.kz, c->stream);
+    c->d_ug.upload(c->ew.ug, c->stream);
+    c->d_sfac.zero(2 * (size_t)std::max(c->ew.kcount, 1), c->stream);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->have_ewald = true;
+  });
+}
+
+int conp_set_pair(conp_ctx *c, int pairmode, double eta, double cut_coul, int ntypes, const double *cutsq,
+                  const double *eta_ij, const double *fo_ij, const double *u0_i, int smartlist,
+                  const int *is_eletype) {
+  return guard(c, [&] {
+    need(c->have_ewald, "conp_set_pair: call conp_set_ewald first (needs g_ewald)");
+    if (ntypes < 1 || !cutsq) CONP_THROW(CONP_ERR_ARG, "Fix conp couldn't detect a Coulombic pair style");
+    if (pairmode != CONP_PAIR_ETA && pairmode != CONP_PAIR_EHGO) CONP_THROW(CONP_ERR_ARG, "bad pairmode");
+    if (pairmode == CONP_PAIR_EHGO && (!eta_ij || !fo_ij || !u0_i))
+      CONP_THROW(CONP_ERR_ARG, "EHGO pair mode needs eta_ij, fo_ij and u0_i tables");
+    if (smartlist && !is_eletype) CONP_THROW(CONP_ERR_ARG, "Invalid fix conp command (Insufficient input entries for etypes)");
+    const int n1 = ntypes + 1;
+    c->pairmode = pairmode; c->eta = eta; c->cut_coul = cut_coul; c->ntypes = ntypes; c->smartlist = smartlist;
+    c->h_cutsq.assign(cutsq, cutsq + (size_t)n1 * n1);
+    std::vector<double> zero((size_t)n1 * n1, 0.0);
+    c->d_eta_ij.upload(eta_ij ? eta_ij : zero.data(), (size_t)n1 * n1, c->stream);
+    c->d_fo_ij.upload(fo_ij ? fo_ij : zero.data(), (size_t)n1 * n1, c->stream);
+    c->h_u0.assign(n1, 0.0);
+    if (u0_i) c->h_u0.assign(u0_i, u0_i + n1);
+    c->d_u0.upload(c->h_u0, c->stream);
+    // cut_coulsq = min(cut_coul^2, ERFC_MAX^2/g^2)  fix_conp.cpp:1236-1238, 1303-1305
+    double cut_coulsq = cut_coul * cut_coul;
+    const double cut_erfc = ERFC_MAX * ERFC_MAX / (c->g_ewald * c->g_ewald);
+    if (cut_coulsq > cut_erfc) cut_coulsq = cut_erfc;
+    std::vector<double> cb((size_t)n1 * n1, 0.0), ca((size_t)n1 * n1, 0.0), cf((size_t)n1 * n1, 0.0);
+    double mb = 0, ma = 0, mf = 0;
+    for (int it = 1; it <= ntypes; ++it)
+      for (int jt = 1; jt <= ntypes; ++jt) {
+        const size_t ij = (size_t)it * n1 + jt;
+        const bool ei = smartlist && is_eletype[it], ej = smartlist && is_eletype[jt];
+        const bool listed_b = !smartlist || (ei != ej);             // request_smartlist :327-332
+        const bool listed_a = !smartlist || (it == jt && ei);       // :322-325
+        const double cs = cutsq[ij];
+        if (listed_b) { cb[ij] = std::min(cs, cut_coulsq); cf[ij] = cs; }
+        if (listed_a) ca[ij] = std::min(cs, cut_coulsq);
+        mb = std::max(mb, cb[ij]); ma = std::max(ma, ca[ij]); mf = std::max(mf, cf[ij]);
+      }
+    c->d_cuteff_b.upload(cb, c->stream);
+    c->d_cuteff_a.upload(ca, c->stream);
+    c->d_cutsq_listed.upload(cf, c->stream);
+    c->rc_b = std::sqrt(mb);
+    c->rc_a = std::sqrt(ma);
+    // post_force guard eta^2 r^2 < ERFC_MAX (sic), fix_conp.cpp:1418-1419
+    c->rc_f = std::sqrt(std::min(mf, ERFC_MAX / (eta * eta) * (1.0 + 1e-9)));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->have_pair = true;
+  });
+}
+
+int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type, const int *side,
+                        const double *xyz) {
+  return guard(c, [&] {
+    need(c->have_cell && c->have_ewald, "conp_set_electrodes: call conp_set_cell/conp_set_ewald first");
+    if (n_ele < 1 || !type || !side || !xyz) CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: empty electrode");
+    if (n_ele > 65535) CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: n_ele > 65535 not supported");
+    const int N = n_ele;
+    c->N = N;
+    c->h_tag.assign(N, 0);
+    if (tag) c->h_tag.assign(tag, tag + N);
+    c->h_type.assign(type, type + N);
+    c->h_side.assign(side, side + N);
+    c->h_xyz.assign(xyz, xyz + 3 * (size_t)N);
+    for (int i = 0; i < N; ++i) {
+      if (side[i] != 1 && side[i] != -1) CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: side must be +1/-1");
+      if (type[i] < 1 || (c->have_pair && type[i] > c->ntypes))
+        CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: atom type out of range");
+    }
+    // equal contiguous row blocks, multiple of 16 rows so every block start is 128-byte aligned
+    c->rpr = (int)round_up((size_t)(N + c->nranks - 1) / c->nranks, 16);
+    c->r0 = std::min(N, c->rank * c->rpr);
+    c->r1 = std::min(N, c->r0 + c->rpr);
+    c->ncols_pad = (int)round_up(N, 16);
+    c->pitch = c->ncols_pad;
+    c->vlen = std::max((size_t)c->nranks * c->rpr, (size_t)c->ncols_pad) + 16;
+    std::vector<double> hx(N), hy(N), hz(N);
+    for (int i = 0; i < N; ++i) { hx[i] = xyz[3 * i]; hy[i] = xyz[3 * i + 1]; hz[i] = xyz[3 * i + 2]; }
+    cudaStream_t s = c->stream;
+    c->d_ex.upload(hx, s); c->d_ey.upload(hy, s); c->d_ez.upload(hz, s);
+    c->d_exyz.upload(c->h_xyz, s);
+    c->d_etype.upload(c->h_type, s);
+    c->d_eside.upload(c->h_side, s);
+    for (DevBuf<double> *v : {&c->d_b, &c->d_bk, &c->d_breal, &c->d_sb, &c->d_q, &c->d_setq, &c->d_dvec, &c->d_setz,
+                              &c->d_qinit})
+      v->zero(c->vlen, s);
+    // electrode axis tables (used by the A build and by Ewald-mode b extraction)
+    const EwaldHost &e = c->ew;
+    const size_t T = (size_t)e.kxmax + e.kymax + e.kzmax + 3;
+    c->d_etab.reserve(T * N);
+    c->launches += launch_axis_tables(s, N, c->d_ex.p, c->d_ey.p, c->d_ez.p, nullptr, e.unitk, e.kxmax, e.kymax,
+                                      e.kzmax, c->d_etab.p);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    c->have_ele = true;
+    c->have_A = c->inverted = c->have_setq = false;
+  });
+}
+
+int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho_coeff, const double *greensfn,
+                    double shift, double shiftone) {
+  return guard(c, [&] {
+    need(c->have_ele, "conp_pppm_setup: call conp_set_electrodes first");
+    if (order < 1 || order > 7) CONP_THROW(CONP_ERR_ARG, "conp_pppm_setup: PPPM order must be 1..7");
+    for (int a = 0; a < 3; ++a)
+      if (mesh[a] < order) CONP_THROW(CONP_ERR_ARG, "conp_pppm_setup: mesh smaller than the stencil");
+    PPPMGeom &g = c->pg;
+    g.nx = mesh[0]; g.ny = mesh[1]; g.nz = mesh[2]; g.order = order;
+    g.nlower = -((order - 1) / 2);
+    const double prd_slab[3] = {c->prd[0], c->prd[1], c->prd[2] * c->slab_volfactor};
+    for (int a = 0; a < 3; ++a) { g.boxlo[a] = c->boxlo[a]; g.delinv[a] = mesh[a] / prd_slab[a]; }
+    g.delvolinv = g.delinv[0] * g.delinv[1] * g.delinv[2];
+    g.shift = shift; g.shiftone = shiftone;
+    const size_t nx = g.nx, ny = g.ny, nz = g.nz, nxh = nx / 2 + 1;
+    c->ngrid = nx * ny * nz;
+    c->nhalf = nxh * ny * nz;
+    cudaStream_t s = c->stream;
+    c->d_rho.upload(rho_coeff, (size_t)order * order, s);
+    // half-spectrum Green's function, symmetrised and pre-scaled by 1/(nx ny nz):
+    // Re IFFT(G rho^) of the reference's complex transform (pppm_conp.cpp:235-266)
+    // equals the real transform with G_sym(k) = (G(k) + G(-k))/2.
+    std::vector<double> gh(c->nhalf);
+    const double scaleinv = 1.0 / ((double)nx * ny * nz);
+    for (size_t kz = 0; kz < nz; ++kz)
+      for (size_t ky = 0; ky < ny; ++ky)
+        for (size_t kx = 0; kx < nxh; ++kx) {
+          const size_t a = (kz * ny + ky) * nx + kx;
+          const size_t b = (((nz - kz) % nz) * ny + ((ny - ky) % ny)) * nx + ((nx - kx) % nx);
+          gh[(kz * ny + ky) * nxh + kx] = 0.5 * (greensfn[a] + greensfn[b]) * scaleinv;
+        }
+    c->d_ghalf.upload(gh, s);
+    c->d_brick.zero(c->ngrid, s);
+    c->d_ubrick.zero(c->ngrid, s);
+    c->d_ebrick.zero(c->ngrid, s);
+    c->d_work.reserve(c->nhalf);
+    c->d_flag.zero(1, s);
+    if (c->plans) { cufftDestroy(c->plan_f); cufftDestroy(c->plan_b); c->plans = false; }
+    CUFFT_CHECK(cufftPlan3d(&c->plan_f, g.nz, g.ny, g.nx, CUFFT_D2Z));
+    CUFFT_CHECK(cufftPlan3d(&c->plan_b, g.nz, g.ny, g.nx, CUFFT_Z2D));
+    CUFFT_CHECK(cufftSetStream(c->plan_f, s));
+    CUFFT_CHECK(cufftSetStream(c->plan_b, s));
+    c->plans = true;
+    c->d_part2grid.reserve(3 * (size_t)c->N);
+    c->d_weights.reserve(3 * (size_t)c->N * order);
+    c->launches += launch_pppm_ele_stencil(s, g, c->d_rho.p, c->N, c->d_ex.p, c->d_ey.p, c->d_ez.p,
+                                           c->d_part2grid.p, c->d_weights.p);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    c->have_pppm = true;
+  });
+}
+
+int conp_build_A(conp_ctx *c) {
+  return guard(c, [&] {
+    need(c->have_ele && c->have_pair, "conp_build_A: electrodes / pair data missing");
+    cudaStream_t s = c->stream;
+    const int N = c->N, nr = c->r1 - c->r0;
+    const EwaldHost &e = c->ew;
+    CUDA_CHECK(cudaEventRecord(c->ev[14], s));
+    c->d_mat.zero((size_t)std::max(nr, 1) * c->pitch, s);
+
+    // ---- k-space Gram on FP64 tensor cores, chunked over k --------------------
+    const int KC = 4096;  // k-vectors per chunk -> panel of 2*KC k-rows
+    const size_t ld = round_up(N, 128) + 128;
+    DevBuf<double> panel;
+    panel.zero((size_t)2 * KC * ld, s);
+    DevBuf<int2> dsegs;
+    for (int k0 = 0; k0 < e.kcount; k0 += KC) {
+      const int kc_real = std::min(KC, e.kcount - k0);
+      const int kc = (int)round_up(kc_real, 8);  // 2*kc multiple of 16
+      if (kc_real != KC) CUDA_CHECK(cudaMemsetAsync(panel.p, 0, sizeof(double) * 2 * (size_t)kc * ld, s));
+      std::vector<int2> segs;
+      int a = k0;
+      while (a < k0 + kc_real) {
+        int b = a + 1;
+        while (b < k0 + kc_real && e.kx[b] == e.kx[a] && e.ky[b] == e.ky[a] && e.kz[b] == e.kz[b - 1] + 1) ++b;
+        segs.push_back(make_int2(a, b));
+        a = b;
+      }
+      dsegs.upload(segs, s);
+      c->launches += launch_ewald_panel(s, N, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, k0, kc, (int)segs.size(),
+                                        dsegs.p, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, panel.p, ld);
+      c->launches += launch_gram_accumulate(s, nr, N, 2 * kc, panel.p + c->r0, panel.p, ld, c->d_mat.p, c->pitch);
+      CUDA_CHECK(cudaStreamSynchronize(s));  // segs / dsegs reuse
+    }
+    // ---- diagonal, self and slab terms -----------------------------------------
+    const double diag_k = e.ug_tot - 2.0 / MY_PIS * c->g_ewald;  // km_ewald.cpp:632
+    const double self_eta = std::sqrt(2.0) / MY_PIS * c->eta;    // fix_conp.cpp:796-800
+    c->launches += launch_a_finish(s, c->r0, c->r1, N, c->d_mat.p, c->pitch, diag_k, c->pairmode, self_eta,
+                                   c->d_u0.p, c->d_etype.p, slab_pref(c), c->d_ez.p);
+    // ---- real-space electrode-electrode pairs -------------------------------------
+    if (c->rc_a > 0.0) {
+      CellGrid g = make_cell_grid(c->boxlo, c->prd, c->periodic, c->rc_a);
+      c->d_packed.reserve(N);
+      c->d_ptype.reserve(N);
+      CUDA_CHECK(cudaMemsetAsync(c->scal(2), 0, sizeof(double), s));
+      DevBuf<double> zeroq;
+      zeroq.zero(N, s);
+      c->launches += launch_pack_count(s, g, N, c->d_exyz.p, nullptr, zeroq.p, c->d_etype.p, c->d_packed.p,
+                                       c->d_ptype.p, nullptr, nullptr, nullptr, c->scal(2));
+      bin_sorted(c, g, N);
+      c->launches += launch_pair_A(s, g, pair_tables(c, c->d_cuteff_a.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
+                                   c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p,
+                                   c->d_cellstart.p, c->d_mat.p, c->pitch);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev[15], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[14], c->ev[15]));
+    c->build_ms = ms;
+    c->have_A = true;
+    c->inverted = false;
+    c->have_atoms = false;  // shared binning buffers were reused
+  });
+}
+
+int conp_load_matrix(conp_ctx *c, const double *full, int is_inverse) {
+  return guard(c, [&] {
+    need(c->have_ele, "conp_load_matrix: call conp_set_electrodes first");
+    if (!full) CONP_THROW(CONP_ERR_ARG, "Invalid fix conp command (Cannot open A matrix file)");
+    const int N = c->N, nr = c->r1 - c->r0;
+    c->d_mat.zero((size_t)std::max(nr, 1) * c->pitch, c->stream);
+    if (nr > 0)
+      CUDA_CHECK(cudaMemcpy2DAsync(c->d_mat.p, c->pitch * sizeof(double), full + (size_t)c->r0 * N,
+                                   (size_t)N * sizeof(double), (size_t)N * sizeof(double), nr,
+                                   cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->have_A = true;
+    c->inverted = is_inverse != 0;
+  });
+}
+
+int conp_get_matrix(conp_ctx *c, double *rows_out) {
+  return guard(c, [&] {
+    need(c->have_A, "conp_get_matrix: no matrix yet");
+    const int N = c->N, nr = c->r1 - c->r0;
+    if (nr > 0)
+      CUDA_CHECK(cudaMemcpy2DAsync(rows_out, (size_t)N * sizeof(double), c->d_mat.p, c->pitch * sizeof(double),
+                                   (size_t)N * sizeof(double), nr, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int conp_invert_project(conp_ctx *c, int nullneutral, int zneutr, int one_electrode, double *ee_out) {
+  return guard(c, [&] {
+    need(c->have_A, "conp_invert_project: no A matrix (conp_build_A / conp_load_matrix)");
+    cudaStream_t s = c->stream;
+    const int N = c->N, nr = c->r1 - c->r0;
+    c->one_electrode = one_electrode ? 1 : 0;
+    CUDA_CHECK(cudaEventRecord(c->ev[14], s));
+    if (!c->inverted) {
+      // assemble the full matrix on every GPU (the reference replicates it per rank, fix_conp.cpp:816-823)
+      DevBuf<double> F;
+      F.reserve((size_t)N * N);
+      if (nr > 0)
+        CUDA_CHECK(cudaMemcpy2DAsync(F.p + (size_t)c->r0 * N, (size_t)N * sizeof(double), c->d_mat.p,
+                                     c->pitch * sizeof(double), (size_t)N * sizeof(double), nr,
+                                     cudaMemcpyDeviceToDevice, s));
+      if (c->nranks > 1) {
+        std::vector<size_t> bytes(c->nranks), offs(c->nranks);
+        for (int r = 0; r < c->nranks; ++r) {
+          const int a = std::min(N, r * c->rpr), b = std::min(N, a + c->rpr);
+          bytes[r] = (size_t)(b - a) * N * sizeof(double);
+          offs[r] = (size_t)a * N * sizeof(double);
+        }
+        comm_allgatherv(c->comm, F.p + (size_t)c->r0 * N, F.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
+      }
+      // LU + solve against the identity (LAPACK dgetrf_/dgetri_ in the reference, fix_conp.cpp:947-949)
+      cusolverDnParams_t params;
+      CUSOLVER_CHECK(cusolverDnCreateParams(&params));
+      size_t ws_dev = 0, ws_host = 0;
+      CUSOLVER_CHECK(cusolverDnXgetrf_bufferSize(c->solver, params, N, N, CUDA_R_64F, F.p, N, CUDA_R_64F, &ws_dev,
+                                                 &ws_host));
+      DevBuf<unsigned char> wdev;
+      wdev.reserve(std::max<size_t>(ws_dev, 16));
+      std::vector<unsigned char> whost(std::max<size_t>(ws_host, 16));
+      DevBuf<int64_t> ipiv;
+      ipiv.reserve(N);
+      DevBuf<int> dinfo;
+      dinfo.zero(2, s);
+      CUSOLVER_CHECK(cusolverDnXgetrf(c->solver, params, N, N, CUDA_R_64F, F.p, N, ipiv.p, CUDA_R_64F, wdev.p,
+                                      ws_dev, whost.data(), ws_host, dinfo.p));
+      int info[2] = {0, 0};
+      CUDA_CHECK(cudaMemcpyAsync(info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (info[0] != 0) {
+        cusolverDnDestroyParams(params);
+        CONP_THROW(CONP_ERR_NUMERIC, "Inversion failed!");
+      }
+      c->d_fullS.reserve((size_t)N * N);
+      c->launches += launch_pad_identity(s, N, c->d_fullS.p, N);
+      CUSOLVER_CHECK(cusolverDnXgetrs(c->solver, params, CUBLAS_OP_N, N, N, CUDA_R_64F, F.p, N, ipiv.p, CUDA_R_64F,
+                                      c->d_fullS.p, N, dinfo.p + 1));
+      CUDA_CHECK(cudaMemcpyAsync(info + 1, dinfo.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      cusolverDnDestroyParams(params);
+      if (info[1] != 0) CONP_THROW(CONP_ERR_NUMERIC, "Inversion failed!");
+      c->launches += 2;
+      F.release();
+      if (!c->one_electrode) project_full(c, c->d_fullS.p, nullneutral, zneutr);  // fix_conp.cpp:958
+      store_rows_from_full(c, c->d_fullS.p);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (!c->one_electrode) c->d_fullS.release();
+      c->inverted = true;
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev[15], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[14], c->ev[15]));
+    c->invert_ms = ms;
+    if (ee_out) *ee_out = c->ee;
+  });
+}
+
+int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int one_electrode, int nullneutral,
+                          int zneutr, double *totsetq_out) {
+  return guard(c, [&] {
+    need(c->have_A && c->inverted, "conp_set_unit_voltage: matrix not inverted (conp_invert_project)");
+    cudaStream_t s = c->stream;
+    const int N = c->N, nr = c->r1 - c->r0;
+    c->evscale = evscale;
+    c->launches += launch_d_vector(s, N, c->d_ez.p, c->d_eside.p, c->ff_flag, evscale, c->boxlo[2], c->prd[2],
+                                   c->d_dvec.p, c->d_setz.p);
+    // get_setq: elesetq = S.d (fix_conp.cpp:1090-1096)
+    c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_dvec.p, c->d_setq.p + c->r0,
+                               c->num_sms);
+    if (c->nranks > 1) comm_allgather(c->comm, c->d_setq.p + c->r0, c->d_setq.p, sizeof(double) * c->rpr, s);
+    std::vector<double> setq(N), setz(N);
+    CUDA_CHECK(cudaMemcpyAsync(setq.data(), c->d_setq.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(setz.data(), c->d_setz.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    double tot = 0, zOAz = 0;
+    for (int i = 0; i < N; ++i) {
+      if (c->h_side[i] == 1) tot += setq[i];  // :1098-1104
+      zOAz += setq[i] * setz[i];              // fix_cond.cpp:62
+    }
+    c->totsetq = tot;
+    c->dd = -tot;
+    // cond_setup2, fix_cond.cpp:57-68
+    {
+      const double lz = c->prd[2], Axy = c->prd[0] * c->prd[1];
+      double vmult = 4 * MY_PI * zOAz * lz / (evscale * Axy);
+      vmult /= 1 + vmult;
+      vmult /= zOAz;
+      c->vmult = vmult;
+    }
+    c->have_qinit = q_init != nullptr;
+    if (q_init) c->d_qinit.upload(q_init, N, s);
+    if (one_electrode && c->d_fullS.p) {  // fix_conp.cpp:1115
+      project_full(c, c->d_fullS.p, nullneutral, zneutr);
+      store_rows_from_full(c, c->d_fullS.p);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      c->d_fullS.release();
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (totsetq_out) *totsetq_out = tot;
+    c->have_setq = true;
+  });
+}
+
+// ---- per step --------------------------------------------------------------------
+
+int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type, const int *mask, int ele_bits,
+                       const int *counts) {
+  return guard(c, [&] {
+    need(c->have_ele && c->have_pair, "conp_post_neighbor: setup incomplete");
+    if (nlocal < 0 || (nlocal > 0 && (!q || !type))) CONP_THROW(CONP_ERR_ARG, "conp_post_neighbor: bad arrays");
+    (void)counts;
+    cudaStream_t s = c->stream;
+    c->nlocal = nlocal;
+    // charged non-electrode atoms; uncharged ones contribute exact zeros to every
+    // term of b (km_ewald.cpp:686, pppm_conp.cpp:161, fix_conp.cpp:1339)
+    c->h_idx.clear();
+    for (int i = 0; i < nlocal; ++i) {
+      if (mask && (mask[i] & ele_bits)) continue;
+      if (type[i] < 1 || type[i] > c->ntypes) CONP_THROW(CONP_ERR_ARG, "conp_post_neighbor: atom type out of range");
+      if (q[i] != 0.0) c->h_idx.push_back(i);
+    }
+    c->m_local = (int)c->h_idx.size();
+    c->m_counts.assign(c->nranks, 0);
+    c->m_offsets.assign(c->nranks, 0);
+    c->m_counts[c->rank] = c->m_local;
+    if (c->nranks > 1) {
+      DevBuf<double> cnt;
+      cnt.zero(c->nranks, s);
+      const double mine = c->m_local;
+      CUDA_CHECK(cudaMemcpyAsync(cnt.p + c->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
+      comm_allreduce_sum_f64(c->comm, cnt.p, c->nranks, s);
+      std::vector<double> h(c->nranks);
+      CUDA_CHECK(cudaMemcpyAsync(h.data(), cnt.p, sizeof(double) * c->nranks, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (int r = 0; r < c->nranks; ++r) c->m_counts[r] = (int)std::llround(h[r]);
+    }
+    int tot = 0;
+    for (int r = 0; r < c->nranks; ++r) { c->m_offsets[r] = tot; tot += c->m_counts[r]; }
+    c->m_total = tot;
+    c->d_qraw.upload(q, nlocal, s);
+    c->d_typeraw.upload(type, nlocal, s);
+    c->d_idx.upload(c->h_idx, s);
+    c->d_xraw.reserve(3 * (size_t)std::max(nlocal, 1));
+    const size_t m = std::max(tot, 1);
+    c->d_packed.reserve(m); c->d_sorted.reserve(m);
+    c->d_ptype.reserve(m); c->d_stype.reserve(m); c->d_ssrc.reserve(m);
+    c->d_cellof.reserve(m); c->d_slot.reserve(m);
+    c->grid_b = make_cell_grid(c->boxlo, c->prd, c->periodic, c->rc_b > 0 ? c->rc_b : 1.0);
+    c->d_cellcount.zero((size_t)c->grid_b.ncells + 1, s);
+    c->d_cellstart.zero((size_t)c->grid_b.ncells + 1, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    c->have_atoms = true;
+  });
+}
+
+int conp_solve_device(conp_ctx *c, const double *x_device, int kspace_mode, int variant, double value) {
+  return guard(c, [&] { solve_device(c, x_device, kspace_mode, variant, value); });
+}
+
+int conp_get_charges(conp_ctx *c, double *q_ele_out, double *scalar_out) {
+  return guard(c, [&] {
+    need(c->solved, "conp_get_charges: no solve yet");
+    double sc[2] = {0, 0};
+    if (q_ele_out)
+      CUDA_CHECK(cudaMemcpyAsync(q_ele_out, c->d_q.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(sc, c->scal(0), sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+    check_range_flag(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (scalar_out) *scalar_out = sc[0];
+  });
+}
+
+int conp_pre_force(conp_ctx *c, const double *x, int kspace_mode, int variant, double value, double *q_ele_out,
+                   double *scalar_out) {
+  return guard(c, [&] {
+    need(c->have_atoms, "conp_pre_force: conp_post_neighbor not called");
+    if (c->nlocal > 0 && !x) CONP_THROW(CONP_ERR_ARG, "conp_pre_force: x is NULL");
+    if (c->nlocal > 0)
+      CUDA_CHECK(cudaMemcpyAsync(c->d_xraw.p, x, sizeof(double) * 3 * (size_t)c->nlocal, cudaMemcpyHostToDevice,
+                                 c->stream));
+    solve_device(c, c->d_xraw.p, kspace_mode, variant, value);
+    double sc[2] = {0, 0};
+    if (q_ele_out)
+      CUDA_CHECK(cudaMemcpyAsync(q_ele_out, c->d_q.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(sc, c->scal(0), sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+    int flag = 0;
+    if (kspace_mode == CONP_KSPACE_PPPM)
+      CUDA_CHECK(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (flag) CONP_THROW(CONP_ERR_RANGE, "Out of range atoms - cannot compute PPPM");
+    if (scalar_out) *scalar_out = sc[0];
+  });
+}
+
+int conp_get_b(conp_ctx *c, double *b_out, double *b_kspace_out) {
+  return guard(c, [&] {
+    need(c->solved, "conp_get_b: no solve yet");
+    cudaStream_t s = c->stream;
+    if (c->nranks > 1) comm_allgather(c->comm, c->d_bk.p + c->r0, c->d_bk.p, sizeof(double) * c->rpr, s);
+    if (b_out) CUDA_CHECK(cudaMemcpyAsync(b_out, c->d_b.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, s));
+    if (b_kspace_out)
+      CUDA_CHECK(cudaMemcpyAsync(b_kspace_out, c->d_bk.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+int conp_get_density(conp_ctx *c, int which, double *brick_out) {
+  return guard(c, [&] {
+    need(c->have_pppm && c->solved, "conp_get_density: no PPPM solve yet");
+    cudaStream_t s = c->stream;
+    const double *src = nullptr;
+    if (which == 0) src = c->d_brick.p;
+    else if (which == 1) src = c->d_ebrick.p;
+    else if (which == 2) {
+      c->d_tmpbrick.reserve(c->ngrid);
+      c->launches += launch_add_bricks(s, c->ngrid, c->d_brick.p, c->d_ebrick.p, c->d_tmpbrick.p);
+      src = c->d_tmpbrick.p;
+    } else CONP_THROW(CONP_ERR_ARG, "conp_get_density: which must be 0, 1 or 2");
+    CUDA_CHECK(cudaMemcpyAsync(brick_out, src, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+int conp_get_potential_brick(conp_ctx *c, double *brick_out) {
+  return guard(c, [&] {
+    need(c->have_pppm && c->solved, "conp_get_potential_brick: no PPPM solve yet");
+    CUDA_CHECK(cudaMemcpyAsync(brick_out, c->d_ubrick.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost,
+                               c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int conp_post_force(conp_ctx *c, double qqrd2e, double *f_out, double *energies_out) {
+  return guard(c, [&] {
+    need(c->solved, "conp_post_force: no solve yet");
+    cudaStream_t s = c->stream;
+    const int N = c->N;
+    CUDA_CHECK(cudaMemsetAsync(c->scal(4), 0, sizeof(double) * 8, s));
+    c->d_fpacked.zero(3 * (size_t)std::max(c->m_total, 1), s);
+    if (c->rc_f > 0.0 && c->m_total > 0) {
+      CellGrid g = c->grid_b;  // same binning, smaller search radius
+      g.rc = c->rc_f;
+      for (int a = 0; a < 3; ++a) g.smax[a] = g.periodic[a] ? (int)std::ceil(g.rc / g.prd[a]) + 1 : 0;
+      c->launches += launch_pair_postforce(s, g, pair_tables(c, c->d_cuteff_b.p), qqrd2e, c->r0, c->r1, c->d_ex.p,
+                                           c->d_ey.p, c->d_ez.p, c->d_etype.p, c->d_q.p, c->d_sorted.p,
+                                           c->d_stype.p, c->d_ssrc.p, c->d_cellstart.p, c->d_cutsq_listed.p,
+                                           c->d_fpacked.p, c->scal(4));
+    }
+    if (c->nranks > 1) {
+      comm_allreduce_sum_f64(c->comm, c->scal(4), 8, s);
+      if (f_out) comm_allreduce_sum_f64(c->comm, c->d_fpacked.p, 3 * (size_t)c->m_total, s);
+    }
+    std::vector<double> q(N), en(8), fp;
+    CUDA_CHECK(cudaMemcpyAsync(q.data(), c->d_q.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(en.data(), c->scal(4), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    if (f_out && c->m_local > 0) {
+      fp.resize(3 * (size_t)c->m_local);
+      CUDA_CHECK(cudaMemcpyAsync(fp.data(), c->d_fpacked.p + 3 * (size_t)c->m_offsets[c->rank],
+                                 sizeof(double) * fp.size(), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    // self energy, fix_conp.cpp:1166-1199
+    double eself = 0;
+    if (c->pairmode == CONP_PAIR_ETA) {
+      double eleqsqsum = 0;
+      for (int i = 0; i < N; ++i) eleqsqsum += q[i] * q[i];
+      eself = qqrd2e * c->eta * eleqsqsum / (std::sqrt(2.0) * MY_PIS);
+    } else {
+      double u0qsqsum = 0;
+      for (int i = 0; i < N; ++i) u0qsqsum += c->h_u0[c->h_type[i]] * q[i] * q[i];
+      eself = qqrd2e * u0qsqsum;
+    }
+    en[1] = eself;
+    if (energies_out) std::memcpy(energies_out, en.data(), sizeof(double) * 8);
+    if (f_out) {
+      std::memset(f_out, 0, sizeof(double) * 3 * (size_t)c->nlocal);
+      for (int j = 0; j < c->m_local; ++j) {
+        const int i = c->h_idx[j];
+        f_out[3 * (size_t)i] = fp[3 * (size_t)j];
+        f_out[3 * (size_t)i + 1] = fp[3 * (size_t)j + 1];
+        f_out[3 * (size_t)i + 2] = fp[3 * (size_t)j + 2];
+      }
+    }
+  });
+}
+
+// ---- instrumentation -------------------------------------------------------------
+
+void *conp_stream(conp_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int conp_sync(conp_ctx *c) {
+  return guard(c, [&] { CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+}
+
+int conp_timer_record(conp_ctx *c, int slot) {
+  return guard(c, [&] {
+    if (slot < 0 || slot >= 14) CONP_THROW(CONP_ERR_ARG, "timer slot out of range");
+    CUDA_CHECK(cudaEventRecord(c->ev[slot], c->stream));
+  });
+}
+
+int conp_timer_elapsed_ms(conp_ctx *c, int a, int b, float *ms_out) {
+  return guard(c, [&] {
+    if (a < 0 || a >= 14 || b < 0 || b >= 14 || !ms_out) CONP_THROW(CONP_ERR_ARG, "timer slot out of range");
+    CUDA_CHECK(cudaEventSynchronize(c->ev[b]));
+    CUDA_CHECK(cudaEventElapsedTime(ms_out, c->ev[a], c->ev[b]));
+  });
+}
+
+int conp_stage_times(conp_ctx *c, int enable, double *out8) {
+  if (!c) return 0;
+  const int n = c->stage_n;
+  if (out8)
+    for (int i = 0; i < NSTAGE; ++i) out8[i] = n ? c->stage_ms[i] / n : 0.0;
+  c->stage_timing = enable != 0;
+  for (auto &v : c->stage_ms) v = 0;
+  c->stage_n = 0;
+  return n;
+}
+
+int conp_bench_gemv(conp_ctx *c, int reps, float *ms_per_rep_out) {
+  return guard(c, [&] {
+    need(c->have_A, "conp_bench_gemv: no matrix resident");
+    const int nr = c->r1 - c->r0;
+    cudaStream_t s = c->stream;
+    launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms);
+    CUDA_CHECK(cudaEventRecord(c->ev[12], s));
+    for (int r = 0; r < reps; ++r)
+      c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms);
+    CUDA_CHECK(cudaEventRecord(c->ev[13], s));
+    CUDA_CHECK(cudaEventSynchronize(c->ev[13]));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[12], c->ev[13]));
+    if (ms_per_rep_out) *ms_per_rep_out = ms / std::max(reps, 1);
+  });
+}
+
+int conp_bench_dgemm_tflops(conp_ctx *c, int n, double *tflops_out) {
+  return guard(c, [&] {
+    DevBuf<double> A, B, C;
+    A.zero((size_t)n * n, c->stream); B.zero((size_t)n * n, c->stream); C.zero((size_t)n * n, c->stream);
+    const double one = 1.0, zero = 0.0;
+    CUBLAS_CHECK(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, n, n, n, &one, A.p, n, B.p, n, &zero, C.p, n));
+    CUDA_CHECK(cudaEventRecord(c->ev[12], c->stream));
+    const int reps = 3;
+    for (int r = 0; r < reps; ++r)
+      CUBLAS_CHECK(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, n, n, n, &one, A.p, n, B.p, n, &zero, C.p, n));
+    CUDA_CHECK(cudaEventRecord(c->ev[13], c->stream));
+    CUDA_CHECK(cudaEventSynchronize(c->ev[13]));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[12], c->ev[13]));
+    if (tflops_out) *tflops_out = 2.0 * n * (double)n * n * reps / (ms * 1e-3) / 1e12;
+  });
+}
+
+}  // extern "C"

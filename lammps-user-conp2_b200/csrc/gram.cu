@@ -1,0 +1,142 @@
+// k-space part of the A matrix as an FP64 tensor-core Gram contraction:
+//     A_ij += sum_k 2 u_k (cos_ik cos_jk + sin_ik sin_jk)
+// i.e. C += Pr^T . Pa with the k-major panel Pt[2*kc][ld] written by
+// ewald_panel (row k holds sqrt(2 u_k) cos / sin of every electrode atom).
+// Replaces KSpaceModuleEwald::aaa_from_sincos_a / ewald_dot_ij
+// (km_ewald.cpp:560-666), which evaluates the same sum pair by pair.
+//
+// tcgen05 has no FP64 kind; the FP64 tensor path on sm_100a is the DMMA
+// instruction (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  CTA tile 128x128,
+// BK = 16, 8 warps each owning a 64x32 sub-tile (32 DMMA accumulators),
+// 3-stage cp.async pipeline.  Bound: FP64 tensor pipe; flops = 2*nrows*n*kdim.
+#include "common.cuh"
+
+namespace conp {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int LDS_ = BM + 4;  // k-row stride in doubles: 4-double pad => conflict-free fragment loads
+constexpr int STAGES = 3;
+constexpr int THREADS = 256;
+
+struct GramSmem {
+  double a[STAGES][BK][LDS_];
+  double b[STAGES][BK][LDS_];
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// panel_r: k-major panel whose columns are this rank's rows (pointer already
+// offset to row_begin); panel_a: same panel from column 0.  Both are padded
+// with zeros to multiples of the tile, so loads need no bounds checks.
+__global__ void __launch_bounds__(THREADS, 1)
+gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, const double *__restrict__ panel_a,
+            size_t ld, double *__restrict__ Cmat, size_t pitch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GramSmem &sm = *reinterpret_cast<GramSmem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps -> 64 x 32 per warp
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const int nk = kdim / BK;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  auto load_stage = [&](int st, int kt) {
+    // 16 k-rows x 128 doubles per operand = 1024 16-byte chunks per operand
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int chunk = tid + c * THREADS;  // 0..1023
+      const int kr = chunk >> 6;            // 64 chunks per k-row
+      const int col = (chunk & 63) * 2;
+      const size_t goff = (size_t)(kt * BK + kr) * ld;
+      cp_async16(&sm.a[st][kr][col], panel_r + goff + i0 + col);
+      cp_async16(&sm.b[st][kr][col], panel_a + goff + j0 + col);
+    }
+  };
+
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row / k within the quad
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < nk) load_stage(nxt % STAGES, nxt);
+    cp_async_commit();
+    const int st = kt % STAGES;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) af[a] = sm.a[st][k4 * 4 + fk][wm * 64 + a * 8 + fr];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = sm.b[st][k4 * 4 + fk][wn * 32 + b * 8 + fr];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + wm * 64 + a * 8 + fr;
+    if (i >= nrows) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = j0 + wn * 32 + b * 8 + 2 * fk;
+      double *p = Cmat + (size_t)i * pitch + j;
+      if (j + 1 < n) {
+        double2 v = *reinterpret_cast<double2 *>(p);
+        v.x += acc[a][b][0];
+        v.y += acc[a][b][1];
+        *reinterpret_cast<double2 *>(p) = v;
+      } else if (j < n) {
+        p[0] += acc[a][b][0];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
+                           const double *panel_all, size_t ld, double *C, size_t pitch) {
+  if (nrows <= 0 || n <= 0 || kdim <= 0) return 0;
+  if (kdim % BK) CONP_THROW(CONP_ERR_ARG, "gram: kdim must be a multiple of %d", BK);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem)));
+    attr_set = true;
+  }
+  dim3 grid((n + BN - 1) / BN, (nrows + BM - 1) / BM);
+  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, C, pitch);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace conp

@@ -1,0 +1,219 @@
+// PPPM-mode k-space kernels (kspace_style pppm/conp):
+//   pppm_spread       PPPMCONP::elyte_particle_map + elyte_make_rho  pppm_conp.cpp:126-228
+//   pppm_green_mul    PPPMCONP::elyte_poisson (the pointwise part)   pppm_conp.cpp:242-249
+//   pppm_ele_stencil  PPPMCONP::aaa_map_rho                          pppm_conp.cpp:318-344
+//   pppm_gather_b     PPPMCONP::b_cal gather + slab term             pppm_conp.cpp:278-314
+//   pppm_ele_spread   PPPMCONP::ele_make_rho                         pppm_conp.cpp:385-426
+// The mesh is one global periodic brick [nz][ny][nx] (x fastest); periodic
+// wrap of the stencil index replaces LAMMPS' ghost-cell exchange
+// (gc->reverse_comm_kspace / forward_comm_kspace, pppm_conp.cpp:114-123).
+// The FFTs are cuFFT D2Z/Z2D (library); everything else is hand-written.
+#include "common.cuh"
+
+namespace conp {
+
+namespace {
+
+constexpr int OFFSET = 16384;  // pppm_conp.cpp:32
+constexpr int MAXORDER = 7;    // LAMMPS PPPM MAXORDER
+
+__device__ __forceinline__ int wrapi(int m, int n) {
+  m %= n;
+  return m < 0 ? m + n : m;
+}
+
+// LAMMPS PPPM::compute_rho1d for one axis (Horner in rho_coeff, same loop as
+// pppm_conp_intel.cpp:290-301); rc is [order][order] with k shifted by -nlower
+__device__ __forceinline__ double rho1d(const double *__restrict__ rc, int order, int k, double d) {
+  double r = 0.0;
+  for (int l = order - 1; l >= 0; --l) r = rc[l * order + k] + r * d;
+  return r;
+}
+
+// one thread per (atom, z-plane n, y-row m); the thread adds its `order`
+// x-consecutive mesh points with red.global.add.f64
+__global__ void __launch_bounds__(256)
+spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, const PosQ *__restrict__ atoms,
+              double *__restrict__ brick, int *__restrict__ range_flag) {
+  __shared__ double rc[MAXORDER * MAXORDER];
+  const int order = g.order;
+  for (int t = threadIdx.x; t < order * order; t += blockDim.x) rc[t] = rho_coeff[t];
+  __syncthreads();
+  const int per_atom = order * order;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (int)(gid / per_atom);
+  if (j >= m_atoms) return;
+  const int nm = (int)(gid - (long long)j * per_atom);
+  const int n = nm / order, m = nm - n * order;
+  const PosQ p = atoms[j];
+  if (p.q == 0.0) return;  // pppm_conp.cpp:161
+  const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
+  const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
+  const double fz = (p.z - g.boxlo[2]) * g.delinv[2];
+  if (!(fabs(fx) < OFFSET / 2 && fabs(fy) < OFFSET / 2 && fabs(fz) < OFFSET / 2)) {
+    *range_flag = 1;  // "Out of range atoms - cannot compute PPPM", pppm_conp.cpp:167
+    return;
+  }
+  const int nx = (int)(fx + g.shift) - OFFSET;  // :146-148
+  const int ny = (int)(fy + g.shift) - OFFSET;
+  const int nz = (int)(fz + g.shift) - OFFSET;
+  const double dx = nx + g.shiftone - fx;  // :199-201
+  const double dy = ny + g.shiftone - fy;
+  const double dz = nz + g.shiftone - fz;
+  const double z0 = g.delvolinv * p.q;  // :205
+  const double y0 = z0 * rho1d(rc, order, n, dz);
+  const double x0 = y0 * rho1d(rc, order, m, dy);
+  const int mz = wrapi(n + g.nlower + nz, g.nz);
+  const int my = wrapi(m + g.nlower + ny, g.ny);
+  double *row = brick + ((size_t)mz * g.ny + my) * g.nx;
+  int mx = wrapi(g.nlower + nx, g.nx);
+  for (int l = 0; l < order; ++l) {
+    atomicAdd(row + mx, x0 * rho1d(rc, order, l, dx));
+    mx = (mx + 1 == g.nx) ? 0 : mx + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+green_mul_kernel(size_t n, cufftDoubleComplex *__restrict__ work, const double *__restrict__ ghalf) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double gq = ghalf[i];
+  cufftDoubleComplex w = work[i];
+  w.x *= gq;
+  w.y *= gq;
+  work[i] = w;
+}
+
+__global__ void __launch_bounds__(128)
+ele_stencil_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int n_ele, const double *__restrict__ ex,
+                   const double *__restrict__ ey, const double *__restrict__ ez, int *__restrict__ part2grid,
+                   double *__restrict__ weights) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ele) return;
+  const double xs[3] = {ex[i], ey[i], ez[i]};
+  for (int ic = 0; ic < 3; ++ic) {
+    const double xlo = xs[ic] - g.boxlo[ic];
+    const int nn = (int)(xlo * g.delinv[ic] + g.shift) - OFFSET;  // :333
+    part2grid[3 * i + ic] = nn;
+    const double d = nn + g.shiftone - xlo * g.delinv[ic];  // :335
+    for (int l = 0; l < g.order; ++l) weights[((size_t)i * 3 + ic) * g.order + l] = rho1d(rho_coeff, g.order, l, d);
+  }
+}
+
+// one warp per electrode row: b_k = -sum w u (pppm_conp.cpp:285-298), slab
+// term (:301-313), then b = b_k + b_real
+__global__ void __launch_bounds__(256)
+gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ part2grid,
+                const double *__restrict__ weights, const double *__restrict__ u_brick,
+                const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
+                const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= row_end) return;
+  const int order = g.order;
+  const int nx = part2grid[3 * i], ny = part2grid[3 * i + 1], nz = part2grid[3 * i + 2];
+  const double *w = weights + (size_t)i * 3 * order;
+  const int npts = order * order * order;
+  double acc = 0.0;
+  for (int t = lane; t < npts; t += 32) {
+    const int n = t / (order * order);
+    const int r = t - n * order * order;
+    const int m = r / order, l = r - m * order;
+    const int mz = wrapi(n + g.nlower + nz, g.nz);
+    const int my = wrapi(m + g.nlower + ny, g.ny);
+    const int mx = wrapi(l + g.nlower + nx, g.nx);
+    const double x0 = w[2 * order + n] * w[order + m] * w[l];
+    acc = fma(x0, u_brick[((size_t)mz * g.ny + my) * g.nx + mx], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    double bk = -acc;
+    if (slab_pref != 0.0) bk -= ez[i] * (slab_pref * qz_sum[0]);
+    b_kspace[i] = bk;
+    b[i] = bk + b_real[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, const double *__restrict__ weights,
+                  const double *__restrict__ q_ele, double *__restrict__ brick) {
+  const int order = g.order;
+  const int per_atom = order * order;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gid / per_atom);
+  if (i >= n_ele) return;
+  const int nm = (int)(gid - (long long)i * per_atom);
+  const int n = nm / order, m = nm - n * order;
+  const int nx = part2grid[3 * i], ny = part2grid[3 * i + 1], nz = part2grid[3 * i + 2];
+  const double *w = weights + (size_t)i * 3 * order;
+  const double z0 = g.delvolinv * q_ele[i];  // pppm_conp.cpp:411
+  const double x0 = z0 * w[2 * order + n] * w[order + m];
+  const int mz = wrapi(n + g.nlower + nz, g.nz);
+  const int my = wrapi(m + g.nlower + ny, g.ny);
+  double *row = brick + ((size_t)mz * g.ny + my) * g.nx;
+  int mx = wrapi(g.nlower + nx, g.nx);
+  for (int l = 0; l < order; ++l) {
+    atomicAdd(row + mx, x0 * w[l]);
+    mx = (mx + 1 == g.nx) ? 0 : mx + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_bricks_kernel(size_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+}  // namespace
+
+int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m, const PosQ *atoms,
+                       double *brick, int *range_flag) {
+  if (m <= 0) return 0;
+  const long long threads = (long long)m * g.order * g.order;
+  spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, rho_coeff, m, atoms, brick, range_flag);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf) {
+  green_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, work, ghalf);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
+                            const double *ey, const double *ez, int *part2grid, double *weights) {
+  if (n <= 0) return 0;
+  ele_stencil_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, rho_coeff, n, ex, ey, ez, part2grid, weights);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *part2grid,
+                         const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
+                         double slab_pref, const double *b_real, double *b_kspace, double *b) {
+  const int n = row_end - row_begin;
+  if (n <= 0) return 0;
+  gather_b_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, row_begin, row_end, part2grid, weights, u_brick, ez, qz_sum,
+                                              slab_pref, b_real, b_kspace, b);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, const double *weights,
+                           const double *q_ele, double *brick) {
+  if (n <= 0) return 0;
+  const long long threads = (long long)n * g.order * g.order;
+  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, part2grid, weights, q_ele, brick);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out) {
+  add_bricks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, a, b, out);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace conp
