@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- electrode charge updates/sec of the per-step solve (b_cal +
+S.b + epilogue + electrode re-spread) on synthetic graphite capacitors.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload cfg4|cfg5|...] [--kspace pppm|ewald]
+
+One "step" = one `conp_pre_force` (FixConp::pre_force, fix_conp.cpp:543-573)
+for the whole electrode with freshly jittered electrolyte positions.
+Prints ONE JSON line (contract in the task statement):
+  value   device-resident updates/s (inputs already in HBM), CUDA events on the
+          library's stream, max over ranks
+  e2e     the same through the host-pointer C-ABI call, H2D of positions and D2H
+          of charges inside the timed region
+  roofline      GEMV launch (dominant kernel): algorithmic bytes / event time
+  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded
+                sample of the same workload, all host cores
+`--impl reference` times only that CPU port (the reference needs LAMMPS, which
+is not available) and never touches the CUDA library.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "lammps-user-conp2_b200"))
+
+from conp_b200 import MockLammps, make_workload  # noqa: E402
+from conp_b200.mockhost import mesh_for_spacing  # noqa: E402
+from conp_b200.system import WORKLOADS  # noqa: E402
+
+METRIC = "electrode charge updates/sec"
+UNIT = "updates/s"
+G_EWALD, CUT, ETA, DV, ACC, MESH_H, SLAB = 0.26, 12.0, 1.979, 2.0, 1e-4, 1.0, 3.0
+JITTER = 0.05
+NSETS = 8
+
+
+def describe(name):
+    w = WORKLOADS[name]
+    n_ele = 2 * w["nlayers"] * 4 * w["ncx"] * w["ncy"]
+    return (f"{name}: synthetic graphite capacitor, {n_ele} electrode atoms / {w['n_elyte']} electrolyte charges, "
+            f"conp, slab {SLAB}, g_ewald {G_EWALD}, cut {CUT} A, PPPM order 5 mesh<= {MESH_H} A, Nevery=1")
+
+
+def make_case(name, kspace):
+    s = make_workload(name)
+    lmp = MockLammps(s, "p p f")
+    lmp.pair_style_coul_long(CUT)
+    mesh = mesh_for_spacing(s.prd, SLAB, MESH_H) if kspace == "pppm" else None
+    lmp.kspace("pppm/conp" if kspace == "pppm" else "pppm", ACC, G_EWALD, slab=SLAB, mesh=mesh)
+    lmp.group_molecule("eleleft", 1)
+    lmp.group_molecule("eleright", 2)
+    arg = f"e eleleft conp 1 eleright {ETA} {DV} log_conp etypes 1 3".split() + (["pppm"] if kspace == "pppm" else [])
+    return lmp, arg
+
+
+def jitter_sets(x, nsets, seed):
+    rng = np.random.default_rng(seed)
+    return [x + rng.normal(0.0, JITTER, x.shape) for _ in range(nsets)]
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_updates_per_s(lmp, arg, S, budget_s, kspace):
+    """Times the CPU oracle's per-step path (b_cal + matvec + epilogue [+ electrode
+    re-spread]) on jittered positions; returns (updates/s, n_updates, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import conp_oracle as O
+    cores = os.cpu_count() or 1
+    O.lib().orc_set_num_threads(cores)
+    fix = O.OracleFixConp(lmp, arg, fft_workers=cores)
+    fix.setup_preinverted(S)
+    x0 = lmp.system.x[fix.oth_idx].copy()
+    sets = jitter_sets(x0, 3, 99)
+    lmp.system.x[fix.oth_idx] = sets[0]
+    fix.pre_force()  # warm-up (FFT plans, page faults)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        lmp.system.x[fix.oth_idx] = sets[(n + 1) % 3]
+        fix.pre_force()
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 50:
+            break
+    return n / el, n, cores
+
+
+def run_reference(args, rank, world):
+    """Reference arm: CPU port of the reference's per-step path, all host cores."""
+    if rank != 0:
+        return
+    name = args.workload or ("cfg4" if world == 1 else "cfg5")
+    lmp, arg = make_case(name, args.kspace)
+    n_ele = int((lmp.system.mol > 0).sum())
+    rng = np.random.default_rng(1234)
+    # S only feeds the O(N^2) matvec, whose cost does not depend on its values; the
+    # true S needs the O(N^2 K) A build, which no CPU finishes in minutes at this size.
+    S = rng.standard_normal((n_ele, n_ele)) * 1e-3
+    S = 0.5 * (S + S.T)
+    S -= S.mean(axis=1, keepdims=True)
+    per_step_budget = 8.0
+    ups, n, cores = cpu_port_updates_per_s(lmp, arg, S, per_step_budget * max(1, min(args.steps, 3)), args.kspace)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / ups, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": describe(name), "kspace": args.kspace},
+        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} full updates of the same workload (random symmetric S, true b path)"},
+        "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm (oracle/), not the reference binary: LAMMPS is not available",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--kspace", default="pppm", choices=["pppm", "ewald"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast-setup", action="store_true",
+                    help="PROFILING ONLY: load a random S instead of building/inverting A (line is marked invalid)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from conp_b200 import abi
+    from conp_b200.fix_conp import make_fix
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(abi.CONP_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(abi.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    name = args.workload or ("cfg4" if world == 1 else "cfg5")
+    lmp, arg = make_case(name, args.kspace)
+    t0 = time.perf_counter()
+    fix = make_fix(lmp, arg, device=local_rank, rank=rank, nranks=world, unique_id=uid)
+    if args.fast_setup:
+        fix.setup_post_neighbor()
+        n_ele = fix.N
+        rng = np.random.default_rng(1234)
+        Sr = rng.standard_normal((n_ele, n_ele)) * 1e-3
+        Sr -= Sr.mean(axis=1, keepdims=True)
+        fix.ctx.load_matrix(Sr, True)
+        del Sr
+        fix.totsetq = fix.ctx.set_unit_voltage(fix.evscale)
+        fix.runstage = 3
+        fix.post_neighbor()
+    else:
+        fix.setup()
+    setup_s = time.perf_counter() - t0
+    ctx = fix.ctx
+    info = ctx.info()
+    kmode = fix.kspace_mode
+    N, M = fix.N, info.n_elyte
+    nlocal = len(fix.owned)
+
+    # jittered position sets: pinned host copies (e2e leg) and device copies (resident leg)
+    sets = jitter_sets(lmp.system.x[fix.owned], NSETS, 20261018 + rank)
+    host_sets = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in sets]
+    dev_sets = [h.cuda() for h in host_sets]
+    q_host = torch.zeros(N, dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg -------------------------------------------------
+    for k in range(args.warmup):
+        ctx.solve_device(dev_sets[k % NSETS].data_ptr(), kmode, 0, DV)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.info().launches
+    ctx.timer_record(0)
+    for k in range(args.steps):
+        ctx.solve_device(dev_sets[k % NSETS].data_ptr(), kmode, 0, DV)
+    ctx.timer_record(1)
+    barrier()
+    ms_total = max_over_ranks(ctx.timer_elapsed_ms(0, 1))
+    launches = int(ctx.info().launches - l0)
+    clocks = sampler.stop() if sampler else None
+    q_dev, _ = ctx.get_charges()
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    # ---- end-to-end leg through the host-pointer ABI call ---------------------
+    for k in range(max(3, args.warmup // 4)):
+        ctx.pre_force_into(host_sets[k % NSETS].data_ptr(), kmode, 0, DV, q_host.data_ptr())
+    barrier()
+    ctx.timer_record(2)
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        ctx.pre_force_into(host_sets[k % NSETS].data_ptr(), kmode, 0, DV, q_host.data_ptr())
+    ctx.timer_record(3)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    e2e_ms = max_over_ranks(max(ctx.timer_elapsed_ms(2, 3), wall_ms)) / args.steps
+    assert args.fast_setup or abs(float(q_host.sum())) < 1e-9, "electroneutrality violated"
+
+    # ---- per-stage event timing inside the pipeline (roofline of the GEMV) -------
+    ctx.stage_times(True)
+    nst = min(args.steps, 50)
+    for k in range(nst):
+        ctx.solve_device(dev_sets[k % NSETS].data_ptr(), kmode, 0, DV)
+    _, st = ctx.stage_times(False)
+    gemv_alone_ms = ctx.bench_gemv(20)
+    stage_names = ["pack", "bin", "pair", "kspace", "gather", "exchange_b", "gemv", "epilogue"]
+    gemv_ms = max_over_ranks(float(st[6]))
+    nrows = info.row_end - info.row_begin
+    gemv_bytes = 8.0 * nrows * N + 8.0 * N + 8.0 * nrows
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
+    G = int(np.prod(lmp.mesh)) if lmp.mesh else 0
+    order = lmp.order
+    b_update = (8.0 * nrows * N + 8.0 * N + 16.0 * nrows + 32.0 * M
+                + ((24.0 * G + 24.0 * order * nrows) if kmode == 1 else
+                   (16.0 * info.kcount + 16.0 * info.kcount_flat * nrows)))
+    roofline = {"bound": "hbm", "kernel": "gemv_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": gemv_bytes, "launch_ms_in_pipeline": gemv_ms, "launch_ms_alone": gemv_alone_ms,
+                "update_bytes": b_update, "update_achieved_gbs": b_update / (ms_step * 1e-3) / 1e9,
+                "update_frac": b_update / (ms_step * 1e-3) / 1e9 / peak,
+                "stage_ms": {n_: float(v) for n_, v in zip(stage_names, st)}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": describe(name), "kspace": args.kspace, "mesh": list(lmp.mesh) if lmp.mesh else None,
+                   "kcount_A": info.kcount, "parallelism": f"S rows sharded x{world}, electrolyte chunks x{world}",
+                   "l2_policy": f"inputs larger than L2 (S row block {8.0*nrows*N/1e6:.0f} MB streamed every step; "
+                                f"{NSETS} jittered position sets, sigma {JITTER} A)"},
+        "electrode_atom_updates_per_s": value * N,
+        "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(nlocal * 24), "d2h_bytes_per_step": int(N * 8 + 16)},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "clocks": clocks,
+        "setup": {"total_s": setup_s, "build_A_ms": info.setup_build_ms, "invert_project_ms": info.setup_invert_ms,
+                  "gram_flops": 4.0 * nrows * N * info.kcount,
+                  "gram_tflops": 4.0 * nrows * N * info.kcount / max(info.setup_build_ms, 1e-9) / 1e9},
+    }
+
+    if args.fast_setup:
+        line["INVALID"] = "fast-setup profiling run: S is random, not a bench value"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.fast_setup:
+        S = ctx.get_matrix()
+        lmp2, arg2 = make_case(name, args.kspace)
+        ups, n, cores = cpu_port_updates_per_s(lmp2, arg2, S, args.cpu_budget, args.kspace)
+        line["cpu_baseline"] = {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n} full updates of the same workload with the GPU-built S"}
+        # parity spot check on the last jitter set used by the sampler
+        del S
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    fix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -359,6 +359,35 @@ class OracleFixConp:
         self.runstage = 3
         self.S = self.aaa_all
 
+    def setup_preinverted(self, S):
+        """Setup with an already inverted+projected matrix (the `inv <file>`
+        path, a_matrix_f == 2, fix_conp.cpp:442-445, 935): used by bench.py to
+        time the per-step path at sizes where the O(N^2 K) A build is out of
+        reach for a CPU."""
+        lmp, a, L = self.lmp, self.args, self.L
+        s = lmp.system
+        N = self.N
+        self.g_ewald = lmp.g_ewald
+        xele, _ = self._ele()
+        if a.pppmflag:
+            self._pppm_setup()
+            self.ewald = None
+        else:
+            self.ewald = OracleEwald(lmp.g_ewald, lmp.accuracy, lmp.q2(), s.natoms, s.prd, lmp.slabflag,
+                                     lmp.slab_volfactor, a.lowmemflag)
+            self.ewald.a_read(xele)
+        self.aaa_all = self.S = np.ascontiguousarray(S, dtype=np.float64)
+        d = np.zeros(N)
+        L.orc_b_setq_cal(N, dp(xele), ip(self.side), int(a.ff_flag), self.evscale, float(s.boxlo[2]),
+                         float(s.prd[2]), dp(d))
+        self.d = d
+        self.setzvec = d / self.evscale
+        self.elesetq = np.zeros(N)
+        L.orc_matvec(N, dp(self.S), dp(d), dp(self.elesetq))
+        self.totsetq = L.orc_totsetq(N, dp(self.elesetq), ip(self.side))
+        self.vmult = None
+        self.runstage = 3
+
     def _inv_project(self):
         s = self.lmp.system
         zhalf = 0.5 * s.prd[2] + s.boxlo[2]
