@@ -158,6 +158,10 @@ struct EwaldHost {
 struct PPPMGeom {
   int nx, ny, nz, order, nlower;
   double boxlo[3], delinv[3], delvolinv, shift, shiftone;
+  // plane pruning (pppm.cu): compact input planes zi <-> (zin_lo + zi) mod nz, zi < nzi;
+  // compact output planes zmap[mz] (device array of nz ints, -1 if the plane is not needed)
+  int nzi, zin_lo, nzo;
+  const int *zmap;
 };
 
 // ---------------------------------------------------------------------------
@@ -215,6 +219,11 @@ int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &p
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m, const PosQ *atoms,
                        double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
+                      const cufftDoubleComplex *rhat, const double *Kr, const cufftDoubleComplex *Kc,
+                      cufftDoubleComplex *uhat);
+int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
+                         const double *compact, double *full);
 int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
                             const double *ey, const double *ez, int *part2grid, double *weights);
 int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *part2grid,

@@ -77,12 +77,14 @@ struct conp_ctx {
 
   // pppm ---------------------------------------------------------------------------
   PPPMGeom pg;
-  size_t ngrid = 0, nhalf = 0;
-  DevBuf<double> d_rho, d_ghalf, d_brick, d_ubrick, d_ebrick, d_weights, d_tmpbrick;
-  DevBuf<int> d_part2grid, d_flag;
-  DevBuf<cufftDoubleComplex> d_work;
+  size_t ngrid = 0, nhalf = 0, plane = 0, ncol = 0;
+  std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
+  std::vector<int> h_zout;              // output planes (sorted)
+  DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
+  DevBuf<int> d_part2grid, d_flag, d_zmap, d_zout;
+  DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
-  bool plans = false;
+  bool plans = false, k_real = true;
 
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
@@ -219,12 +221,13 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
   // ---- k-space part of b --------------------------------------------------------
   const double spref = slab_pref(c);
   if (kspace_mode == CONP_KSPACE_PPPM) {
-    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * c->ngrid, s));
+    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)c->pg.nzi * c->plane, s));
     CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
     c->launches += launch_pppm_spread(s, c->pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_brick.p, c->d_flag.p);
-    CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_work.p));
-    c->launches += launch_pppm_green_mul(s, c->nhalf, c->d_work.p, c->d_ghalf.p);
-    CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_work.p, c->d_ubrick.p));
+    CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
+    c->launches += launch_pppm_zconv(s, (int)c->ncol, c->pg.nz, c->pg.nzi, c->pg.zin_lo, c->pg.nzo, c->d_zout.p,
+                                     c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p);
+    CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
     c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_part2grid.p, c->d_weights.p, c->d_ubrick.p,
@@ -257,7 +260,7 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
                                       c->totsetq, value, c->one_electrode, c->scal(2), c->prd[2], c->vmult,
                                       c->d_q.p, c->scal(0));
   if (kspace_mode == CONP_KSPACE_PPPM) {  // kspmod->update_charge() -> ele_make_rho
-    CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * c->ngrid, s));
+    CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, s));
     c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_part2grid.p, c->d_weights.p, c->d_q.p,
                                           c->d_ebrick.p);
   }
@@ -556,12 +559,16 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     const size_t nx = g.nx, ny = g.ny, nz = g.nz, nxh = nx / 2 + 1;
     c->ngrid = nx * ny * nz;
     c->nhalf = nxh * ny * nz;
+    c->plane = nx * ny;
+    c->ncol = nxh * ny;
+    const size_t ncol = c->ncol;
     cudaStream_t s = c->stream;
     c->d_rho.upload(rho_coeff, (size_t)order * order, s);
     // half-spectrum Green's function, symmetrised and pre-scaled by 1/(nx ny nz):
     // Re IFFT(G rho^) of the reference's complex transform (pppm_conp.cpp:235-266)
     // equals the real transform with G_sym(k) = (G(k) + G(-k))/2.
-    std::vector<double> gh(c->nhalf);
+    std::vector<double> &gh = c->h_ghalf;
+    gh.resize(c->nhalf);
     const double scaleinv = 1.0 / ((double)nx * ny * nz);
     for (size_t kz = 0; kz < nz; ++kz)
       for (size_t ky = 0; ky < ny; ++ky)
@@ -570,22 +577,79 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
           const size_t b = (((nz - kz) % nz) * ny + ((ny - ky) % ny)) * nx + ((nx - kx) % nx);
           gh[(kz * ny + ky) * nxh + kx] = 0.5 * (greensfn[a] + greensfn[b]) * scaleinv;
         }
-    c->d_ghalf.upload(gh, s);
-    c->d_brick.zero(c->ngrid, s);
-    c->d_ubrick.zero(c->ngrid, s);
-    c->d_ebrick.zero(c->ngrid, s);
-    c->d_work.reserve(c->nhalf);
-    c->d_flag.zero(1, s);
-    if (c->plans) { cufftDestroy(c->plan_f); cufftDestroy(c->plan_b); c->plans = false; }
-    CUFFT_CHECK(cufftPlan3d(&c->plan_f, g.nz, g.ny, g.nx, CUFFT_D2Z));
-    CUFFT_CHECK(cufftPlan3d(&c->plan_b, g.nz, g.ny, g.nx, CUFFT_Z2D));
-    CUFFT_CHECK(cufftSetStream(c->plan_f, s));
-    CUFFT_CHECK(cufftSetStream(c->plan_b, s));
-    c->plans = true;
+    // ---- cached electrode stencils and the output planes they touch ----------
     c->d_part2grid.reserve(3 * (size_t)c->N);
     c->d_weights.reserve(3 * (size_t)c->N * order);
     c->launches += launch_pppm_ele_stencil(s, g, c->d_rho.p, c->N, c->d_ex.p, c->d_ey.p, c->d_ez.p,
                                            c->d_part2grid.p, c->d_weights.p);
+    std::vector<int> p2g(3 * (size_t)c->N);
+    CUDA_CHECK(cudaMemcpyAsync(p2g.data(), c->d_part2grid.p, sizeof(int) * p2g.size(), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<int> zmap(nz, -1);
+    for (int i = 0; i < c->N; ++i)
+      for (int n = 0; n < order; ++n) {
+        int mz = (p2g[3 * (size_t)i + 2] + g.nlower + n) % (int)nz;
+        if (mz < 0) mz += (int)nz;
+        zmap[mz] = 0;
+      }
+    c->h_zout.clear();
+    for (int mz = 0; mz < (int)nz; ++mz)
+      if (zmap[mz] == 0) { zmap[mz] = (int)c->h_zout.size(); c->h_zout.push_back(mz); }
+    g.nzo = (int)c->h_zout.size();
+    c->d_zmap.upload(zmap, s);
+    c->d_zout.upload(c->h_zout, s);
+    g.zmap = c->d_zmap.p;
+    // ---- input planes: what the box can reach (all of them if z is periodic) ----
+    if (c->periodic[2]) {
+      g.zin_lo = 0;
+      g.nzi = (int)nz;
+    } else {
+      const int base_hi = (int)(c->prd[2] * g.delinv[2] + shift) - 16384;
+      const int lo = g.nlower - 2, hi = base_hi + order / 2 + 2;
+      g.zin_lo = lo;
+      g.nzi = hi - lo + 1;
+      if (g.nzi >= (int)nz) { g.zin_lo = 0; g.nzi = (int)nz; }
+    }
+    // ---- z-convolution kernel table K[col][d] = sum_kz gh[kz][col] exp(+2 pi i kz d / nz) ----
+    {
+      std::vector<cufftDoubleComplex> gc(c->nhalf);
+      for (size_t i = 0; i < c->nhalf; ++i) { gc[i].x = gh[i]; gc[i].y = 0.0; }
+      DevBuf<cufftDoubleComplex> dgc;
+      dgc.upload(gc, s);
+      c->d_Kc.reserve(c->nhalf);
+      cufftHandle p1;
+      int n1[1] = {(int)nz};
+      CUFFT_CHECK(cufftPlanMany(&p1, 1, n1, n1, (int)ncol, 1, n1, 1, (int)nz, CUFFT_Z2Z, (int)ncol));
+      CUFFT_CHECK(cufftSetStream(p1, s));
+      CUFFT_CHECK(cufftExecZ2Z(p1, dgc.p, c->d_Kc.p, CUFFT_INVERSE));
+      CUDA_CHECK(cudaMemcpyAsync(gc.data(), c->d_Kc.p, sizeof(cufftDoubleComplex) * c->nhalf, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      cufftDestroy(p1);
+      double mre = 0, mim = 0;
+      for (size_t i = 0; i < c->nhalf; ++i) { mre = std::max(mre, std::fabs(gc[i].x)); mim = std::max(mim, std::fabs(gc[i].y)); }
+      c->k_real = mim <= 1e-14 * mre;
+      if (c->k_real) {
+        std::vector<double> kr(c->nhalf);
+        for (size_t i = 0; i < c->nhalf; ++i) kr[i] = gc[i].x;
+        c->d_Kr.upload(kr, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        c->d_Kc.release();
+      }
+    }
+    // ---- compact bricks and batched 2-D plans -------------------------------------
+    c->d_brick.zero((size_t)g.nzi * c->plane, s);
+    c->d_ubrick.zero((size_t)g.nzo * c->plane, s);
+    c->d_ebrick.zero((size_t)g.nzo * c->plane, s);
+    c->d_rhat.reserve((size_t)g.nzi * ncol);
+    c->d_uhat.reserve((size_t)g.nzo * ncol);
+    c->d_flag.zero(1, s);
+    if (c->plans) { cufftDestroy(c->plan_f); cufftDestroy(c->plan_b); c->plans = false; }
+    int n2[2] = {g.ny, g.nx}, er[2] = {g.ny, g.nx}, ec[2] = {g.ny, (int)nxh};
+    CUFFT_CHECK(cufftPlanMany(&c->plan_f, 2, n2, er, 1, (int)c->plane, ec, 1, (int)ncol, CUFFT_D2Z, g.nzi));
+    CUFFT_CHECK(cufftPlanMany(&c->plan_b, 2, n2, ec, 1, (int)ncol, er, 1, (int)c->plane, CUFFT_Z2D, g.nzo));
+    CUFFT_CHECK(cufftSetStream(c->plan_f, s));
+    CUFFT_CHECK(cufftSetStream(c->plan_b, s));
+    c->plans = true;
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->have_pppm = true;
   });
@@ -906,16 +970,23 @@ int conp_get_b(conp_ctx *c, double *b_out, double *b_kspace_out) {
 int conp_get_density(conp_ctx *c, int which, double *brick_out) {
   return guard(c, [&] {
     need(c->have_pppm && c->solved, "conp_get_density: no PPPM solve yet");
+    if (which < 0 || which > 2) CONP_THROW(CONP_ERR_ARG, "conp_get_density: which must be 0, 1 or 2");
     cudaStream_t s = c->stream;
-    const double *src = nullptr;
-    if (which == 0) src = c->d_brick.p;
-    else if (which == 1) src = c->d_ebrick.p;
-    else if (which == 2) {
-      c->d_tmpbrick.reserve(c->ngrid);
-      c->launches += launch_add_bricks(s, c->ngrid, c->d_brick.p, c->d_ebrick.p, c->d_tmpbrick.p);
-      src = c->d_tmpbrick.p;
-    } else CONP_THROW(CONP_ERR_ARG, "conp_get_density: which must be 0, 1 or 2");
-    CUDA_CHECK(cudaMemcpyAsync(brick_out, src, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, s));
+    const PPPMGeom &g = c->pg;
+    // the solver keeps only the planes that can be non-zero; expand to the full mesh here
+    DevBuf<double> full;
+    full.zero(c->ngrid, s);
+    if (which == 0 || which == 2)
+      c->launches += launch_expand_planes(s, c->plane, g.nzi, g.nz, g.zin_lo, nullptr, c->d_brick.p, full.p);
+    if (which == 1) c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, full.p);
+    if (which == 2) {
+      DevBuf<double> fe;
+      fe.zero(c->ngrid, s);
+      c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, fe.p);
+      c->launches += launch_add_bricks(s, c->ngrid, full.p, fe.p, full.p);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(brick_out, full.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
   });
 }
@@ -923,9 +994,28 @@ int conp_get_density(conp_ctx *c, int which, double *brick_out) {
 int conp_get_potential_brick(conp_ctx *c, double *brick_out) {
   return guard(c, [&] {
     need(c->have_pppm && c->solved, "conp_get_potential_brick: no PPPM solve yet");
-    CUDA_CHECK(cudaMemcpyAsync(brick_out, c->d_ubrick.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost,
-                               c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    // full-mesh potential on demand (the per-step path only evaluates the electrode planes):
+    // the reference's 3-D transform, pppm_conp.cpp:230-267
+    cudaStream_t s = c->stream;
+    const PPPMGeom &g = c->pg;
+    DevBuf<double> full, gd;
+    DevBuf<cufftDoubleComplex> work;
+    full.zero(c->ngrid, s);
+    work.reserve(c->nhalf);
+    gd.upload(c->h_ghalf, s);
+    c->launches += launch_expand_planes(s, c->plane, g.nzi, g.nz, g.zin_lo, nullptr, c->d_brick.p, full.p);
+    cufftHandle pf, pb;
+    CUFFT_CHECK(cufftPlan3d(&pf, g.nz, g.ny, g.nx, CUFFT_D2Z));
+    CUFFT_CHECK(cufftPlan3d(&pb, g.nz, g.ny, g.nx, CUFFT_Z2D));
+    CUFFT_CHECK(cufftSetStream(pf, s));
+    CUFFT_CHECK(cufftSetStream(pb, s));
+    CUFFT_CHECK(cufftExecD2Z(pf, full.p, work.p));
+    c->launches += launch_pppm_green_mul(s, c->nhalf, work.p, gd.p);
+    CUFFT_CHECK(cufftExecZ2D(pb, work.p, full.p));
+    CUDA_CHECK(cudaMemcpyAsync(brick_out, full.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cufftDestroy(pf);
+    cufftDestroy(pb);
   });
 }
 

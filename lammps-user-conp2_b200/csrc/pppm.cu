@@ -4,10 +4,25 @@
 //   pppm_ele_stencil  PPPMCONP::aaa_map_rho                          pppm_conp.cpp:318-344
 //   pppm_gather_b     PPPMCONP::b_cal gather + slab term             pppm_conp.cpp:278-314
 //   pppm_ele_spread   PPPMCONP::ele_make_rho                         pppm_conp.cpp:385-426
+//   pppm_zconv        PPPMCONP::elyte_poisson along z                pppm_conp.cpp:230-267
 // The mesh is one global periodic brick [nz][ny][nx] (x fastest); periodic
 // wrap of the stencil index replaces LAMMPS' ghost-cell exchange
 // (gc->reverse_comm_kspace / forward_comm_kspace, pppm_conp.cpp:114-123).
-// The FFTs are cuFFT D2Z/Z2D (library); everything else is hand-written.
+//
+// Plane pruning.  The reference transforms the whole mesh (3-D FFT, multiply
+// by greensfn, inverse 3-D FFT).  Here only the z-planes that can hold charge
+// ("input planes": the box plus the stencil reach; in slab geometry 1/slab of
+// the mesh) are transformed in (x,y), and the potential is produced only on
+// the planes the cached electrode stencils read ("output planes", static).
+// Along z the FFT -> greensfn -> inverse FFT chain is applied exactly as the
+// circular convolution it is:
+//     u^(kx,ky;zo) = sum_zi K(kx,ky;(zo-zi) mod nz) rho^(kx,ky;zi),
+//     K(kx,ky;d)   = sum_kz greensfn(kx,ky,kz)/(nx ny nz) exp(+2 pi i kz d/nz)
+// (K is tabulated once at setup).  The result equals the full transform up to
+// rounding; zero planes contribute exact zeros.  Bricks are stored compactly:
+// density [nzi][ny][nx] with plane zi <-> (zin_lo + zi) mod nz, potential and
+// electrode density [nzo][ny][nx] with plane index zmap[mz].
+// The 2-D FFTs are cuFFT (library); everything else is hand-written.
 #include "common.cuh"
 
 namespace conp {
@@ -63,14 +78,89 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
   const double z0 = g.delvolinv * p.q;  // :205
   const double y0 = z0 * rho1d(rc, order, n, dz);
   const double x0 = y0 * rho1d(rc, order, m, dy);
-  const int mz = wrapi(n + g.nlower + nz, g.nz);
+  const int zi = wrapi(n + g.nlower + nz - g.zin_lo, g.nz);  // compact input plane
+  if (zi >= g.nzi) {
+    *range_flag = 1;  // outside the planes the box can reach: "Out of range atoms"
+    return;
+  }
   const int my = wrapi(m + g.nlower + ny, g.ny);
-  double *row = brick + ((size_t)mz * g.ny + my) * g.nx;
+  double *row = brick + ((size_t)zi * g.ny + my) * g.nx;
   int mx = wrapi(g.nlower + nx, g.nx);
   for (int l = 0; l < order; ++l) {
     atomicAdd(row + mx, x0 * rho1d(rc, order, l, dx));
     mx = (mx + 1 == g.nx) ? 0 : mx + 1;
   }
+}
+
+// z-convolution with the tabulated kernel.  Block = ZC_COLS consecutive
+// (kx,ky) columns (128 B of the plane-major spectra), one warp per column,
+// lanes = output planes.  rho^ of the block is staged in shared memory.
+constexpr int ZC_COLS = 8;
+
+template <bool REALK>
+__global__ void __launch_bounds__(ZC_COLS * 32)
+zconv_kernel(int ncol, int nz, int nzi, int zin_lo, int nzo, const int *__restrict__ zout_list,
+             const double2 *__restrict__ rhat, const double *__restrict__ Kr, const double2 *__restrict__ Kc,
+             double2 *__restrict__ uhat) {
+  extern __shared__ __align__(16) unsigned char zc_smem[];
+  double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzi][ZC_COLS]
+  const int c0 = blockIdx.x * ZC_COLS;
+  for (int idx = threadIdx.x; idx < nzi * ZC_COLS; idx += blockDim.x) {
+    const int zi = idx / ZC_COLS, cc = idx - zi * ZC_COLS;
+    const int c = c0 + cc;
+    rh[idx] = (c < ncol) ? rhat[(size_t)zi * ncol + c] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = c0 + w;
+  if (c >= ncol) return;
+  for (int zo = lane; zo < nzo; zo += 32) {
+    // d = (zout - (zin_lo + zi)) mod nz, walked downwards with zi
+    int d = (zout_list[zo] - zin_lo) % nz;
+    if (d < 0) d += nz;
+    double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+    if (REALK) {
+      const double *krow = Kr + (size_t)c * nz;
+      int zi = 0;
+      for (; zi + 1 < nzi; zi += 2) {
+        const double k0 = __ldg(krow + d);
+        d = d ? d - 1 : nz - 1;
+        const double k1 = __ldg(krow + d);
+        d = d ? d - 1 : nz - 1;
+        const double2 r0 = rh[zi * ZC_COLS + w], r1 = rh[(zi + 1) * ZC_COLS + w];
+        ar0 = fma(k0, r0.x, ar0); ai0 = fma(k0, r0.y, ai0);
+        ar1 = fma(k1, r1.x, ar1); ai1 = fma(k1, r1.y, ai1);
+      }
+      if (zi < nzi) {
+        const double k0 = __ldg(krow + d);
+        const double2 r0 = rh[zi * ZC_COLS + w];
+        ar0 = fma(k0, r0.x, ar0); ai0 = fma(k0, r0.y, ai0);
+      }
+    } else {
+      const double2 *krow = Kc + (size_t)c * nz;
+      for (int zi = 0; zi < nzi; ++zi) {
+        const double2 k = krow[d];
+        d = d ? d - 1 : nz - 1;
+        const double2 r = rh[zi * ZC_COLS + w];
+        ar0 = fma(k.x, r.x, ar0); ar0 = fma(-k.y, r.y, ar0);
+        ai0 = fma(k.x, r.y, ai0); ai0 = fma(k.y, r.x, ai0);
+      }
+    }
+    uhat[(size_t)zo * ncol + c] = make_double2(ar0 + ar1, ai0 + ai1);
+  }
+}
+
+// compact <-> full brick copies for the on-demand outputs
+__global__ void __launch_bounds__(256)
+expand_planes_kernel(size_t plane, int nplanes, int nz, int lo, const int *__restrict__ list,
+                     const double *__restrict__ compact, double *__restrict__ full) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane * (size_t)nplanes) return;
+  const int p = (int)(i / plane);
+  const size_t r = i - (size_t)p * plane;
+  int mz = list ? list[p] : (lo + p) % nz;
+  if (mz < 0) mz += nz;
+  full[(size_t)mz * plane + r] = compact[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -119,11 +209,11 @@ gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ 
     const int n = t / (order * order);
     const int r = t - n * order * order;
     const int m = r / order, l = r - m * order;
-    const int mz = wrapi(n + g.nlower + nz, g.nz);
+    const int zo = g.zmap[wrapi(n + g.nlower + nz, g.nz)];  // compact output plane
     const int my = wrapi(m + g.nlower + ny, g.ny);
     const int mx = wrapi(l + g.nlower + nx, g.nx);
     const double x0 = w[2 * order + n] * w[order + m] * w[l];
-    acc = fma(x0, u_brick[((size_t)mz * g.ny + my) * g.nx + mx], acc);
+    acc = fma(x0, u_brick[((size_t)zo * g.ny + my) * g.nx + mx], acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -149,9 +239,9 @@ ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, cons
   const double *w = weights + (size_t)i * 3 * order;
   const double z0 = g.delvolinv * q_ele[i];  // pppm_conp.cpp:411
   const double x0 = z0 * w[2 * order + n] * w[order + m];
-  const int mz = wrapi(n + g.nlower + nz, g.nz);
+  const int zo = g.zmap[wrapi(n + g.nlower + nz, g.nz)];
   const int my = wrapi(m + g.nlower + ny, g.ny);
-  double *row = brick + ((size_t)mz * g.ny + my) * g.nx;
+  double *row = brick + ((size_t)zo * g.ny + my) * g.nx;
   int mx = wrapi(g.nlower + nx, g.nx);
   for (int l = 0; l < order; ++l) {
     atomicAdd(row + mx, x0 * w[l]);
@@ -178,6 +268,40 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
 
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf) {
   green_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, work, ghalf);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
+                      const cufftDoubleComplex *rhat, const double *Kr, const cufftDoubleComplex *Kc,
+                      cufftDoubleComplex *uhat) {
+  const size_t smem = sizeof(double2) * (size_t)nzi * ZC_COLS;
+  static size_t smem_set_r = 0, smem_set_c = 0;
+  const int grid = (ncol + ZC_COLS - 1) / ZC_COLS;
+  if (Kr) {
+    if (smem > smem_set_r) {
+      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set_r = smem;
+    }
+    zconv_kernel<true><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list,
+                                                        (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
+  } else {
+    if (smem > smem_set_c) {
+      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set_c = smem;
+    }
+    zconv_kernel<false><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list,
+                                                         (const double2 *)rhat, nullptr, (const double2 *)Kc,
+                                                         (double2 *)uhat);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
+                         const double *compact, double *full) {
+  const size_t tot = plane * (size_t)nplanes;
+  expand_planes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(plane, nplanes, nz, lo, list, compact, full);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
