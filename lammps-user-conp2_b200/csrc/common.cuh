@@ -124,6 +124,12 @@ struct __align__(32) PosQ {
   double x, y, z, q;
 };
 
+// electrode atom in the static cell-sorted list (wrapped position, eleall index, type)
+struct __align__(32) EPos {
+  double x, y, z;
+  int idx, type;
+};
+
 // ---------------------------------------------------------------------------
 // geometry of the uniform cell grid used to bin point charges
 // ---------------------------------------------------------------------------
@@ -182,18 +188,32 @@ void comm_allreduce_sum_f64(Comm *, double *buf, size_t n, cudaStream_t);
 // ---------------------------------------------------------------------------
 
 // gemv.cu ------------------------------------------------------------------
+// update_charge epilogue parameters (device pointers); see charge_epilogue() in gemv.cu
+struct ChargeEpilogue {
+  int enabled, variant, n, row_offset, one_electrode;
+  double totsetq, lz, vmult;
+  const double *value;   // dV | QR | D in device memory
+  const double *dipole;  // sum q z of the non-electrode atoms
+  const int *side;
+  const double *setz, *setq, *qinit, *sb;
+  double *q_out, *scalar_out /* [0]=scalar, [1]=potdiff */, *partials /* 2 per block */;
+  unsigned int *counter;
+};
 // out[r] = sum_c S[r*pitch + c] * b[c], r < nrows, c < ncols_pad (pad columns of S and b are zero).
+// With ep != nullptr the charge epilogue runs in the tail of the same kernel (single-GPU path).
 int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int ncols_pad, const double *b,
-                double *out, int num_sms);
-// conp/conq/cond epilogue over the full eleallq vector (single block)
-int launch_update_charge(cudaStream_t s, int variant, int n, const double *sb, const double *setq,
-                         const double *qinit, const int *side, const double *setz, double totsetq,
-                         double value, int one_electrode, const double *dipole_dev, double lz, double vmult,
-                         double *q_out, double *scalar_out /* [0]=scalar, [1]=potdiff */);
+                double *out, int num_sms, const ChargeEpilogue *ep);
+int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep);
+int launch_finalize_q(cudaStream_t s, int n, const double *sb, const double *setq, const double *qinit,
+                      const double *scal /* [1] = potdiff */, double *q_out);
 
 // pair.cu ------------------------------------------------------------------
 CellGrid make_cell_grid(const double lo[3], const double prd[3], const int periodic[3], double rc);
-// pack: gather raw positions -> wrapped PosQ, accumulate sum(q z) [slab/cond dipole], count per cell
+// host: static electrode structures (electrodes never move)
+void build_electrode_cells(const CellGrid &g, int begin, int end, const double *xyz, const int *type,
+                           std::vector<EPos> &sorted, std::vector<int> &cell_start);
+void build_near_mask(const CellGrid &g, int begin, int end, const double *xyz, std::vector<unsigned char> &mask);
+// per-step counting sort of the point charges: pack (+histogram, + sum q z), scan, scatter
 int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
                       const double *q, const int *type, PosQ *packed, int *packed_type, int *cell_of, int *slot,
                       int *cell_count, double *qz_sum);
@@ -202,26 +222,29 @@ int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, const PosQ *p
 int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start);
 int launch_cell_scatter(cudaStream_t s, int m, const PosQ *packed, const int *type, const int *cell_of,
                         const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type, int *sorted_src);
+// charges sitting in a cell within reach of an electrode atom (near_count must be zeroed); post_force only
+int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const unsigned char *near_mask,
+                     int *near_list, int *near_count);
+// b_real[i] = -sum_j q_j dudq(r_ij), rows [row_begin,row_end), against the cell-sorted point charges
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
                   const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const int *cell_start, double *b_real /* indexed by global row */);
-int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
-                  const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const int *sorted_src, const int *cell_start, double *A_rows,
-                  size_t pitch);
-int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e, int row_begin,
-                          int row_end, const double *ex, const double *ey, const double *ez, const int *etype,
-                          const double *q_ele, const PosQ *sorted, const int *sorted_type, const int *sorted_src,
-                          const int *cell_start, const double *cutsq_listed, double *f_packed /* m x 3 */,
-                          double *energies /* 8 */);
+                  const int *sorted_type, const int *cell_start, double *b_real);
+int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
+                  const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
+                  const double *ez, const int *etype, double *A_rows, size_t pitch);
+int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e,
+                          const EPos *esorted, const int *cell_start, const double *q_ele, const PosQ *packed,
+                          const int *packed_type, const int *near_list, const int *near_count, int max_near,
+                          const double *cutsq_listed, double *f_packed /* m x 3 */, double *energies /* 8 */,
+                          int num_sms);
 
 // pppm.cu ------------------------------------------------------------------
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m, const PosQ *atoms,
                        double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
 int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
-                      const cufftDoubleComplex *rhat, const double *Kr, const cufftDoubleComplex *Kc,
-                      cufftDoubleComplex *uhat);
+                      const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
+                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
                          const double *compact, double *full);
 int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
@@ -229,8 +252,10 @@ int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho
 int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *part2grid,
                          const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
                          double slab_pref /* 4 pi / V or 0 */, const double *b_real, double *b_kspace, double *b);
+// electrode re-spread; forms q_i = sb_i + potdiff*setq_i (+qinit_i) on the fly and stores it to q_out
 int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, const double *weights,
-                           const double *q_ele, double *brick);
+                           const double *sb, const double *setq, const double *qinit, const double *scal,
+                           double *q_out, double *brick);
 int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out);
 
 // ewald.cu -----------------------------------------------------------------

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 using namespace conp;
@@ -71,9 +72,14 @@ struct conp_ctx {
   DevBuf<double> d_xraw, d_qraw;
   DevBuf<int> d_typeraw, d_idx;
   DevBuf<PosQ> d_packed, d_sorted;
-  DevBuf<int> d_ptype, d_stype, d_ssrc, d_cellof, d_slot, d_cellcount, d_cellstart;
-  CellGrid grid_b;
+  DevBuf<int> d_ptype, d_stype, d_ssrc, d_cellof, d_slot, d_cellcount, d_cellstart, d_nearlist, d_nearcount;
   DevBuf<double> d_fpacked;
+  // static electrode cell structures for the real-space kernels (own rows)
+  CellGrid grid_b;
+  bool static_cells = false;
+  DevBuf<EPos> d_esorted;
+  DevBuf<int> d_ecellstart;
+  DevBuf<unsigned char> d_nearmask;
 
   // pppm ---------------------------------------------------------------------------
   PPPMGeom pg;
@@ -81,13 +87,23 @@ struct conp_ctx {
   std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
   std::vector<int> h_zout;              // output planes (sorted)
   DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
-  DevBuf<int> d_part2grid, d_flag, d_zmap, d_zout;
+  DevBuf<int> d_part2grid, d_flag, d_zmap, d_zout, d_krad;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
   bool plans = false, k_real = true;
 
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
+
+  // epilogue scratch + CUDA-graph replay of the step ----------------------------------
+  DevBuf<double> d_partials;
+  DevBuf<unsigned int> d_counter;
+  PinnedBuf<double> h_value;  // ring of staged `value` arguments
+  int value_slot = 0;
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  long long graph_launches[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  int eager_runs[2][3] = {{0, 0, 0}, {0, 0, 0}};
 
   // timing ----------------------------------------------------------------------------
   cudaEvent_t ev[16];
@@ -97,6 +113,7 @@ struct conp_ctx {
   int stage_n = 0;
 
   // scalars in d_scal: [0] scalar_output [1] potdiff [2] qz_sum [3] projection total [4..11] energies
+  // [12] value (dV | QR | D) of the current solve
   double *scal(int i) { return d_scal.p + i; }
 };
 
@@ -141,19 +158,56 @@ double slab_pref(const conp_ctx *c) {
   return 4.0 * MY_PI / volume;  // km_ewald.cpp:839, pppm_conp.cpp:307
 }
 
-// bin an arbitrary packed set (positions already wrapped) into grid g
-void bin_sorted(conp_ctx *c, const CellGrid &g, int m) {
-  c->d_cellcount.zero((size_t)g.ncells + 1, c->stream);
-  c->d_cellstart.reserve((size_t)g.ncells + 1);
-  c->d_cellof.reserve(m);
-  c->d_slot.reserve(m);
-  c->d_sorted.reserve(m);
-  c->d_stype.reserve(m);
-  c->d_ssrc.reserve(m);
-  c->launches += launch_bin_positions(c->stream, g, m, c->d_packed.p, c->d_cellof.p, c->d_slot.p, c->d_cellcount.p);
-  c->launches += launch_cell_scan(c->stream, g.ncells, c->d_cellcount.p, c->d_cellstart.p);
-  c->launches += launch_cell_scatter(c->stream, m, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
-                                     c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p);
+// electrodes never move: sort this rank's rows into the cell grid once and mark
+// the cells from which a point charge can reach them
+void ensure_static_cells(conp_ctx *c) {
+  if (c->static_cells) return;
+  c->grid_b = make_cell_grid(c->boxlo, c->prd, c->periodic, c->rc_b > 0 ? c->rc_b : 1.0);
+  std::vector<EPos> sorted;
+  std::vector<int> cs;
+  std::vector<unsigned char> mask;
+  build_electrode_cells(c->grid_b, c->r0, c->r1, c->h_xyz.data(), c->h_type.data(), sorted, cs);
+  build_near_mask(c->grid_b, c->r0, c->r1, c->h_xyz.data(), mask);
+  if (sorted.empty()) sorted.resize(1);
+  c->d_esorted.upload(sorted, c->stream);
+  c->d_ecellstart.upload(cs, c->stream);
+  c->d_nearmask.upload(mask, c->stream);
+  c->d_nearcount.zero(1, c->stream);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->static_cells = true;
+}
+
+void drop_graphs(conp_ctx *c) {
+  for (auto &row : c->graph_exec)
+    for (auto &g : row)
+      if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  for (auto &row : c->eager_runs)
+    for (auto &n : row) n = 0;
+}
+
+ChargeEpilogue make_epilogue(conp_ctx *c, int variant, bool fused) {
+  ChargeEpilogue ep;
+  std::memset(&ep, 0, sizeof(ep));
+  ep.enabled = 1;
+  ep.variant = variant;
+  ep.n = c->N;
+  ep.row_offset = fused ? c->r0 : 0;
+  ep.one_electrode = c->one_electrode;
+  ep.totsetq = c->totsetq;
+  ep.lz = c->prd[2];
+  ep.vmult = c->vmult;
+  ep.value = c->scal(12);
+  ep.dipole = c->scal(2);
+  ep.side = c->d_eside.p;
+  ep.setz = c->d_setz.p;
+  ep.setq = c->d_setq.p;
+  ep.qinit = c->have_qinit ? c->d_qinit.p : nullptr;
+  ep.sb = c->d_sb.p;
+  ep.q_out = c->d_q.p;
+  ep.scalar_out = c->scal(0);
+  ep.partials = c->d_partials.p;
+  ep.counter = c->d_counter.p;
+  return ep;
 }
 
 void stage_mark(conp_ctx *c, int i) {
@@ -161,22 +215,21 @@ void stage_mark(conp_ctx *c, int i) {
 }
 
 // --------------------------------------------------------------------------
-// the per-step pipeline (device side, asynchronous on c->stream)
+// the per-step pipeline (device side, asynchronous on c->stream).  Inputs:
+// positions in c->d_xraw, the variant's value in scal(12).  Everything here is
+// stream-ordered and capturable into a CUDA graph.
 // --------------------------------------------------------------------------
-void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant, double value) {
-  need(c->have_setq, "conp_pre_force: setup incomplete (conp_set_unit_voltage not called)");
-  need(c->have_atoms, "conp_pre_force: conp_post_neighbor not called");
-  if (kspace_mode == CONP_KSPACE_PPPM) need(c->have_pppm, "conp_pre_force: PPPM mode needs conp_pppm_setup");
-  if (variant < 0 || variant > 2) CONP_THROW(CONP_ERR_ARG, "conp_pre_force: unknown variant %d", variant);
+void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   cudaStream_t s = c->stream;
   const int nr = c->r1 - c->r0;
   const bool multi = c->nranks > 1;
+  const double *x_dev = c->d_xraw.p;
 
   stage_mark(c, 0);
-  // ---- pack (+ bin when single rank) ---------------------------------
+  // ---- counting sort of the point charges: pack (+histogram, sum q z), scan, scatter ----
   CUDA_CHECK(cudaMemsetAsync(c->scal(2), 0, sizeof(double), s));
   const CellGrid &g = c->grid_b;
-  c->d_cellcount.zero((size_t)g.ncells + 1, s);
+  CUDA_CHECK(cudaMemsetAsync(c->d_cellcount.p, 0, sizeof(int) * ((size_t)g.ncells + 1), s));
   PosQ *packed_local = c->d_packed.p + c->m_offsets[c->rank];
   int *ptype_local = c->d_ptype.p + c->m_offsets[c->rank];
   if (!multi) {
@@ -209,12 +262,12 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
   stage_mark(c, 2);
 
   // ---- real-space part of b (blist_coul_cal) ---------------------------------
-  if (c->rc_b > 0.0 && c->m_total > 0) {
+  if (c->rc_b > 0.0 && c->m_total > 0 && nr > 0) {
     c->launches += launch_pair_b(s, g, pair_tables(c, c->d_cuteff_b.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
                                  c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_cellstart.p,
                                  c->d_breal.p);
   } else {
-    CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * nr, s));
+    CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * std::max(nr, 1), s));
   }
   stage_mark(c, 3);
 
@@ -226,7 +279,8 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
     c->launches += launch_pppm_spread(s, c->pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_brick.p, c->d_flag.p);
     CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
     c->launches += launch_pppm_zconv(s, (int)c->ncol, c->pg.nz, c->pg.nzi, c->pg.zin_lo, c->pg.nzo, c->d_zout.p,
-                                     c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p);
+                                     c->d_krad.p, c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p,
+                                     c->d_uhat.p);
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
@@ -234,8 +288,6 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
   } else {
     const EwaldHost &e = c->ew;
-    const size_t T = (size_t)e.kxmax + e.kymax + e.kzmax + 3;
-    c->d_jtab.reserve(T * (size_t)std::max(c->m_total, 1));
     c->launches += launch_axis_tables(s, c->m_total, nullptr, nullptr, nullptr, c->d_sorted.p, e.unitk, e.kxmax,
                                       e.kymax, e.kzmax, c->d_jtab.p);
     c->launches += launch_ewald_sfac(s, c->m_total, c->d_sorted.p, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
@@ -247,24 +299,80 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
   }
   stage_mark(c, 5);
 
-  // ---- exchange b, GEMV, exchange S.b --------------------------------------------
+  // ---- exchange b, GEMV (+ fused epilogue on one GPU), exchange S.b ------------------
   if (multi) comm_allgather(c->comm, c->d_b.p + c->r0, c->d_b.p, sizeof(double) * c->rpr, s);
   stage_mark(c, 6);
-  c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms);
-  if (multi) comm_allgather(c->comm, c->d_sb.p + c->r0, c->d_sb.p, sizeof(double) * c->rpr, s);
-  stage_mark(c, 7);
-
-  // ---- epilogue -------------------------------------------------------------------
-  c->launches += launch_update_charge(s, variant, c->N, c->d_sb.p, c->d_setq.p,
-                                      c->have_qinit ? c->d_qinit.p : nullptr, c->d_eside.p, c->d_setz.p,
-                                      c->totsetq, value, c->one_electrode, c->scal(2), c->prd[2], c->vmult,
-                                      c->d_q.p, c->scal(0));
-  if (kspace_mode == CONP_KSPACE_PPPM) {  // kspmod->update_charge() -> ele_make_rho
+  if (!multi) {
+    const ChargeEpilogue ep = make_epilogue(c, variant, true);
+    c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
+                               &ep);
+    stage_mark(c, 7);
+  } else {
+    c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
+                               nullptr);
+    comm_allgather(c->comm, c->d_sb.p + c->r0, c->d_sb.p, sizeof(double) * c->rpr, s);
+    stage_mark(c, 7);
+    c->launches += launch_update_charge(s, make_epilogue(c, variant, false));
+  }
+  const double *qinit = c->have_qinit ? c->d_qinit.p : nullptr;
+  if (kspace_mode == CONP_KSPACE_PPPM) {  // charges + kspmod->update_charge() -> ele_make_rho
     CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, s));
-    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_part2grid.p, c->d_weights.p, c->d_q.p,
-                                          c->d_ebrick.p);
+    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_part2grid.p, c->d_weights.p, c->d_sb.p,
+                                          c->d_setq.p, qinit, c->scal(0), c->d_q.p, c->d_ebrick.p);
+  } else {
+    c->launches += launch_finalize_q(s, c->N, c->d_sb.p, c->d_setq.p, qinit, c->scal(0), c->d_q.p);
   }
   stage_mark(c, 8);
+}
+
+void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant, double value) {
+  need(c->have_setq, "conp_pre_force: setup incomplete (conp_set_unit_voltage not called)");
+  need(c->have_atoms, "conp_pre_force: conp_post_neighbor not called");
+  if (kspace_mode != CONP_KSPACE_PPPM && kspace_mode != CONP_KSPACE_EWALD)
+    CONP_THROW(CONP_ERR_ARG, "conp_pre_force: unknown kspace mode %d", kspace_mode);
+  if (kspace_mode == CONP_KSPACE_PPPM) need(c->have_pppm, "conp_pre_force: PPPM mode needs conp_pppm_setup");
+  if (variant < 0 || variant > 2) CONP_THROW(CONP_ERR_ARG, "conp_pre_force: unknown variant %d", variant);
+  cudaStream_t s = c->stream;
+  if (x_dev != c->d_xraw.p && c->nlocal > 0)
+    CUDA_CHECK(cudaMemcpyAsync(c->d_xraw.p, x_dev, sizeof(double) * 3 * (size_t)c->nlocal, cudaMemcpyDeviceToDevice,
+                               s));
+  double *slot = c->h_value.p + (c->value_slot++ & 63);
+  *slot = value;
+  CUDA_CHECK(cudaMemcpyAsync(c->scal(12), slot, sizeof(double), cudaMemcpyHostToDevice, s));
+  if (kspace_mode == CONP_KSPACE_EWALD) {
+    const EwaldHost &e = c->ew;
+    c->d_jtab.reserve(((size_t)e.kxmax + e.kymax + e.kzmax + 3) * (size_t)std::max(c->m_total, 1));
+  }
+
+  cudaGraphExec_t &exec = c->graph_exec[kspace_mode][variant];
+  if (!c->use_graph || c->stage_timing) {
+    enqueue_step(c, kspace_mode, variant);
+  } else if (exec) {
+    CUDA_CHECK(cudaGraphLaunch(exec, s));
+    c->launches += c->graph_launches[kspace_mode][variant];
+  } else if (c->eager_runs[kspace_mode][variant]++ < 1) {
+    enqueue_step(c, kspace_mode, variant);  // first run eager: sets kernel attributes, sizes buffers
+  } else {
+    const long long before = c->launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue_step(c, kspace_mode, variant);
+    } catch (...) {
+      cudaStreamEndCapture(s, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+    c->graph_launches[kspace_mode][variant] = c->launches - before;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      exec = nullptr;
+      CONP_THROW(CONP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    CUDA_CHECK(cudaGraphLaunch(exec, s));
+  }
   c->solved = true;
   if (c->stage_timing) {
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -363,6 +471,10 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     for (auto &ev : c->ev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
     c->d_scal.zero(16, c->stream);
+    c->d_partials.zero(2 * 1024, c->stream);
+    c->d_counter.zero(1, c->stream);
+    c->h_value.reserve(64);
+    c->use_graph = getenv("CONP_NO_GRAPH") == nullptr;
     c->comm = comm_create(rank, nranks, unique_id);
     CUSOLVER_CHECK(cusolverDnCreate(&c->solver));
     CUSOLVER_CHECK(cusolverDnSetStream(c->solver, c->stream));
@@ -382,6 +494,7 @@ void conp_destroy(conp_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
   if (c->plans) {
     cufftDestroy(c->plan_f);
     cufftDestroy(c->plan_b);
@@ -492,6 +605,7 @@ int conp_set_pair(conp_ctx *c, int pairmode, double eta, double cut_coul, int nt
     c->rc_f = std::sqrt(std::min(mf, ERFC_MAX / (eta * eta) * (1.0 + 1e-9)));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->have_pair = true;
+    c->static_cells = false;
   });
 }
 
@@ -538,6 +652,7 @@ int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type,
                                       e.kzmax, c->d_etab.p);
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->have_ele = true;
+    c->static_cells = false;
     c->have_A = c->inverted = c->have_setq = false;
   });
 }
@@ -628,6 +743,32 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
       double mre = 0, mim = 0;
       for (size_t i = 0; i < c->nhalf; ++i) { mre = std::max(mre, std::fabs(gc[i].x)); mim = std::max(mim, std::fabs(gc[i].y)); }
       c->k_real = mim <= 1e-14 * mre;
+      // per-column window radius.  |K| falls off like the Ewald Gaussian (or exp(-k|d|) for the
+      // smallest k_xy) until it hits the ~1e-16 noise floor of this FFT-built table, so the radius
+      // is read off at the 1e-13 level, where the table is still clean, and extended by 20 % + 2
+      // planes (a Gaussian that is 1e-13 at R is < 1e-18 at 1.2 R).
+      {
+        std::vector<int> krad(ncol, 0);
+        for (size_t col = 0; col < ncol; ++col) {
+          const cufftDoubleComplex *row = gc.data() + col * nz;
+          double kmax = 0;
+          for (size_t d = 0; d < nz; ++d) kmax = std::max(kmax, std::hypot(row[d].x, row[d].y));
+          const double thr = 1e-13 * kmax;
+          int R = 0;
+          for (size_t d = 0; d < nz; ++d)
+            if (kmax > 0 && std::hypot(row[d].x, row[d].y) >= thr) R = std::max(R, (int)std::min(d, nz - d));
+          krad[col] = (int)std::ceil(1.2 * R) + 2;
+        }
+        if (getenv("CONP_DEBUG")) {
+          long long tot = 0;
+          int full = 0;
+          for (int r : krad) { tot += r; full += (2 * r + 1 >= (int)nz); }
+          fprintf(stderr, "[conp] zconv window radius: mean %.1f planes, %d of %zu columns full (nzi %d, nzo %d)\n",
+                  (double)tot / ncol, full, ncol, g.nzi, g.nzo);
+        }
+        c->d_krad.upload(krad, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+      }
       if (c->k_real) {
         std::vector<double> kr(c->nhalf);
         for (size_t i = 0; i < c->nhalf; ++i) kr[i] = gc[i].x;
@@ -651,6 +792,7 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     CUFFT_CHECK(cufftSetStream(c->plan_b, s));
     c->plans = true;
     CUDA_CHECK(cudaStreamSynchronize(s));
+    drop_graphs(c);
     c->have_pppm = true;
   });
 }
@@ -696,17 +838,15 @@ int conp_build_A(conp_ctx *c) {
     // ---- real-space electrode-electrode pairs -------------------------------------
     if (c->rc_a > 0.0) {
       CellGrid g = make_cell_grid(c->boxlo, c->prd, c->periodic, c->rc_a);
-      c->d_packed.reserve(N);
-      c->d_ptype.reserve(N);
-      CUDA_CHECK(cudaMemsetAsync(c->scal(2), 0, sizeof(double), s));
-      DevBuf<double> zeroq;
-      zeroq.zero(N, s);
-      c->launches += launch_pack_count(s, g, N, c->d_exyz.p, nullptr, zeroq.p, c->d_etype.p, c->d_packed.p,
-                                       c->d_ptype.p, nullptr, nullptr, nullptr, c->scal(2));
-      bin_sorted(c, g, N);
-      c->launches += launch_pair_A(s, g, pair_tables(c, c->d_cuteff_a.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
-                                   c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p,
-                                   c->d_cellstart.p, c->d_mat.p, c->pitch);
+      std::vector<EPos> sorted;
+      std::vector<int> cs;
+      build_electrode_cells(g, 0, N, c->h_xyz.data(), c->h_type.data(), sorted, cs);
+      DevBuf<EPos> dsorted;
+      DevBuf<int> dcs;
+      dsorted.upload(sorted, s);
+      dcs.upload(cs, s);
+      c->launches += launch_pair_A(s, g, pair_tables(c, c->d_cuteff_a.p), dsorted.p, dcs.p, c->r0, c->r1, c->d_ex.p,
+                                   c->d_ey.p, c->d_ez.p, c->d_etype.p, c->d_mat.p, c->pitch);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
     CUDA_CHECK(cudaEventRecord(c->ev[15], s));
@@ -716,7 +856,6 @@ int conp_build_A(conp_ctx *c) {
     c->build_ms = ms;
     c->have_A = true;
     c->inverted = false;
-    c->have_atoms = false;  // shared binning buffers were reused
   });
 }
 
@@ -829,7 +968,7 @@ int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int
                                    c->d_dvec.p, c->d_setz.p);
     // get_setq: elesetq = S.d (fix_conp.cpp:1090-1096)
     c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_dvec.p, c->d_setq.p + c->r0,
-                               c->num_sms);
+                               c->num_sms, nullptr);
     if (c->nranks > 1) comm_allgather(c->comm, c->d_setq.p + c->r0, c->d_setq.p, sizeof(double) * c->rpr, s);
     std::vector<double> setq(N), setz(N);
     CUDA_CHECK(cudaMemcpyAsync(setq.data(), c->d_setq.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
@@ -860,6 +999,7 @@ int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
     if (totsetq_out) *totsetq_out = tot;
+    drop_graphs(c);
     c->have_setq = true;
   });
 }
@@ -908,9 +1048,11 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     c->d_packed.reserve(m); c->d_sorted.reserve(m);
     c->d_ptype.reserve(m); c->d_stype.reserve(m); c->d_ssrc.reserve(m);
     c->d_cellof.reserve(m); c->d_slot.reserve(m);
-    c->grid_b = make_cell_grid(c->boxlo, c->prd, c->periodic, c->rc_b > 0 ? c->rc_b : 1.0);
+    c->d_nearlist.reserve(m);
+    ensure_static_cells(c);
     c->d_cellcount.zero((size_t)c->grid_b.ncells + 1, s);
     c->d_cellstart.zero((size_t)c->grid_b.ncells + 1, s);
+    drop_graphs(c);
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->have_atoms = true;
   });
@@ -1026,14 +1168,17 @@ int conp_post_force(conp_ctx *c, double qqrd2e, double *f_out, double *energies_
     const int N = c->N;
     CUDA_CHECK(cudaMemsetAsync(c->scal(4), 0, sizeof(double) * 8, s));
     c->d_fpacked.zero(3 * (size_t)std::max(c->m_total, 1), s);
-    if (c->rc_f > 0.0 && c->m_total > 0) {
-      CellGrid g = c->grid_b;  // same binning, smaller search radius
+    if (c->rc_f > 0.0 && c->m_total > 0 && c->r1 > c->r0) {
+      CellGrid g = c->grid_b;  // same electrode binning, smaller search radius
       g.rc = c->rc_f;
       for (int a = 0; a < 3; ++a) g.smax[a] = g.periodic[a] ? (int)std::ceil(g.rc / g.prd[a]) + 1 : 0;
-      c->launches += launch_pair_postforce(s, g, pair_tables(c, c->d_cuteff_b.p), qqrd2e, c->r0, c->r1, c->d_ex.p,
-                                           c->d_ey.p, c->d_ez.p, c->d_etype.p, c->d_q.p, c->d_sorted.p,
-                                           c->d_stype.p, c->d_ssrc.p, c->d_cellstart.p, c->d_cutsq_listed.p,
-                                           c->d_fpacked.p, c->scal(4));
+      CUDA_CHECK(cudaMemsetAsync(c->d_nearcount.p, 0, sizeof(int), s));
+      c->launches += launch_near_list(s, c->grid_b, c->m_total, c->d_packed.p, c->d_nearmask.p, c->d_nearlist.p,
+                                      c->d_nearcount.p);
+      c->launches += launch_pair_postforce(s, g, pair_tables(c, c->d_cuteff_b.p), qqrd2e, c->d_esorted.p,
+                                           c->d_ecellstart.p, c->d_q.p, c->d_packed.p, c->d_ptype.p,
+                                           c->d_nearlist.p, c->d_nearcount.p, c->m_total, c->d_cutsq_listed.p,
+                                           c->d_fpacked.p, c->scal(4), c->num_sms);
     }
     if (c->nranks > 1) {
       comm_allreduce_sum_f64(c->comm, c->scal(4), 8, s);
@@ -1112,10 +1257,11 @@ int conp_bench_gemv(conp_ctx *c, int reps, float *ms_per_rep_out) {
     need(c->have_A, "conp_bench_gemv: no matrix resident");
     const int nr = c->r1 - c->r0;
     cudaStream_t s = c->stream;
-    launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms);
+    launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms, nullptr);
     CUDA_CHECK(cudaEventRecord(c->ev[12], s));
     for (int r = 0; r < reps; ++r)
-      c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms);
+      c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
+                                 nullptr);
     CUDA_CHECK(cudaEventRecord(c->ev[13], s));
     CUDA_CHECK(cudaEventSynchronize(c->ev[13]));
     float ms = 0;

@@ -14,6 +14,8 @@
 // in flight per SM, enough to cover HBM latency at 6.5 TB/s / 148 SMs.
 #include "common.cuh"
 
+#include <cstring>
+
 namespace conp {
 
 namespace {
@@ -84,9 +86,78 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   return p;
 }
 
+// ---------------------------------------------------------------------------
+// update_charge epilogue (fix_conp.cpp:1143-1159, fix_conq.cpp:74-86,
+// fix_cond.cpp:99-123), shared by the fused GEMV tail and the stand-alone kernel.
+// Every block sums sum_{left} (S.b)_i and sum_i setz_i (S.b)_i over its own rows,
+// publishes the two partials and takes a ticket; the last block to arrive
+// reduces the partials with a fixed-shape tree (deterministic) and fixes the
+// potential difference.  The charges q_i = (S.b)_i + potdiff*setq_i (+qinit_i)
+// are formed by the consumer kernels (ele_spread / finalize_q).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce_ordered(double v, double *sh, int tid, int nthreads, int bar_id) {
+  // fixed-shape tree over `nthreads` (power of two) threads
+  sh[tid] = v;
+  for (int o = nthreads >> 1; o > 0; o >>= 1) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    if (tid < o) sh[tid] += sh[tid + o];
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  const double r = sh[0];
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  return r;
+}
+
+// called by `nthreads` threads (tid 0..nthreads-1) of every block; a, z are the
+// thread's partial sums over rows of this block
+__device__ void charge_epilogue(const ChargeEpilogue &ep, double a, double z, int tid, int nthreads, int bar_id,
+                                double *sh /* >= nthreads doubles */, int *sh_flag) {
+  const double pl = block_reduce_ordered(a, sh, tid, nthreads, bar_id);
+  const double pz = block_reduce_ordered(z, sh, tid, nthreads, bar_id);
+  if (tid == 0) {
+    ep.partials[2 * blockIdx.x] = pl;
+    ep.partials[2 * blockIdx.x + 1] = pz;
+    __threadfence();
+    const unsigned ticket = atomicAdd(ep.counter, 1u);
+    *sh_flag = (ticket == gridDim.x - 1);
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  if (!*sh_flag) return;
+  __threadfence();
+  double ta = 0.0, tz = 0.0;
+  for (unsigned k = tid; k < gridDim.x; k += nthreads) {
+    ta += __ldcg(ep.partials + 2 * k);
+    tz += __ldcg(ep.partials + 2 * k + 1);
+  }
+  const double tot_left = block_reduce_ordered(ta, sh, tid, nthreads, bar_id);
+  const double tot_z = block_reduce_ordered(tz, sh, tid, nthreads, bar_id);
+  if (tid == 0) {
+    const double value = __ldcg(ep.value);
+    double potdiff, scalar;
+    if (ep.variant == CONP_VARIANT_CONP) {  // fix_conp.cpp:1149-1159
+      potdiff = value;
+      scalar = potdiff * ep.totsetq + tot_left;
+    } else if (ep.variant == CONP_VARIANT_CONQ) {  // fix_conq.cpp:74-80
+      const double netcharge_right = -tot_left;
+      scalar = -(value - netcharge_right) / ep.totsetq;
+      if (ep.one_electrode) scalar += 2 * value / ep.totsetq;
+      potdiff = scalar;
+    } else {  // fix_cond.cpp:101-115; dipole[0] = sum q z over non-electrode atoms
+      const double dipole_all = -__ldcg(ep.dipole);
+      potdiff = value - dipole_all / ep.lz;
+      potdiff -= tot_z;
+      potdiff *= ep.vmult;
+      scalar = potdiff;
+    }
+    ep.scalar_out[0] = scalar;
+    ep.scalar_out[1] = potdiff;
+    *ep.counter = 0u;  // ready for the next launch
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 gemv_tma_kernel(const double *__restrict__ S, size_t pitch, int nrows, int ncols_pad,
-                const double *__restrict__ b, double *__restrict__ out) {
+                const double *__restrict__ b, double *__restrict__ out, ChargeEpilogue ep) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
@@ -189,75 +260,54 @@ gemv_tma_kernel(const double *__restrict__ S, size_t pitch, int nrows, int ncols
       out[r0 + tid] = v;
     }
   }
+  if (ep.enabled) {
+    // the tile ring is idle now: reuse stage 0 as reduction scratch.  The barrier also makes this
+    // block's rows of `out` visible to all of its threads.
+    double *scratch = &sm.st[0].tile[0][0];
+    int *flag = reinterpret_cast<int *>(&sm.red[0][0][0]);
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+    double a = 0.0, z = 0.0;
+    for (int r = row_a + tid; r < row_b; r += CONSUMERS) {
+      const double v = out[r];
+      const int gi = ep.row_offset + r;
+      if (ep.side[gi] == 1) a += v;
+      z = fma(ep.setz[gi], v, z);
+    }
+    charge_epilogue(ep, a, z, tid, CONSUMERS, 1, scratch, flag);
+  }
 }
 
-// ---------------------------------------------------------------------------
-// update_charge epilogue: one block, deterministic reductions
-// ---------------------------------------------------------------------------
-__device__ double block_sum_1024(double v, double *sh) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (warp == 0) {
-    t = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) sh[32] = t;
+// stand-alone epilogue over the full (gathered) S.b vector: the multi-GPU path
+constexpr int UC_THREADS = 256;
+
+__global__ void __launch_bounds__(UC_THREADS)
+update_charge_kernel(ChargeEpilogue ep) {
+  __shared__ double sh[UC_THREADS];
+  __shared__ int flag;
+  double a = 0.0, z = 0.0;
+  for (int i = blockIdx.x * UC_THREADS + threadIdx.x; i < ep.n; i += gridDim.x * UC_THREADS) {
+    const double v = ep.sb[i];
+    if (ep.side[i] == 1) a += v;
+    z = fma(ep.setz[i], v, z);
   }
-  __syncthreads();
-  return sh[32];
+  charge_epilogue(ep, a, z, threadIdx.x, UC_THREADS, 0, sh, &flag);
 }
 
-__global__ void __launch_bounds__(1024, 1)
-update_charge_kernel(int variant, int n, const double *__restrict__ sb, const double *__restrict__ setq,
-                     const double *__restrict__ qinit, const int *__restrict__ side,
-                     const double *__restrict__ setz, double totsetq, double value, int one_electrode,
-                     const double *__restrict__ dipole_dev, double lz, double vmult, double *__restrict__ q_out,
-                     double *__restrict__ scalar_out) {
-  __shared__ double sh[33];
-  double part = 0.0;
-  if (variant == CONP_VARIANT_COND) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) part += setz[i] * sb[i];
-  } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      if (side[i] == 1) part += sb[i];
-  }
-  const double tot = block_sum_1024(part, sh);
-  double potdiff, scalar;
-  if (variant == CONP_VARIANT_CONP) {  // fix_conp.cpp:1149-1159
-    potdiff = value;
-    scalar = potdiff * totsetq + tot;
-  } else if (variant == CONP_VARIANT_CONQ) {  // fix_conq.cpp:74-80
-    const double netcharge_right = -tot;
-    scalar = -(value - netcharge_right) / totsetq;
-    if (one_electrode) scalar += 2 * value / totsetq;
-    potdiff = scalar;
-  } else {  // fix_cond.cpp:101-115; dipole_dev[0] = sum q z over non-electrode atoms
-    const double dipole_all = -dipole_dev[0];
-    potdiff = value - dipole_all / lz;
-    potdiff -= tot;
-    potdiff *= vmult;
-    scalar = potdiff;
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double q = sb[i] + potdiff * setq[i];
-    if (qinit) q += qinit[i];
-    q_out[i] = q;
-  }
-  if (threadIdx.x == 0) {
-    scalar_out[0] = scalar;
-    scalar_out[1] = potdiff;
-  }
+// q_i = (S.b)_i + potdiff * setq_i (+ qinit_i): fix_conp.cpp:1153-1158
+__global__ void __launch_bounds__(256)
+finalize_q_kernel(int n, const double *__restrict__ sb, const double *__restrict__ setq,
+                  const double *__restrict__ qinit, const double *__restrict__ scal, double *__restrict__ q_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double q = sb[i] + scal[1] * setq[i];
+  if (qinit) q += qinit[i];
+  q_out[i] = q;
 }
 
 }  // namespace
 
 int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int ncols_pad, const double *b,
-                double *out, int num_sms) {
+                double *out, int num_sms, const ChargeEpilogue *ep) {
   if (nrows <= 0) return 0;
   static bool attr_set = false;
   const size_t smem = sizeof(Smem);
@@ -266,17 +316,25 @@ int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int nc
     attr_set = true;
   }
   int grid = num_sms < nrows ? num_sms : nrows;
-  gemv_tma_kernel<<<grid, THREADS, smem, s>>>(S, pitch, nrows, ncols_pad, b, out);
+  ChargeEpilogue e;
+  if (ep) e = *ep;
+  else { memset(&e, 0, sizeof(e)); }
+  gemv_tma_kernel<<<grid, THREADS, smem, s>>>(S, pitch, nrows, ncols_pad, b, out, e);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int launch_update_charge(cudaStream_t s, int variant, int n, const double *sb, const double *setq,
-                         const double *qinit, const int *side, const double *setz, double totsetq, double value,
-                         int one_electrode, const double *dipole_dev, double lz, double vmult, double *q_out,
-                         double *scalar_out) {
-  update_charge_kernel<<<1, 1024, 0, s>>>(variant, n, sb, setq, qinit, side, setz, totsetq, value, one_electrode,
-                                          dipole_dev, lz, vmult, q_out, scalar_out);
+int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep) {
+  int grid = (ep.n + UC_THREADS * 4 - 1) / (UC_THREADS * 4);
+  grid = grid < 1 ? 1 : (grid > 128 ? 128 : grid);
+  update_charge_kernel<<<grid, UC_THREADS, 0, s>>>(ep);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_finalize_q(cudaStream_t s, int n, const double *sb, const double *setq, const double *qinit,
+                      const double *scal, double *q_out) {
+  finalize_q_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, sb, setq, qinit, scal, q_out);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -11,7 +11,6 @@ namespace conp {
 
 namespace {
 
-constexpr double MY_PIS = 1.77245385090551602729;
 
 __global__ void __launch_bounds__(256)
 a_finish_kernel(int row_begin, int row_end, int n, double *__restrict__ A, size_t pitch, double diag_kspace,

@@ -1,5 +1,4 @@
-// Real-space electrode<->point-charge kernels and the cell binning that
-// replaces LAMMPS' neighbour lists on the device.
+// Real-space electrode<->point-charge kernels.
 //
 //   pair_b         FixConp::blist_coul_cal        fix_conp.cpp:1281-1365
 //   pair_A         FixConp::alist_coul_cal        fix_conp.cpp:1209-1279
@@ -8,13 +7,17 @@
 //
 // The pair set is geometric (rsq < cutsq[it][jt] and rsq < cut_coulsq,
 // fix_conp.cpp:1333-1334) over *all* periodic images, which is what LAMMPS'
-// ghost atoms provide.  Point charges are counting-sorted into a uniform
-// cell grid every step; one warp owns one electrode atom, lanes stride the
-// x-contiguous cell runs (coalesced 32-byte PosQ loads), and the candidates
-// that pass the distance test are compacted through a per-warp shared-memory
-// queue so the expensive FP64 erfc evaluation always runs on full warps.
+// ghost atoms provide.  Point charges are counting-sorted into a uniform cell
+// grid every step (this also gives the PPPM spread its memory locality);
+// electrode atoms never move and are sorted once at setup on the host.  One
+// warp owns one electrode row, lanes stride the x-contiguous cell runs
+// (coalesced 32-byte loads), rows of cells are culled against the cut-off
+// sphere, and the candidates that pass the distance test are compacted
+// through a per-warp shared-memory queue so the FP64 erfc evaluation always
+// runs on full warps.  The row sum stays in registers: no atomics for b.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 namespace conp {
@@ -54,7 +57,7 @@ __device__ __forceinline__ double ferfcr_sqrt(double a2_r2) {
 
 enum { MODE_B = 0, MODE_A = 1 };
 
-// dudq of fix_conp.cpp:1263-1264 / 1335-1336
+// dudq of fix_conp.cpp:1263-1264 / 1335-1336; (it, jt) = (electrode type, partner type)
 template <int MODE>
 __device__ __forceinline__ double dudq_pair(const PairTables &pt, double rsq, int it, int jt) {
   double v = erfcr_sqrt(pt.g_ewald * pt.g_ewald * rsq) * pt.g_ewald;
@@ -87,8 +90,9 @@ __device__ __forceinline__ double wrap_coord(const CellGrid &g, int a, double x)
 }
 
 // ---------------------------------------------------------------------------
-// binning
+// per-step counting sort of the point charges
 // ---------------------------------------------------------------------------
+// pack: raw LAMMPS positions -> wrapped PosQ + type, sum(q z), cell histogram
 __global__ void __launch_bounds__(256)
 pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int *__restrict__ idx,
                   const double *__restrict__ q, const int *__restrict__ type, PosQ *__restrict__ packed,
@@ -114,7 +118,6 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
       slot[j] = atomicAdd(&cell_count[cell], 1);
     }
   }
-  // block reduction of q*z
   __shared__ double sh[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) qz += __shfl_xor_sync(0xffffffffu, qz, o);
@@ -149,7 +152,6 @@ cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict
   const int a = min(t * per, ncells), b = min(a + per, ncells);
   int sum = 0;
   for (int c = a; c < b; ++c) sum += cell_count[c];
-  // block exclusive scan of `sum`
   const int lane = t & 31, warp = t >> 5;
   int incl = sum;
 #pragma unroll
@@ -167,7 +169,7 @@ cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict
       const int v = __shfl_up_sync(0xffffffffu, wi, o);
       if (lane >= o) wi += v;
     }
-    sh[lane] = wi - w;  // exclusive warp offsets
+    sh[lane] = wi - w;
     if (lane == 31) sh[32] = wi;
   }
   __syncthreads();
@@ -189,56 +191,52 @@ cell_scatter_kernel(int m, const PosQ *__restrict__ packed, const int *__restric
   const int d = cell_start[cell_of[j]] + slot[j];
   sorted[d] = packed[j];
   sorted_type[d] = type[j];
-  if (sorted_src) sorted_src[d] = j;
+  sorted_src[d] = j;
+}
+
+// near list over the gathered charges: warp-aggregated append
+__global__ void __launch_bounds__(256)
+near_list_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, const unsigned char *__restrict__ near_mask,
+                 int *__restrict__ near_list, int *__restrict__ near_count) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool near = false;
+  if (j < m) {
+    const PosQ p = packed[j];
+    const int cell = (cell_coord(g, 2, p.z) * g.nc[1] + cell_coord(g, 1, p.y)) * g.nc[0] + cell_coord(g, 0, p.x);
+    near = near_mask[cell] != 0 && p.q != 0.0;
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, near);
+  if (mask == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(near_count, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (near) near_list[base + __popc(mask & ((1u << lane) - 1u))] = j;
 }
 
 // ---------------------------------------------------------------------------
-// warp-per-electrode-atom traversal with candidate compaction
+// warp traversal of the static electrode cell grid around a point
 // ---------------------------------------------------------------------------
 constexpr int PAIR_WARPS = 8;
 constexpr int QCAP = 64;
 
 struct WarpQueue {
   double rsq[QCAP];
-  double q[QCAP];
-  int j[QCAP];
-  int t[QCAP];
+  double aux[QCAP];  // MODE_B: partner charge
+  int i[QCAP];       // MODE_A: partner electrode index
+  int t[QCAP];       // partner type
 };
 
-template <int MODE>
-__device__ __forceinline__ void consume(const PairTables &pt, const WarpQueue &wq, int e, int it, int i_global,
-                                        double &acc, double *A_row) {
-  const double rsq = wq.rsq[e];
-  const double d = dudq_pair<MODE>(pt, rsq, it, wq.t[e]);
-  if (MODE == MODE_B) {
-    acc = fma(wq.q[e], d, acc);
-  } else {
-    (void)i_global;
-    atomicAdd(A_row + wq.j[e], d);
-  }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double *__restrict__ ex,
-            const double *__restrict__ ey, const double *__restrict__ ez, const int *__restrict__ etype,
-            const PosQ *__restrict__ sorted, const int *__restrict__ sorted_type,
-            const int *__restrict__ sorted_src, const int *__restrict__ cell_start, double *__restrict__ out,
-            size_t pitch) {
-  __shared__ WarpQueue queues[PAIR_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = row_begin + blockIdx.x * PAIR_WARPS + warp;
-  if (i >= row_end) return;
-  WarpQueue &wq = queues[warp];
-  const double xi = ex[i], yi = ey[i], zi = ez[i];
-  const int it = etype[i];
-  const double *cut_row = pt.cuteff + it * (pt.ntypes + 1);
+// Visit, warp-cooperatively, every electrode atom image within sqrt(max cuteff)
+// of (xi,yi,zi).  F(lane-candidate) is called for all lanes of each chunk of 32
+// consecutive sorted electrode atoms: f(valid, e, shx, shy, shz).
+template <class F>
+__device__ __forceinline__ void traverse(const CellGrid &g, const int *__restrict__ cell_start, double xi,
+                                         double yi, double zi, int lane, F &&f) {
   const double rc = g.rc;
-  double acc = 0.0;
-  int qn = 0;
-  double *A_row = (MODE == MODE_A) ? out + (size_t)(i - row_begin) * pitch : nullptr;
-  const unsigned lt_mask = (1u << lane) - 1u;
-
+  // FP32 is enough for the conservative "row of cells beyond the cut-off sphere" test
+  const float csy = (float)(g.prd[1] / g.nc[1]), csz = (float)(g.prd[2] / g.nc[2]);
+  const float rc2f = (float)(rc * rc) * 1.0001f;
   for (int sz = -g.smax[2]; sz <= g.smax[2]; ++sz) {
     const double shz = sz * g.prd[2];
     int lz = (int)floor((zi - shz - rc - g.lo[2]) * g.cinv[2]);
@@ -260,139 +258,155 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
         if (g.periodic[0] && (hx < 0 || lx > g.nc[0] - 1)) continue;
         lx = max(0, min(lx, g.nc[0] - 1));
         hx = max(0, min(hx, g.nc[0] - 1));
-        const bool zero_shift = (sx == 0 && sy == 0 && sz == 0);
+        const float fy = (float)(yi - shy - g.lo[1]), fz = (float)(zi - shz - g.lo[2]);
         for (int cz = lz; cz <= hz; ++cz) {
+          float dz = fmaxf(fmaxf(cz * csz - fz, fz - (cz + 1) * csz), 0.0f);
+          if (!g.periodic[2] && (cz == 0 || cz == g.nc[2] - 1)) dz = 0.0f;  // edge cells hold clamped atoms
           for (int cy = ly; cy <= hy; ++cy) {
+            float dy = fmaxf(fmaxf(cy * csy - fy, fy - (cy + 1) * csy), 0.0f);
+            if (!g.periodic[1] && (cy == 0 || cy == g.nc[1] - 1)) dy = 0.0f;
+            if (dy * dy + dz * dz > rc2f) continue;
             const int base = (cz * g.nc[1] + cy) * g.nc[0];
             const int jb = __ldg(cell_start + base + lx);
             const int je = __ldg(cell_start + base + hx + 1);
-            for (int j0 = jb; j0 < je; j0 += 32) {
-              const int j = j0 + lane;
-              bool pass = false;
-              double rsq = 0.0, qj = 0.0;
-              int jt = 0, jsrc = 0;
-              if (j < je) {
-                const PosQ p = sorted[j];
-                jt = sorted_type[j];
-                const double dx = xi - (p.x + shx);
-                const double dy = yi - (p.y + shy);
-                const double dz = zi - (p.z + shz);
-                rsq = dx * dx + dy * dy + dz * dz;
-                qj = p.q;
-                pass = rsq < __ldg(cut_row + jt);
-                if (MODE == MODE_A) {
-                  jsrc = sorted_src[j];
-                  if (zero_shift && jsrc == i) pass = false;  // no self pair; self images are kept
-                }
-              }
-              const unsigned mask = __ballot_sync(0xffffffffu, pass);
-              if (pass) {
-                const int pos = qn + __popc(mask & lt_mask);
-                wq.rsq[pos] = rsq;
-                wq.q[pos] = qj;
-                wq.j[pos] = jsrc;
-                wq.t[pos] = jt;
-              }
-              qn += __popc(mask);
-              if (qn >= 32) {
-                __syncwarp();
-                consume<MODE>(pt, wq, qn - 32 + lane, it, i, acc, A_row);
-                qn -= 32;
-                __syncwarp();
-              }
-            }
+            for (int j0 = jb; j0 < je; j0 += 32) f(j0 + lane < je, j0 + lane, shx, shy, shz);
           }
         }
       }
     }
   }
+}
+
+// One warp per electrode row i of [row_begin, row_end).
+// MODE_B: targets = cell-sorted point charges; b_real[i] = -sum_j q_j dudq (fix_conp.cpp:1339)
+// MODE_A: targets = cell-sorted electrode atoms; A[i][j] += dudq (fix_conp.cpp:1270), self images kept
+template <int MODE>
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 4)
+pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double *__restrict__ ex,
+            const double *__restrict__ ey, const double *__restrict__ ez, const int *__restrict__ etype,
+            const int *__restrict__ cell_start,
+            const PosQ *__restrict__ sorted, const int *__restrict__ sorted_type,  // MODE_B targets
+            const EPos *__restrict__ esorted,                                      // MODE_A targets
+            double *__restrict__ out, size_t pitch) {
+  __shared__ WarpQueue queues[PAIR_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = row_begin + blockIdx.x * PAIR_WARPS + warp;
+  if (i >= row_end) return;
+  WarpQueue &wq = queues[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const double xi = ex[i], yi = ey[i], zi = ez[i];
+  const int it = etype[i];
+  const double *cut_row = pt.cuteff + it * (pt.ntypes + 1);
+  double *A_row = (MODE == MODE_A) ? out + (size_t)(i - row_begin) * pitch : nullptr;
+  double acc = 0.0;
+  int qn = 0;
+  auto consume = [&](int e) {
+    const double d = dudq_pair<MODE>(pt, wq.rsq[e], it, wq.t[e]);
+    if (MODE == MODE_B) acc = fma(wq.aux[e], d, acc);
+    else atomicAdd(A_row + wq.i[e], d);
+  };
+  traverse(g, cell_start, xi, yi, zi, lane, [&](bool valid, int k, double shx, double shy, double shz) {
+    bool pass = false;
+    double rsq = 0.0, qj = 0.0;
+    int jt = 0, jidx = 0;
+    if (valid) {
+      double px, py, pz;
+      if (MODE == MODE_B) {
+        const PosQ p = sorted[k];
+        px = p.x; py = p.y; pz = p.z; qj = p.q;
+        jt = sorted_type[k];
+      } else {
+        const EPos e = esorted[k];
+        px = e.x; py = e.y; pz = e.z;
+        jt = e.type; jidx = e.idx;
+      }
+      const double dx = xi - (px + shx), dy = yi - (py + shy), dz = zi - (pz + shz);
+      rsq = dx * dx + dy * dy + dz * dz;
+      pass = rsq < __ldg(cut_row + jt);
+      if (MODE == MODE_A && jidx == i && shx == 0.0 && shy == 0.0 && shz == 0.0) pass = false;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, pass);
+    if (pass) {
+      const int pos = qn + __popc(mask & lt_mask);
+      wq.rsq[pos] = rsq; wq.aux[pos] = qj; wq.i[pos] = jidx; wq.t[pos] = jt;
+    }
+    qn += __popc(mask);
+    if (qn >= 32) {
+      __syncwarp();
+      consume(qn - 32 + lane);
+      qn -= 32;
+      __syncwarp();
+    }
+  });
   __syncwarp();
-  if (lane < qn) consume<MODE>(pt, wq, lane, it, i, acc, A_row);
+  if (lane < qn) consume(lane);
   if (MODE == MODE_B) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[i] = -acc;  // m[elei] -= q[j]*dudq, fix_conp.cpp:1339
+    if (lane == 0) out[i] = -acc;
   }
 }
 
-// post-force Gaussian correction; hits are rare (eta^2 r^2 < 5.8), so no queue
+// post-force Gaussian correction; one warp per near charge, hits are rare
+// (eta^2 r^2 < 5.8, fix_conp.cpp:1418-1419), so no queue.  The charge gets
+// -del*forcecoul with del = electrode - charge (fix_conp.cpp:1425-1434).
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_postforce_kernel(CellGrid g, PairTables pt, double qqrd2e, int row_begin, int row_end,
-                      const double *__restrict__ ex, const double *__restrict__ ey,
-                      const double *__restrict__ ez, const int *__restrict__ etype,
-                      const double *__restrict__ q_ele, const PosQ *__restrict__ sorted,
-                      const int *__restrict__ sorted_type, const int *__restrict__ sorted_src,
-                      const int *__restrict__ cell_start, const double *__restrict__ cutsq_listed,
-                      double *__restrict__ f_packed, double *__restrict__ energies) {
+pair_postforce_kernel(CellGrid g, PairTables pt, double qqrd2e, const EPos *__restrict__ esorted,
+                      const int *__restrict__ cell_start, const double *__restrict__ q_ele,
+                      const PosQ *__restrict__ packed, const int *__restrict__ packed_type,
+                      const int *__restrict__ near_list, const int *__restrict__ near_count,
+                      const double *__restrict__ cutsq_listed, double *__restrict__ f_packed,
+                      double *__restrict__ energies) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = row_begin + blockIdx.x * PAIR_WARPS + warp;
+  const int nwarps_total = gridDim.x * PAIR_WARPS;
+  const int nwork = __ldg(near_count);
   double ecoul = 0.0, v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
-  if (i < row_end) {
-    const double xi = ex[i], yi = ey[i], zi = ez[i], qi = q_ele[i];
-    const int it = etype[i];
-    const double *cut_row = cutsq_listed + it * (pt.ntypes + 1);
-    const double rc = g.rc;
-    for (int sz = -g.smax[2]; sz <= g.smax[2]; ++sz) {
-      const double shz = sz * g.prd[2];
-      int lz = (int)floor((zi - shz - rc - g.lo[2]) * g.cinv[2]);
-      int hz = (int)floor((zi - shz + rc - g.lo[2]) * g.cinv[2]);
-      if (g.periodic[2] && (hz < 0 || lz > g.nc[2] - 1)) continue;
-      lz = max(0, min(lz, g.nc[2] - 1));
-      hz = max(0, min(hz, g.nc[2] - 1));
-      for (int sy = -g.smax[1]; sy <= g.smax[1]; ++sy) {
-        const double shy = sy * g.prd[1];
-        int ly = (int)floor((yi - shy - rc - g.lo[1]) * g.cinv[1]);
-        int hy = (int)floor((yi - shy + rc - g.lo[1]) * g.cinv[1]);
-        if (g.periodic[1] && (hy < 0 || ly > g.nc[1] - 1)) continue;
-        ly = max(0, min(ly, g.nc[1] - 1));
-        hy = max(0, min(hy, g.nc[1] - 1));
-        for (int sx = -g.smax[0]; sx <= g.smax[0]; ++sx) {
-          const double shx = sx * g.prd[0];
-          int lx = (int)floor((xi - shx - rc - g.lo[0]) * g.cinv[0]);
-          int hx = (int)floor((xi - shx + rc - g.lo[0]) * g.cinv[0]);
-          if (g.periodic[0] && (hx < 0 || lx > g.nc[0] - 1)) continue;
-          lx = max(0, min(lx, g.nc[0] - 1));
-          hx = max(0, min(hx, g.nc[0] - 1));
-          for (int cz = lz; cz <= hz; ++cz)
-            for (int cy = ly; cy <= hy; ++cy) {
-              const int base = (cz * g.nc[1] + cy) * g.nc[0];
-              const int jb = cell_start[base + lx], je = cell_start[base + hx + 1];
-              for (int j = jb + lane; j < je; j += 32) {
-                const PosQ p = sorted[j];
-                const int jt = sorted_type[j];
-                const double dx = xi - (p.x + shx), dy = yi - (p.y + shy), dz = zi - (p.z + shz);
-                const double rsq = dx * dx + dy * dy + dz * dz;
-                if (rsq < cut_row[jt]) {                      // fix_conp.cpp:1417
-                  const double etarij2 = pt.eta * pt.eta * rsq;  // :1418
-                  if (etarij2 < ERFC_MAX) {                    // :1419 (sic: not squared)
-                    const double prefactor = qqrd2e * qi * p.q;
-                    double pf, pp;
-                    if (pt.pairmode == CONP_PAIR_EHGO) {
-                      const int ij = it * (pt.ntypes + 1) + jt;
-                      const double etaij = pt.eta_ij[ij], foij = pt.fo_ij[ij];
-                      const double e2 = etaij * etaij * rsq;
-                      pf = e2 * foij * exp(-0.5 * e2) - ferfcr_sqrt(e2) * etaij;  // ehgo_force :1568-1573
-                      pp = foij * exp(-0.5 * e2) - erfcr_sqrt(e2) * etaij;       // ehgo_potential
-                    } else {
-                      pf = -ferfcr_sqrt(etarij2) * pt.eta;  // eta_force :1477-1480
-                      pp = -erfcr_sqrt(etarij2) * pt.eta;   // eta_potential
-                    }
-                    const double forcecoul = prefactor * pf;
-                    const double fpair = forcecoul / rsq;
-                    // del = electrode - electrolyte; the electrolyte atom gets -del*forcecoul (:1425-1434)
-                    const int src = sorted_src[j];
-                    atomicAdd(f_packed + 3 * (size_t)src, -dx * forcecoul);
-                    atomicAdd(f_packed + 3 * (size_t)src + 1, -dy * forcecoul);
-                    atomicAdd(f_packed + 3 * (size_t)src + 2, -dz * forcecoul);
-                    ecoul += prefactor * pp;  // ev_tally ecoul :1435-1436
-                    v0 += dx * dx * fpair; v1 += dy * dy * fpair; v2 += dz * dz * fpair;
-                    v3 += dx * dy * fpair; v4 += dx * dz * fpair; v5 += dy * dz * fpair;
-                  }
-                }
-              }
-            }
+  for (int w = blockIdx.x * PAIR_WARPS + warp; w < nwork; w += nwarps_total) {
+    const int j = near_list[w];
+    const PosQ p = packed[j];
+    const int jt = packed_type[j];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    traverse(g, cell_start, p.x, p.y, p.z, lane, [&](bool valid, int k, double shx, double shy, double shz) {
+      if (!valid) return;
+      const EPos e = esorted[k];
+      // del = x_electrode - x_charge (the reference's delx with i = electrode)
+      const double dx = (e.x + shx) - p.x, dy = (e.y + shy) - p.y, dz = (e.z + shz) - p.z;
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      const int it = e.type;
+      if (rsq < __ldg(cutsq_listed + it * (pt.ntypes + 1) + jt)) {  // fix_conp.cpp:1417
+        const double etarij2 = pt.eta * pt.eta * rsq;                // :1418
+        if (etarij2 < ERFC_MAX) {                                    // :1419 (sic: not squared)
+          const double prefactor = qqrd2e * q_ele[e.idx] * p.q;
+          double pf, pp;
+          if (pt.pairmode == CONP_PAIR_EHGO) {
+            const int ij = it * (pt.ntypes + 1) + jt;
+            const double etaij = pt.eta_ij[ij], foij = pt.fo_ij[ij];
+            const double e2 = etaij * etaij * rsq;
+            pf = e2 * foij * exp(-0.5 * e2) - ferfcr_sqrt(e2) * etaij;  // ehgo_force :1568-1573
+            pp = foij * exp(-0.5 * e2) - erfcr_sqrt(e2) * etaij;       // ehgo_potential
+          } else {
+            pf = -ferfcr_sqrt(etarij2) * pt.eta;  // eta_force :1477-1480
+            pp = -erfcr_sqrt(etarij2) * pt.eta;   // eta_potential
+          }
+          const double forcecoul = prefactor * pf;
+          const double fpair = forcecoul / rsq;
+          fx -= dx * forcecoul; fy -= dy * forcecoul; fz -= dz * forcecoul;
+          ecoul += prefactor * pp;  // ev_tally ecoul :1435-1436
+          v0 += dx * dx * fpair; v1 += dy * dy * fpair; v2 += dz * dz * fpair;
+          v3 += dx * dy * fpair; v4 += dx * dz * fpair; v5 += dy * dz * fpair;
         }
       }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      fx += __shfl_xor_sync(0xffffffffu, fx, o);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o);
+      fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (lane == 0 && (fx != 0.0 || fy != 0.0 || fz != 0.0)) {
+      atomicAdd(f_packed + 3 * (size_t)j, fx);  // multi-GPU: each rank adds its own rows' share
+      atomicAdd(f_packed + 3 * (size_t)j + 1, fy);
+      atomicAdd(f_packed + 3 * (size_t)j + 2, fz);
     }
   }
   double vals[7] = {ecoul, v0, v1, v2, v3, v4, v5};
@@ -407,6 +421,9 @@ pair_postforce_kernel(CellGrid g, PairTables pt, double qqrd2e, int row_begin, i
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
 CellGrid make_cell_grid(const double lo[3], const double prd[3], const int periodic[3], double rc) {
   CellGrid g;
   long long tot = 1;
@@ -422,7 +439,6 @@ CellGrid make_cell_grid(const double lo[3], const double prd[3], const int perio
     g.smax[a] = periodic[a] ? (int)std::ceil(rc / prd[a]) + 1 : 0;
     tot *= nc;
   }
-  // bound the cell count (memory for cell_start and the single-block scan)
   while (tot > (1LL << 22)) {
     int amax = 0;
     for (int a = 1; a < 3; ++a)
@@ -435,6 +451,76 @@ CellGrid make_cell_grid(const double lo[3], const double prd[3], const int perio
   g.rc = rc;
   g.ncells = (int)tot;
   return g;
+}
+
+namespace {
+inline double h_wrap(const CellGrid &g, int a, double x) {
+  if (g.periodic[a]) x -= std::floor((x - g.lo[a]) / g.prd[a]) * g.prd[a];
+  return x;
+}
+inline int h_cell(const CellGrid &g, int a, double x) {
+  int k = (int)std::floor((x - g.lo[a]) * g.cinv[a]);
+  return std::max(0, std::min(k, g.nc[a] - 1));
+}
+}  // namespace
+
+// Counting sort of electrode rows [begin, end) into grid g (host; electrodes are static).
+void build_electrode_cells(const CellGrid &g, int begin, int end, const double *xyz, const int *type,
+                           std::vector<EPos> &sorted, std::vector<int> &cell_start) {
+  const int n = end - begin;
+  cell_start.assign((size_t)g.ncells + 1, 0);
+  std::vector<int> cell(std::max(n, 0));
+  std::vector<EPos> tmp(std::max(n, 0));
+  for (int k = 0; k < n; ++k) {
+    const int i = begin + k;
+    EPos e;
+    e.x = h_wrap(g, 0, xyz[3 * (size_t)i]);
+    e.y = h_wrap(g, 1, xyz[3 * (size_t)i + 1]);
+    e.z = h_wrap(g, 2, xyz[3 * (size_t)i + 2]);
+    e.idx = i;
+    e.type = type[i];
+    tmp[k] = e;
+    cell[k] = (h_cell(g, 2, e.z) * g.nc[1] + h_cell(g, 1, e.y)) * g.nc[0] + h_cell(g, 0, e.x);
+    cell_start[(size_t)cell[k] + 1]++;
+  }
+  for (int c = 0; c < g.ncells; ++c) cell_start[(size_t)c + 1] += cell_start[c];
+  sorted.resize(std::max(n, 0));
+  std::vector<int> cursor(cell_start.begin(), cell_start.end() - 1);
+  for (int k = 0; k < n; ++k) sorted[cursor[cell[k]]++] = tmp[k];
+}
+
+// Cells from which a point charge can reach an electrode atom of rows
+// [begin, end): every cell a traversal from inside it could need is covered
+// by marking, for each electrode atom, the cells overlapping its rc-sphere's
+// bounding box (all periodic shifts), dilated by one cell against rounding.
+void build_near_mask(const CellGrid &g, int begin, int end, const double *xyz, std::vector<unsigned char> &mask) {
+  mask.assign((size_t)g.ncells, 0);
+  for (int i = begin; i < end; ++i) {
+    int lo[3], hi[3];
+    bool all[3];
+    for (int a = 0; a < 3; ++a) {
+      const double x = h_wrap(g, a, xyz[3 * (size_t)i + a]);
+      lo[a] = (int)std::floor((x - g.rc - g.lo[a]) * g.cinv[a]) - 1;
+      hi[a] = (int)std::floor((x + g.rc - g.lo[a]) * g.cinv[a]) + 1;
+      all[a] = (hi[a] - lo[a] + 1 >= g.nc[a]);
+    }
+    for (int cz = lo[2]; cz <= hi[2]; ++cz) {
+      int wz = cz;
+      if (g.periodic[2]) { wz %= g.nc[2]; if (wz < 0) wz += g.nc[2]; }
+      else if (wz < 0 || wz >= g.nc[2]) { if (all[2]) continue; wz = std::max(0, std::min(wz, g.nc[2] - 1)); }
+      for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+        int wy = cy;
+        if (g.periodic[1]) { wy %= g.nc[1]; if (wy < 0) wy += g.nc[1]; }
+        else if (wy < 0 || wy >= g.nc[1]) { if (all[1]) continue; wy = std::max(0, std::min(wy, g.nc[1] - 1)); }
+        for (int cx = lo[0]; cx <= hi[0]; ++cx) {
+          int wx = cx;
+          if (g.periodic[0]) { wx %= g.nc[0]; if (wx < 0) wx += g.nc[0]; }
+          else if (wx < 0 || wx >= g.nc[0]) { if (all[0]) continue; wx = std::max(0, std::min(wx, g.nc[0] - 1)); }
+          mask[((size_t)wz * g.nc[1] + wy) * g.nc[0] + wx] = 1;
+        }
+      }
+    }
+  }
 }
 
 int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
@@ -470,38 +556,45 @@ int launch_cell_scatter(cudaStream_t s, int m, const PosQ *packed, const int *ty
   return 1;
 }
 
+int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const unsigned char *near_mask,
+                     int *near_list, int *near_count) {
+  if (m <= 0) return 0;
+  near_list_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, packed, near_mask, near_list, near_count);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
                   const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
                   const int *sorted_type, const int *cell_start, double *b_real) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
   pair_kernel<MODE_B><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, row_begin, row_end, ex, ey, ez, etype, sorted, sorted_type, nullptr, cell_start, b_real, 0);
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, sorted, sorted_type, nullptr, b_real, 0);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
-                  const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const int *sorted_src, const int *cell_start, double *A_rows,
-                  size_t pitch) {
+int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
+                  const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
+                  const double *ez, const int *etype, double *A_rows, size_t pitch) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
   pair_kernel<MODE_A><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, row_begin, row_end, ex, ey, ez, etype, sorted, sorted_type, sorted_src, cell_start, A_rows, pitch);
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, nullptr, nullptr, esorted, A_rows, pitch);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e, int row_begin,
-                          int row_end, const double *ex, const double *ey, const double *ez, const int *etype,
-                          const double *q_ele, const PosQ *sorted, const int *sorted_type, const int *sorted_src,
-                          const int *cell_start, const double *cutsq_listed, double *f_packed, double *energies) {
-  const int n = row_end - row_begin;
-  if (n <= 0) return 0;
-  pair_postforce_kernel<<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, qqrd2e, row_begin, row_end, ex, ey, ez, etype, q_ele, sorted, sorted_type, sorted_src, cell_start,
-      cutsq_listed, f_packed, energies);
+int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e,
+                          const EPos *esorted, const int *cell_start, const double *q_ele, const PosQ *packed,
+                          const int *packed_type, const int *near_list, const int *near_count, int max_near,
+                          const double *cutsq_listed, double *f_packed, double *energies, int num_sms) {
+  if (max_near <= 0) return 0;
+  int grid = std::min((max_near + PAIR_WARPS - 1) / PAIR_WARPS, num_sms * 8);
+  pair_postforce_kernel<<<grid, PAIR_WARPS * 32, 0, s>>>(g, pt, qqrd2e, esorted, cell_start, q_ele, packed,
+                                                         packed_type, near_list, near_count, cutsq_listed,
+                                                         f_packed, energies);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -46,7 +46,9 @@ __device__ __forceinline__ double rho1d(const double *__restrict__ rc, int order
 }
 
 // one thread per (atom, z-plane n, y-row m); the thread adds its `order`
-// x-consecutive mesh points with red.global.add.f64
+// x-consecutive mesh points with red.global.add.f64.  (A point-per-thread
+// mapping that puts the `order` x-neighbours in adjacent lanes was measured 3x
+// slower: same-sector atomics of one warp instruction serialise in L2.)
 __global__ void __launch_bounds__(256)
 spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, const PosQ *__restrict__ atoms,
               double *__restrict__ brick, int *__restrict__ range_flag) {
@@ -93,15 +95,23 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
 }
 
 // z-convolution with the tabulated kernel.  Block = ZC_COLS consecutive
-// (kx,ky) columns (128 B of the plane-major spectra), one warp per column,
-// lanes = output planes.  rho^ of the block is staged in shared memory.
+// (kx,ky) columns (128 B of the plane-major spectra), one warp per column;
+// for each output plane the lanes stride the input planes of the window
+// (coalesced table reads, every load of a run in flight at once) and the
+// partial sums are combined with warp shuffles.  rho^ of the block is staged
+// in shared memory.
+// For k_xy != 0 the kernel decays like the Ewald Gaussian / exp(-|k_xy| |dz|):
+// krad[col] bounds the circular |d| beyond which |K| is below ~1e-18 of the
+// column maximum (measured on the table at setup, see ctx.cu), and only input
+// planes inside that window are visited; the dropped tail is below the
+// rounding level of the reference's own FFTs.
 constexpr int ZC_COLS = 8;
 
 template <bool REALK>
 __global__ void __launch_bounds__(ZC_COLS * 32)
 zconv_kernel(int ncol, int nz, int nzi, int zin_lo, int nzo, const int *__restrict__ zout_list,
-             const double2 *__restrict__ rhat, const double *__restrict__ Kr, const double2 *__restrict__ Kc,
-             double2 *__restrict__ uhat) {
+             const int *__restrict__ krad, const double2 *__restrict__ rhat, const double *__restrict__ Kr,
+             const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
   extern __shared__ __align__(16) unsigned char zc_smem[];
   double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzi][ZC_COLS]
   const int c0 = blockIdx.x * ZC_COLS;
@@ -114,39 +124,47 @@ zconv_kernel(int ncol, int nz, int nzi, int zin_lo, int nzo, const int *__restri
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = c0 + w;
   if (c >= ncol) return;
-  for (int zo = lane; zo < nzo; zo += 32) {
-    // d = (zout - (zin_lo + zi)) mod nz, walked downwards with zi
-    int d = (zout_list[zo] - zin_lo) % nz;
-    if (d < 0) d += nz;
-    double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
-    if (REALK) {
-      const double *krow = Kr + (size_t)c * nz;
-      int zi = 0;
-      for (; zi + 1 < nzi; zi += 2) {
-        const double k0 = __ldg(krow + d);
-        d = d ? d - 1 : nz - 1;
-        const double k1 = __ldg(krow + d);
-        d = d ? d - 1 : nz - 1;
-        const double2 r0 = rh[zi * ZC_COLS + w], r1 = rh[(zi + 1) * ZC_COLS + w];
-        ar0 = fma(k0, r0.x, ar0); ai0 = fma(k0, r0.y, ai0);
-        ar1 = fma(k1, r1.x, ar1); ai1 = fma(k1, r1.y, ai1);
-      }
-      if (zi < nzi) {
-        const double k0 = __ldg(krow + d);
-        const double2 r0 = rh[zi * ZC_COLS + w];
-        ar0 = fma(k0, r0.x, ar0); ai0 = fma(k0, r0.y, ai0);
-      }
-    } else {
-      const double2 *krow = Kc + (size_t)c * nz;
-      for (int zi = 0; zi < nzi; ++zi) {
-        const double2 k = krow[d];
-        d = d ? d - 1 : nz - 1;
+  const int R = krad[c];
+  const double *krow = REALK ? Kr + (size_t)c * nz : nullptr;
+  const double2 *kcrow = REALK ? nullptr : Kc + (size_t)c * nz;
+  for (int zo = 0; zo < nzo; ++zo) {
+    // a = position of the output plane on the ring, in input-plane coordinates
+    int a = (__ldg(zout_list + zo) - zin_lo) % nz;
+    if (a < 0) a += nz;
+    double ar = 0.0, ai = 0.0;
+    // input planes z0..z1 (inclusive); table index d = (a - zi) mod nz
+    auto run = [&](int z0, int z1) {
+      z0 = max(z0, 0);
+      z1 = min(z1, nzi - 1);
+      for (int zi = z0 + lane; zi <= z1; zi += 32) {
+        int d = a - zi;
+        d += (d < 0) ? nz : 0;
+        d -= (d >= nz) ? nz : 0;
         const double2 r = rh[zi * ZC_COLS + w];
-        ar0 = fma(k.x, r.x, ar0); ar0 = fma(-k.y, r.y, ar0);
-        ai0 = fma(k.x, r.y, ai0); ai0 = fma(k.y, r.x, ai0);
+        if (REALK) {
+          const double k = __ldg(krow + d);
+          ar = fma(k, r.x, ar);
+          ai = fma(k, r.y, ai);
+        } else {
+          const double2 k = kcrow[d];
+          ar = fma(k.x, r.x, ar); ar = fma(-k.y, r.y, ar);
+          ai = fma(k.x, r.y, ai); ai = fma(k.y, r.x, ai);
+        }
       }
+    };
+    if (2 * R + 1 >= nz) {
+      run(0, nzi - 1);
+    } else {
+      run(a - R, a + R);                        // main window
+      if (a - R < 0) run(a - R + nz, nz - 1);   // wrapped from below
+      if (a + R >= nz) run(0, a + R - nz);      // wrapped from above
     }
-    uhat[(size_t)zo * ncol + c] = make_double2(ar0 + ar1, ai0 + ai1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ar += __shfl_xor_sync(0xffffffffu, ar, o);
+      ai += __shfl_xor_sync(0xffffffffu, ai, o);
+    }
+    if (lane == 0) uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
   }
 }
 
@@ -225,9 +243,14 @@ gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ 
   }
 }
 
+// electrode re-spread with the cached weights; one thread per (atom, n, m) row.
+// The new charge q_i = (S.b)_i + potdiff*setq_i (+qinit_i) (fix_conp.cpp:1153-1158)
+// is formed here from the epilogue scalars and stored by the atom's first thread.
 __global__ void __launch_bounds__(256)
 ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, const double *__restrict__ weights,
-                  const double *__restrict__ q_ele, double *__restrict__ brick) {
+                  const double *__restrict__ sb, const double *__restrict__ setq,
+                  const double *__restrict__ qinit, const double *__restrict__ scal, double *__restrict__ q_out,
+                  double *__restrict__ brick) {
   const int order = g.order;
   const int per_atom = order * order;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,7 +260,10 @@ ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, cons
   const int n = nm / order, m = nm - n * order;
   const int nx = part2grid[3 * i], ny = part2grid[3 * i + 1], nz = part2grid[3 * i + 2];
   const double *w = weights + (size_t)i * 3 * order;
-  const double z0 = g.delvolinv * q_ele[i];  // pppm_conp.cpp:411
+  double qi = sb[i] + scal[1] * setq[i];
+  if (qinit) qi += qinit[i];
+  if (nm == 0) q_out[i] = qi;
+  const double z0 = g.delvolinv * qi;  // pppm_conp.cpp:411
   const double x0 = z0 * w[2 * order + n] * w[order + m];
   const int zo = g.zmap[wrapi(n + g.nlower + nz, g.nz)];
   const int my = wrapi(m + g.nlower + ny, g.ny);
@@ -273,8 +299,8 @@ int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, co
 }
 
 int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
-                      const cufftDoubleComplex *rhat, const double *Kr, const cufftDoubleComplex *Kc,
-                      cufftDoubleComplex *uhat) {
+                      const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
+                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
   const size_t smem = sizeof(double2) * (size_t)nzi * ZC_COLS;
   static size_t smem_set_r = 0, smem_set_c = 0;
   const int grid = (ncol + ZC_COLS - 1) / ZC_COLS;
@@ -283,14 +309,14 @@ int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set_r = smem;
     }
-    zconv_kernel<true><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list,
+    zconv_kernel<true><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list, krad,
                                                         (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
   } else {
     if (smem > smem_set_c) {
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set_c = smem;
     }
-    zconv_kernel<false><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list,
+    zconv_kernel<false><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list, krad,
                                                          (const double2 *)rhat, nullptr, (const double2 *)Kc,
                                                          (double2 *)uhat);
   }
@@ -326,10 +352,12 @@ int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int r
 }
 
 int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, const double *weights,
-                           const double *q_ele, double *brick) {
+                           const double *sb, const double *setq, const double *qinit, const double *scal,
+                           double *q_out, double *brick) {
   if (n <= 0) return 0;
   const long long threads = (long long)n * g.order * g.order;
-  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, part2grid, weights, q_ele, brick);
+  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, part2grid, weights, sb, setq, qinit,
+                                                                     scal, q_out, brick);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -229,7 +229,7 @@ def test_step_is_repeatable_and_tracks_moving_atoms():
         q_close(fix.pre_force(), ref.pre_force())
     qa = fix.pre_force()
     qb = fix.pre_force()
-    assert np.abs(qa - qb).max() <= 1e-13 * np.abs(qa).max()
+    assert np.abs(qa - qb).max() <= 1e-12 * np.abs(qa).max()  # atomics reorder sums
     fix.close()
 
 
