@@ -220,15 +220,16 @@ int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_
 int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, int *cell_of, int *slot,
                          int *cell_count);
 int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start);
-int launch_cell_scatter(cudaStream_t s, int m, const PosQ *packed, const int *type, const int *cell_of,
-                        const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type, int *sorted_src);
+int launch_cell_scatter(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const int *type,
+                        const int *cell_of, const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type,
+                        int *sorted_src, float4 *sorted_f);
 // charges sitting in a cell within reach of an electrode atom (near_count must be zeroed); post_force only
 int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const unsigned char *near_mask,
                      int *near_list, int *near_count);
 // b_real[i] = -sum_j q_j dudq(r_ij), rows [row_begin,row_end), against the cell-sorted point charges
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
                   const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const int *cell_start, double *b_real);
+                  const int *sorted_type, const float4 *sorted_f, const int *cell_start, double *b_real);
 int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
                   const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
                   const double *ez, const int *etype, double *A_rows, size_t pitch);
@@ -249,11 +250,13 @@ int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int 
                          const double *compact, double *full);
 int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
                             const double *ey, const double *ez, int *part2grid, double *weights);
-int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *part2grid,
+// wrapped stencil indices [n][3][order] (x, y, compact z plane) of the static electrode atoms; needs g.zmap
+int launch_pppm_ele_index(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, int *widx);
+int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *widx,
                          const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
                          double slab_pref /* 4 pi / V or 0 */, const double *b_real, double *b_kspace, double *b);
 // electrode re-spread; forms q_i = sb_i + potdiff*setq_i (+qinit_i) on the fly and stores it to q_out
-int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, const double *weights,
+int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,
                            const double *sb, const double *setq, const double *qinit, const double *scal,
                            double *q_out, double *brick);
 int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out);

@@ -72,6 +72,7 @@ struct conp_ctx {
   DevBuf<double> d_xraw, d_qraw;
   DevBuf<int> d_typeraw, d_idx;
   DevBuf<PosQ> d_packed, d_sorted;
+  DevBuf<float4> d_sortedf;
   DevBuf<int> d_ptype, d_stype, d_ssrc, d_cellof, d_slot, d_cellcount, d_cellstart, d_nearlist, d_nearcount;
   DevBuf<double> d_fpacked;
   // static electrode cell structures for the real-space kernels (own rows)
@@ -87,7 +88,7 @@ struct conp_ctx {
   std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
   std::vector<int> h_zout;              // output planes (sorted)
   DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
-  DevBuf<int> d_part2grid, d_flag, d_zmap, d_zout, d_krad;
+  DevBuf<int> d_part2grid, d_widx, d_flag, d_zmap, d_zout, d_krad;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
   bool plans = false, k_real = true;
@@ -229,7 +230,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   // ---- counting sort of the point charges: pack (+histogram, sum q z), scan, scatter ----
   CUDA_CHECK(cudaMemsetAsync(c->scal(2), 0, sizeof(double), s));
   const CellGrid &g = c->grid_b;
-  CUDA_CHECK(cudaMemsetAsync(c->d_cellcount.p, 0, sizeof(int) * ((size_t)g.ncells + 1), s));
+  CUDA_CHECK(cudaMemsetAsync(c->d_cellcount.p, 0, sizeof(int) * ((size_t)g.ncells + 8), s));
   PosQ *packed_local = c->d_packed.p + c->m_offsets[c->rank];
   int *ptype_local = c->d_ptype.p + c->m_offsets[c->rank];
   if (!multi) {
@@ -257,15 +258,15 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                         c->d_cellcount.p);
   }
   c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p);
-  c->launches += launch_cell_scatter(s, c->m_total, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
-                                     c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p);
+  c->launches += launch_cell_scatter(s, g, c->m_total, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
+                                     c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p, c->d_sortedf.p);
   stage_mark(c, 2);
 
   // ---- real-space part of b (blist_coul_cal) ---------------------------------
   if (c->rc_b > 0.0 && c->m_total > 0 && nr > 0) {
     c->launches += launch_pair_b(s, g, pair_tables(c, c->d_cuteff_b.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
-                                 c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_cellstart.p,
-                                 c->d_breal.p);
+                                 c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_sortedf.p,
+                                 c->d_cellstart.p, c->d_breal.p);
   } else {
     CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * std::max(nr, 1), s));
   }
@@ -284,7 +285,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
-    c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_part2grid.p, c->d_weights.p, c->d_ubrick.p,
+    c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_widx.p, c->d_weights.p, c->d_ubrick.p,
                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
   } else {
     const EwaldHost &e = c->ew;
@@ -317,7 +318,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   const double *qinit = c->have_qinit ? c->d_qinit.p : nullptr;
   if (kspace_mode == CONP_KSPACE_PPPM) {  // charges + kspmod->update_charge() -> ele_make_rho
     CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, s));
-    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_part2grid.p, c->d_weights.p, c->d_sb.p,
+    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_widx.p, c->d_weights.p, c->d_sb.p,
                                           c->d_setq.p, qinit, c->scal(0), c->d_q.p, c->d_ebrick.p);
   } else {
     c->launches += launch_finalize_q(s, c->N, c->d_sb.p, c->d_setq.p, qinit, c->scal(0), c->d_q.p);
@@ -714,6 +715,8 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     c->d_zmap.upload(zmap, s);
     c->d_zout.upload(c->h_zout, s);
     g.zmap = c->d_zmap.p;
+    c->d_widx.reserve(3 * (size_t)c->N * order);
+    c->launches += launch_pppm_ele_index(s, g, c->N, c->d_part2grid.p, c->d_widx.p);
     // ---- input planes: what the box can reach (all of them if z is periodic) ----
     if (c->periodic[2]) {
       g.zin_lo = 0;
@@ -1045,13 +1048,13 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     c->d_idx.upload(c->h_idx, s);
     c->d_xraw.reserve(3 * (size_t)std::max(nlocal, 1));
     const size_t m = std::max(tot, 1);
-    c->d_packed.reserve(m); c->d_sorted.reserve(m);
+    c->d_packed.reserve(m); c->d_sorted.reserve(m); c->d_sortedf.reserve(m);
     c->d_ptype.reserve(m); c->d_stype.reserve(m); c->d_ssrc.reserve(m);
     c->d_cellof.reserve(m); c->d_slot.reserve(m);
     c->d_nearlist.reserve(m);
     ensure_static_cells(c);
-    c->d_cellcount.zero((size_t)c->grid_b.ncells + 1, s);
-    c->d_cellstart.zero((size_t)c->grid_b.ncells + 1, s);
+    c->d_cellcount.zero((size_t)c->grid_b.ncells + 8, s);
+    c->d_cellstart.zero((size_t)c->grid_b.ncells + 8, s);
     drop_graphs(c);
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->have_atoms = true;

@@ -142,56 +142,68 @@ bin_positions_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, int *__
   slot[j] = atomicAdd(&cell_count[cell], 1);
 }
 
-// exclusive scan of cell_count -> cell_start[ncells+1]; one block, each thread
-// owns a contiguous run of cells
+// exclusive scan of cell_count -> cell_start[ncells+1]; one block walks the
+// histogram in coalesced int4 tiles of 4096 cells (cell_count is padded with
+// zeros to a multiple of 4)
 __global__ void __launch_bounds__(1024, 1)
 cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict__ cell_start) {
-  __shared__ int sh[33];
-  const int t = threadIdx.x;
-  const int per = (ncells + 1023) / 1024;
-  const int a = min(t * per, ncells), b = min(a + per, ncells);
-  int sum = 0;
-  for (int c = a; c < b; ++c) sum += cell_count[c];
-  const int lane = t & 31, warp = t >> 5;
-  int incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) sh[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int w = sh[lane];
-    int wi = w;
+  __shared__ int wsum[32];
+  __shared__ int tile_total;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int carry = 0;
+  for (int base = 0; base < ncells; base += 4096) {
+    const int idx = base + 4 * t;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (idx < ncells) v = *reinterpret_cast<const int4 *>(cell_count + idx);
+    const int s1 = v.x + v.y, s2 = s1 + v.z, tsum = s2 + v.w;
+    int incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += v;
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
     }
-    sh[lane] = wi - w;
-    if (lane == 31) sh[32] = wi;
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = wsum[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += u;
+      }
+      wsum[lane] = wi - w;
+      if (lane == 31) tile_total = wi;
+    }
+    __syncthreads();
+    const int excl = carry + wsum[warp] + incl - tsum;
+    if (idx < ncells) {
+      cell_start[idx] = excl;
+      if (idx + 1 < ncells) cell_start[idx + 1] = excl + v.x;
+      if (idx + 2 < ncells) cell_start[idx + 2] = excl + s1;
+      if (idx + 3 < ncells) cell_start[idx + 3] = excl + s2;
+    }
+    carry += tile_total;
+    __syncthreads();
   }
-  __syncthreads();
-  int run = sh[warp] + incl - sum;
-  for (int c = a; c < b; ++c) {
-    cell_start[c] = run;
-    run += cell_count[c];
-  }
-  if (t == 0) cell_start[ncells] = sh[32];
+  if (t == 0) cell_start[ncells] = carry;
 }
 
 __global__ void __launch_bounds__(256)
-cell_scatter_kernel(int m, const PosQ *__restrict__ packed, const int *__restrict__ type,
+cell_scatter_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, const int *__restrict__ type,
                     const int *__restrict__ cell_of, const int *__restrict__ slot,
                     const int *__restrict__ cell_start, PosQ *__restrict__ sorted,
-                    int *__restrict__ sorted_type, int *__restrict__ sorted_src) {
+                    int *__restrict__ sorted_type, int *__restrict__ sorted_src,
+                    float4 *__restrict__ sorted_f) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   const int d = cell_start[cell_of[j]] + slot[j];
-  sorted[d] = packed[j];
+  const PosQ p = packed[j];
+  sorted[d] = p;
   sorted_type[d] = type[j];
   sorted_src[d] = j;
+  // FP32 copy relative to the box corner for the conservative distance prefilter (pair_b)
+  sorted_f[d] = make_float4((float)(p.x - g.lo[0]), (float)(p.y - g.lo[1]), (float)(p.z - g.lo[2]), 0.0f);
 }
 
 // near list over the gathered charges: warp-aggregated append
@@ -221,10 +233,11 @@ constexpr int PAIR_WARPS = 8;
 constexpr int QCAP = 64;
 
 struct WarpQueue {
-  double rsq[QCAP];
-  double aux[QCAP];  // MODE_B: partner charge
-  int i[QCAP];       // MODE_A: partner electrode index
-  int t[QCAP];       // partner type
+  double rsq[QCAP];  // MODE_A: rsq            MODE_B: image shift x
+  double aux[QCAP];  //                        MODE_B: image shift y
+  double shz[QCAP];  //                        MODE_B: image shift z
+  int i[QCAP];       // MODE_A: partner index  MODE_B: index into the sorted charges
+  int t[QCAP];       // MODE_A: partner type
 };
 
 // Visit, warp-cooperatively, every electrode atom image within sqrt(max cuteff)
@@ -278,7 +291,10 @@ __device__ __forceinline__ void traverse(const CellGrid &g, const int *__restric
 }
 
 // One warp per electrode row i of [row_begin, row_end).
-// MODE_B: targets = cell-sorted point charges; b_real[i] = -sum_j q_j dudq (fix_conp.cpp:1339)
+// MODE_B: targets = cell-sorted point charges; b_real[i] = -sum_j q_j dudq (fix_conp.cpp:1339).
+//         Candidates are screened in FP32 (positions relative to the box corner, threshold
+//         widened by 1e-4 so no true pair is lost); survivors are re-tested exactly in FP64
+//         against cutsq / cut_coulsq when they are consumed.
 // MODE_A: targets = cell-sorted electrode atoms; A[i][j] += dudq (fix_conp.cpp:1270), self images kept
 template <int MODE>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, 4)
@@ -286,6 +302,7 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
             const double *__restrict__ ey, const double *__restrict__ ez, const int *__restrict__ etype,
             const int *__restrict__ cell_start,
             const PosQ *__restrict__ sorted, const int *__restrict__ sorted_type,  // MODE_B targets
+            const float4 *__restrict__ sorted_f, float cutmax_f,
             const EPos *__restrict__ esorted,                                      // MODE_A targets
             double *__restrict__ out, size_t pitch) {
   __shared__ WarpQueue queues[PAIR_WARPS];
@@ -301,34 +318,46 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
   double acc = 0.0;
   int qn = 0;
   auto consume = [&](int e) {
-    const double d = dudq_pair<MODE>(pt, wq.rsq[e], it, wq.t[e]);
-    if (MODE == MODE_B) acc = fma(wq.aux[e], d, acc);
-    else atomicAdd(A_row + wq.i[e], d);
+    if (MODE == MODE_B) {
+      // exact FP64 distance of the screened candidate
+      const int k = wq.i[e];
+      const PosQ p = sorted[k];
+      const int jt = sorted_type[k];
+      const double dx = xi - (p.x + wq.rsq[e]), dy = yi - (p.y + wq.aux[e]), dz = zi - (p.z + wq.shz[e]);
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      if (rsq < __ldg(cut_row + jt)) acc = fma(p.q, dudq_pair<MODE_B>(pt, rsq, it, jt), acc);
+    } else {
+      atomicAdd(A_row + wq.i[e], dudq_pair<MODE_A>(pt, wq.rsq[e], it, wq.t[e]));
+    }
   };
   traverse(g, cell_start, xi, yi, zi, lane, [&](bool valid, int k, double shx, double shy, double shz) {
     bool pass = false;
-    double rsq = 0.0, qj = 0.0;
+    double rsq = 0.0;
     int jt = 0, jidx = 0;
-    if (valid) {
-      double px, py, pz;
-      if (MODE == MODE_B) {
-        const PosQ p = sorted[k];
-        px = p.x; py = p.y; pz = p.z; qj = p.q;
-        jt = sorted_type[k];
-      } else {
-        const EPos e = esorted[k];
-        px = e.x; py = e.y; pz = e.z;
-        jt = e.type; jidx = e.idx;
+    if (MODE == MODE_B) {
+      if (valid) {
+        const float4 pf = sorted_f[k];
+        const float fx = (float)(xi - shx - g.lo[0]) - pf.x;
+        const float fy = (float)(yi - shy - g.lo[1]) - pf.y;
+        const float fz = (float)(zi - shz - g.lo[2]) - pf.z;
+        pass = fx * fx + fy * fy + fz * fz < cutmax_f;
       }
-      const double dx = xi - (px + shx), dy = yi - (py + shy), dz = zi - (pz + shz);
+    } else if (valid) {
+      const EPos e = esorted[k];
+      jt = e.type; jidx = e.idx;
+      const double dx = xi - (e.x + shx), dy = yi - (e.y + shy), dz = zi - (e.z + shz);
       rsq = dx * dx + dy * dy + dz * dz;
       pass = rsq < __ldg(cut_row + jt);
-      if (MODE == MODE_A && jidx == i && shx == 0.0 && shy == 0.0 && shz == 0.0) pass = false;
+      if (jidx == i && shx == 0.0 && shy == 0.0 && shz == 0.0) pass = false;
     }
     const unsigned mask = __ballot_sync(0xffffffffu, pass);
     if (pass) {
       const int pos = qn + __popc(mask & lt_mask);
-      wq.rsq[pos] = rsq; wq.aux[pos] = qj; wq.i[pos] = jidx; wq.t[pos] = jt;
+      if (MODE == MODE_B) {
+        wq.rsq[pos] = shx; wq.aux[pos] = shy; wq.shz[pos] = shz; wq.i[pos] = k;
+      } else {
+        wq.rsq[pos] = rsq; wq.i[pos] = jidx; wq.t[pos] = jt;
+      }
     }
     qn += __popc(mask);
     if (qn >= 32) {
@@ -547,11 +576,12 @@ int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cel
   return 1;
 }
 
-int launch_cell_scatter(cudaStream_t s, int m, const PosQ *packed, const int *type, const int *cell_of,
-                        const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type, int *sorted_src) {
+int launch_cell_scatter(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const int *type,
+                        const int *cell_of, const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type,
+                        int *sorted_src, float4 *sorted_f) {
   if (m <= 0) return 0;
-  cell_scatter_kernel<<<(m + 255) / 256, 256, 0, s>>>(m, packed, type, cell_of, slot, cell_start, sorted,
-                                                      sorted_type, sorted_src);
+  cell_scatter_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, packed, type, cell_of, slot, cell_start, sorted,
+                                                      sorted_type, sorted_src, sorted_f);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -566,11 +596,18 @@ int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packe
 
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
                   const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const int *cell_start, double *b_real) {
+                  const int *sorted_type, const float4 *sorted_f, const int *cell_start, double *b_real) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
+  // FP32 screen radius: the grid's search radius widened so that rounding cannot reject a true pair.
+  // Coordinates relative to the box corner carry <= 2^-23 * extent each; the squared distance then
+  // errs by <= 2 sqrt(3) rc * (4 * 2^-23 * extent), doubled for safety.
+  const double extent = std::max(std::max(g.prd[0], g.prd[1]), g.prd[2]) + 2.0 * g.rc;
+  const double slack = 2.0 * (2.0 * std::sqrt(3.0) * g.rc * 4.0 * extent * 1.1920929e-7) + 1e-4 * g.rc * g.rc;
+  const float cutmax_f = (float)(g.rc * g.rc + slack);
   pair_kernel<MODE_B><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, sorted, sorted_type, nullptr, b_real, 0);
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, sorted, sorted_type, sorted_f, cutmax_f, nullptr,
+      b_real, 0);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -581,7 +618,8 @@ int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
   pair_kernel<MODE_A><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, nullptr, nullptr, esorted, A_rows, pitch);
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, nullptr, nullptr, nullptr, 0.0f, esorted, A_rows,
+      pitch);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -94,62 +94,82 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
   }
 }
 
-// z-convolution with the tabulated kernel.  Block = ZC_COLS consecutive
-// (kx,ky) columns (128 B of the plane-major spectra), one warp per column;
-// for each output plane the lanes stride the input planes of the window
-// (coalesced table reads, every load of a run in flight at once) and the
-// partial sums are combined with warp shuffles.  rho^ of the block is staged
-// in shared memory.
+// z-convolution with the tabulated kernel.  A block owns `cols` consecutive
+// (kx,ky) columns (cols*16 B of every plane of the plane-major spectra).  It
+// stages rho^ of those columns (all input planes) and their kernel rows K[d]
+// in shared memory with coalesced loads, then each thread owns one (column,
+// output plane) pair and runs its window out of shared memory.
 // For k_xy != 0 the kernel decays like the Ewald Gaussian / exp(-|k_xy| |dz|):
 // krad[col] bounds the circular |d| beyond which |K| is below ~1e-18 of the
 // column maximum (measured on the table at setup, see ctx.cu), and only input
 // planes inside that window are visited; the dropped tail is below the
 // rounding level of the reference's own FFTs.
-constexpr int ZC_COLS = 8;
+constexpr int ZC_THREADS = 256;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
+}
 
 template <bool REALK>
-__global__ void __launch_bounds__(ZC_COLS * 32)
-zconv_kernel(int ncol, int nz, int nzi, int zin_lo, int nzo, const int *__restrict__ zout_list,
+__global__ void __launch_bounds__(ZC_THREADS)
+zconv_kernel(int ncol, int cols, int nz, int nzi, int zin_lo, int nzo, const int *__restrict__ zout_list,
              const int *__restrict__ krad, const double2 *__restrict__ rhat, const double *__restrict__ Kr,
              const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
   extern __shared__ __align__(16) unsigned char zc_smem[];
-  double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzi][ZC_COLS]
-  const int c0 = blockIdx.x * ZC_COLS;
-  for (int idx = threadIdx.x; idx < nzi * ZC_COLS; idx += blockDim.x) {
-    const int zi = idx / ZC_COLS, cc = idx - zi * ZC_COLS;
-    const int c = c0 + cc;
-    rh[idx] = (c < ncol) ? rhat[(size_t)zi * ncol + c] : make_double2(0.0, 0.0);
+  double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzi][cols]
+  const int kstride = REALK ? (nz | 1) : nz;            // odd row pitch: conflict-free across columns
+  double *ksr = reinterpret_cast<double *>(rh + (size_t)nzi * cols);  // REALK: [cols][kstride]
+  double2 *ksc = reinterpret_cast<double2 *>(ksr);                     // else:  [cols][nz]
+  const int c0 = blockIdx.x * cols;
+  // staging with cp.async: every load of the block is in flight at once (the kernel is
+  // latency-bound otherwise); columns past ncol are clamped to the last one and never stored
+  for (int idx = threadIdx.x; idx < nzi * cols; idx += blockDim.x) {
+    const int zi = idx / cols, cc = idx - zi * cols;
+    const int c = min(c0 + cc, ncol - 1);
+    cp_async<16>(&rh[idx], &rhat[(size_t)zi * ncol + c]);
   }
+  for (int cc = 0; cc < cols; ++cc) {
+    const int c = min(c0 + cc, ncol - 1);
+    if (REALK) {
+      const double *src = Kr + (size_t)c * nz;
+      for (int d = threadIdx.x; d < nz; d += blockDim.x) cp_async<8>(&ksr[cc * kstride + d], src + d);
+    } else {
+      const double2 *src = Kc + (size_t)c * nz;
+      for (int d = threadIdx.x; d < nz; d += blockDim.x) cp_async<16>(&ksc[cc * kstride + d], src + d);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = c0 + w;
-  if (c >= ncol) return;
-  const int R = krad[c];
-  const double *krow = REALK ? Kr + (size_t)c * nz : nullptr;
-  const double2 *kcrow = REALK ? nullptr : Kc + (size_t)c * nz;
-  for (int zo = 0; zo < nzo; ++zo) {
+  for (int item = threadIdx.x; item < cols * nzo; item += blockDim.x) {
+    const int zo = item / cols, cc = item - zo * cols;
+    const int c = c0 + cc;
+    if (c >= ncol) continue;
+    const int R = krad[c];
     // a = position of the output plane on the ring, in input-plane coordinates
-    int a = (__ldg(zout_list + zo) - zin_lo) % nz;
+    int a = (zout_list[zo] - zin_lo) % nz;
     if (a < 0) a += nz;
     double ar = 0.0, ai = 0.0;
     // input planes z0..z1 (inclusive); table index d = (a - zi) mod nz
     auto run = [&](int z0, int z1) {
       z0 = max(z0, 0);
       z1 = min(z1, nzi - 1);
-      for (int zi = z0 + lane; zi <= z1; zi += 32) {
-        int d = a - zi;
-        d += (d < 0) ? nz : 0;
-        d -= (d >= nz) ? nz : 0;
-        const double2 r = rh[zi * ZC_COLS + w];
+      int d = a - z0;
+      d += (d < 0) ? nz : 0;
+      d -= (d >= nz) ? nz : 0;
+      for (int zi = z0; zi <= z1; ++zi) {
+        const double2 r = rh[zi * cols + cc];
         if (REALK) {
-          const double k = __ldg(krow + d);
+          const double k = ksr[cc * kstride + d];
           ar = fma(k, r.x, ar);
           ai = fma(k, r.y, ai);
         } else {
-          const double2 k = kcrow[d];
+          const double2 k = ksc[cc * kstride + d];
           ar = fma(k.x, r.x, ar); ar = fma(-k.y, r.y, ar);
           ai = fma(k.x, r.y, ai); ai = fma(k.y, r.x, ai);
         }
+        d = d ? d - 1 : nz - 1;
       }
     };
     if (2 * R + 1 >= nz) {
@@ -159,12 +179,7 @@ zconv_kernel(int ncol, int nz, int nzi, int zin_lo, int nzo, const int *__restri
       if (a - R < 0) run(a - R + nz, nz - 1);   // wrapped from below
       if (a + R >= nz) run(0, a + R - nz);      // wrapped from above
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ar += __shfl_xor_sync(0xffffffffu, ar, o);
-      ai += __shfl_xor_sync(0xffffffffu, ai, o);
-    }
-    if (lane == 0) uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
+    uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
   }
 }
 
@@ -208,10 +223,25 @@ ele_stencil_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int n_ele, 
   }
 }
 
+// wrapped stencil indices of the (static) electrode atoms: widx[i][0][l] = mx, [1][m] = my,
+// [2][n] = compact output plane; removes all integer modulo work from gather / re-spread
+__global__ void __launch_bounds__(128)
+ele_index_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, int *__restrict__ widx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ele) return;
+  const int dims[3] = {g.nx, g.ny, g.nz};
+  for (int ic = 0; ic < 3; ++ic)
+    for (int l = 0; l < g.order; ++l) {
+      int m = wrapi(l + g.nlower + part2grid[3 * i + ic], dims[ic]);
+      if (ic == 2) m = g.zmap[m];
+      widx[((size_t)i * 3 + ic) * g.order + l] = m;
+    }
+}
+
 // one warp per electrode row: b_k = -sum w u (pppm_conp.cpp:285-298), slab
 // term (:301-313), then b = b_k + b_real
 __global__ void __launch_bounds__(256)
-gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ part2grid,
+gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ widx,
                 const double *__restrict__ weights, const double *__restrict__ u_brick,
                 const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
                 const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b) {
@@ -219,19 +249,16 @@ gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ 
   const int i = row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
   if (i >= row_end) return;
   const int order = g.order;
-  const int nx = part2grid[3 * i], ny = part2grid[3 * i + 1], nz = part2grid[3 * i + 2];
   const double *w = weights + (size_t)i * 3 * order;
+  const int *wi = widx + (size_t)i * 3 * order;
   const int npts = order * order * order;
   double acc = 0.0;
   for (int t = lane; t < npts; t += 32) {
     const int n = t / (order * order);
     const int r = t - n * order * order;
     const int m = r / order, l = r - m * order;
-    const int zo = g.zmap[wrapi(n + g.nlower + nz, g.nz)];  // compact output plane
-    const int my = wrapi(m + g.nlower + ny, g.ny);
-    const int mx = wrapi(l + g.nlower + nx, g.nx);
     const double x0 = w[2 * order + n] * w[order + m] * w[l];
-    acc = fma(x0, u_brick[((size_t)zo * g.ny + my) * g.nx + mx], acc);
+    acc = fma(x0, u_brick[((size_t)wi[2 * order + n] * g.ny + wi[order + m]) * g.nx + wi[l]], acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -247,7 +274,7 @@ gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ 
 // The new charge q_i = (S.b)_i + potdiff*setq_i (+qinit_i) (fix_conp.cpp:1153-1158)
 // is formed here from the epilogue scalars and stored by the atom's first thread.
 __global__ void __launch_bounds__(256)
-ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, const double *__restrict__ weights,
+ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, const double *__restrict__ weights,
                   const double *__restrict__ sb, const double *__restrict__ setq,
                   const double *__restrict__ qinit, const double *__restrict__ scal, double *__restrict__ q_out,
                   double *__restrict__ brick) {
@@ -258,21 +285,15 @@ ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, cons
   if (i >= n_ele) return;
   const int nm = (int)(gid - (long long)i * per_atom);
   const int n = nm / order, m = nm - n * order;
-  const int nx = part2grid[3 * i], ny = part2grid[3 * i + 1], nz = part2grid[3 * i + 2];
   const double *w = weights + (size_t)i * 3 * order;
+  const int *wi = widx + (size_t)i * 3 * order;
   double qi = sb[i] + scal[1] * setq[i];
   if (qinit) qi += qinit[i];
   if (nm == 0) q_out[i] = qi;
   const double z0 = g.delvolinv * qi;  // pppm_conp.cpp:411
   const double x0 = z0 * w[2 * order + n] * w[order + m];
-  const int zo = g.zmap[wrapi(n + g.nlower + nz, g.nz)];
-  const int my = wrapi(m + g.nlower + ny, g.ny);
-  double *row = brick + ((size_t)zo * g.ny + my) * g.nx;
-  int mx = wrapi(g.nlower + nx, g.nx);
-  for (int l = 0; l < order; ++l) {
-    atomicAdd(row + mx, x0 * w[l]);
-    mx = (mx + 1 == g.nx) ? 0 : mx + 1;
-  }
+  double *row = brick + ((size_t)wi[2 * order + n] * g.ny + wi[order + m]) * g.nx;
+  for (int l = 0; l < order; ++l) atomicAdd(row + wi[l], x0 * w[l]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -301,24 +322,32 @@ int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, co
 int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
                       const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
                       const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
-  const size_t smem = sizeof(double2) * (size_t)nzi * ZC_COLS;
+  // widest column group whose rho^ + K rows fit in shared memory
+  const size_t kbytes = Kr ? sizeof(double) * (size_t)(nz | 1) : sizeof(double2) * (size_t)nz;
+  int cols = 8;
+  size_t smem = 0;
+  for (; cols >= 1; cols >>= 1) {
+    smem = (sizeof(double2) * (size_t)nzi + kbytes) * cols;
+    if (smem <= 200 * 1024) break;
+  }
+  if (cols < 1) CONP_THROW(CONP_ERR_ARG, "PPPM mesh too deep in z for the z-convolution kernel (nz = %d)", nz);
   static size_t smem_set_r = 0, smem_set_c = 0;
-  const int grid = (ncol + ZC_COLS - 1) / ZC_COLS;
+  const int grid = (ncol + cols - 1) / cols;
   if (Kr) {
     if (smem > smem_set_r) {
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set_r = smem;
     }
-    zconv_kernel<true><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list, krad,
-                                                        (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
+    zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzi, zin_lo, nzo, zout_list, krad,
+                                                      (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
   } else {
     if (smem > smem_set_c) {
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set_c = smem;
     }
-    zconv_kernel<false><<<grid, ZC_COLS * 32, smem, s>>>(ncol, nz, nzi, zin_lo, nzo, zout_list, krad,
-                                                         (const double2 *)rhat, nullptr, (const double2 *)Kc,
-                                                         (double2 *)uhat);
+    zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzi, zin_lo, nzo, zout_list, krad,
+                                                       (const double2 *)rhat, nullptr, (const double2 *)Kc,
+                                                       (double2 *)uhat);
   }
   CUDA_CHECK(cudaGetLastError());
   return 1;
@@ -340,23 +369,30 @@ int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho
   return 1;
 }
 
-int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *part2grid,
+int launch_pppm_ele_index(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, int *widx) {
+  if (n <= 0) return 0;
+  ele_index_kernel<<<(n + 127) / 128, 128, 0, s>>>(g, n, part2grid, widx);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *widx,
                          const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
                          double slab_pref, const double *b_real, double *b_kspace, double *b) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
-  gather_b_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, row_begin, row_end, part2grid, weights, u_brick, ez, qz_sum,
+  gather_b_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, row_begin, row_end, widx, weights, u_brick, ez, qz_sum,
                                               slab_pref, b_real, b_kspace, b);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, const double *weights,
+int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,
                            const double *sb, const double *setq, const double *qinit, const double *scal,
                            double *q_out, double *brick) {
   if (n <= 0) return 0;
   const long long threads = (long long)n * g.order * g.order;
-  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, part2grid, weights, sb, setq, qinit,
+  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, widx, weights, sb, setq, qinit,
                                                                      scal, q_out, brick);
   CUDA_CHECK(cudaGetLastError());
   return 1;
