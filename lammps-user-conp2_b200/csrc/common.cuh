@@ -217,9 +217,12 @@ void build_near_mask(const CellGrid &g, int begin, int end, const double *xyz, s
 int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
                       const double *q, const int *type, PosQ *packed, int *packed_type, int *cell_of, int *slot,
                       int *cell_count, double *qz_sum);
-int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, int *cell_of, int *slot,
-                         int *cell_count);
-int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start);
+// multi-GPU layout: nranks blocks of mpad slots, counts[r] valid charges each; m = nranks*mpad
+int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, int mpad, const int *counts,
+                         const PosQ *packed, int *cell_of, int *slot, int *cell_count);
+// qz_sum != nullptr: also sum the per-rank sum(q z) partials stored in the last slot of every block
+int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start, const PosQ *packed,
+                     int mpad, int nranks, double *qz_sum);
 int launch_cell_scatter(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const int *type,
                         const int *cell_of, const int *slot, const int *cell_start, PosQ *sorted, int *sorted_type,
                         int *sorted_src, float4 *sorted_f);
@@ -283,8 +286,10 @@ int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, in
 
 // gram.cu ------------------------------------------------------------------
 // C[i][j] += sum_k Pt[k][row_begin+i] * Pt[k][j] (k-major panel, ld doubles per k-row); FP64 tensor cores
+// lower_only: skip tiles strictly above the diagonal (single-GPU build; completed by launch_gram_mirror)
 int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
-                           const double *panel_all, size_t ld, double *C, size_t pitch);
+                           const double *panel_all, size_t ld, double *C, size_t pitch, int lower_only);
+int launch_gram_mirror(cudaStream_t s, int n, double *C, size_t pitch);
 
 // linalg.cu ----------------------------------------------------------------
 int launch_a_finish(cudaStream_t s, int row_begin, int row_end, int n, double *A_rows, size_t pitch,

@@ -68,7 +68,9 @@ struct conp_ctx {
 
   // atoms ------------------------------------------------------------------------
   int nlocal = 0, m_local = 0, m_total = 0;
+  int mpad = 0, m_slots = 0;  // multi-GPU: every rank's packed block has mpad slots (last one carries sum q z)
   std::vector<int> h_idx, m_counts, m_offsets;
+  DevBuf<int> d_mcounts;
   DevBuf<double> d_xraw, d_qraw;
   DevBuf<int> d_typeraw, d_idx;
   DevBuf<PosQ> d_packed, d_sorted;
@@ -242,23 +244,18 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   }
   stage_mark(c, 1);
   if (multi) {
-    std::vector<size_t> bytes(c->nranks), offs(c->nranks);
-    for (int r = 0; r < c->nranks; ++r) {
-      bytes[r] = (size_t)c->m_counts[r] * sizeof(PosQ);
-      offs[r] = (size_t)c->m_offsets[r] * sizeof(PosQ);
-    }
-    comm_allgatherv(c->comm, packed_local, c->d_packed.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
-    for (int r = 0; r < c->nranks; ++r) {
-      bytes[r] = (size_t)c->m_counts[r] * sizeof(int);
-      offs[r] = (size_t)c->m_offsets[r] * sizeof(int);
-    }
-    comm_allgatherv(c->comm, ptype_local, c->d_ptype.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
-    comm_allreduce_sum_f64(c->comm, c->scal(2), 1, s);
-    c->launches += launch_bin_positions(s, g, c->m_total, c->d_packed.p, c->d_cellof.p, c->d_slot.p,
-                                        c->d_cellcount.p);
+    // one equal-block allgather moves every rank's positions; the sum(q z) partial rides in the
+    // block's last (padding) slot.  Types and charges are static between reneighbourings and were
+    // gathered in conp_post_neighbor.
+    CUDA_CHECK(cudaMemcpyAsync(&packed_local[c->mpad - 1].x, c->scal(2), sizeof(double), cudaMemcpyDeviceToDevice,
+                               s));
+    comm_allgather(c->comm, packed_local, c->d_packed.p, sizeof(PosQ) * (size_t)c->mpad, s);
+    c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, c->d_mcounts.p, c->d_packed.p, c->d_cellof.p,
+                                        c->d_slot.p, c->d_cellcount.p);
   }
-  c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p);
-  c->launches += launch_cell_scatter(s, g, c->m_total, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
+  c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p, c->d_packed.p, c->mpad,
+                                  c->nranks, multi ? c->scal(2) : nullptr);
+  c->launches += launch_cell_scatter(s, g, c->m_slots, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
                                      c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p, c->d_sortedf.p);
   stage_mark(c, 2);
 
@@ -830,9 +827,11 @@ int conp_build_A(conp_ctx *c) {
       dsegs.upload(segs, s);
       c->launches += launch_ewald_panel(s, N, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, k0, kc, (int)segs.size(),
                                         dsegs.p, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, panel.p, ld);
-      c->launches += launch_gram_accumulate(s, nr, N, 2 * kc, panel.p + c->r0, panel.p, ld, c->d_mat.p, c->pitch);
+      c->launches += launch_gram_accumulate(s, nr, N, 2 * kc, panel.p + c->r0, panel.p, ld, c->d_mat.p, c->pitch,
+                                            c->nranks == 1);
       CUDA_CHECK(cudaStreamSynchronize(s));  // segs / dsegs reuse
     }
+    if (c->nranks == 1) c->launches += launch_gram_mirror(s, N, c->d_mat.p, c->pitch);  // the Gram is symmetric
     // ---- diagonal, self and slab terms -----------------------------------------
     const double diag_k = e.ug_tot - 2.0 / MY_PIS * c->g_ewald;  // km_ewald.cpp:632
     const double self_eta = std::sqrt(2.0) / MY_PIS * c->eta;    // fix_conp.cpp:796-800
@@ -1040,18 +1039,38 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
       CUDA_CHECK(cudaStreamSynchronize(s));
       for (int r = 0; r < c->nranks; ++r) c->m_counts[r] = (int)std::llround(h[r]);
     }
-    int tot = 0;
-    for (int r = 0; r < c->nranks; ++r) { c->m_offsets[r] = tot; tot += c->m_counts[r]; }
+    int tot = 0, cmax = 0;
+    for (int r = 0; r < c->nranks; ++r) { tot += c->m_counts[r]; cmax = std::max(cmax, c->m_counts[r]); }
     c->m_total = tot;
+    if (c->nranks > 1) {
+      c->mpad = cmax + 1;  // + the slot that carries sum(q z)
+      c->m_slots = c->nranks * c->mpad;
+      for (int r = 0; r < c->nranks; ++r) c->m_offsets[r] = r * c->mpad;
+    } else {
+      c->mpad = std::max(c->m_local, 1);
+      c->m_slots = c->m_local;
+      c->m_offsets[0] = 0;
+    }
+    c->d_mcounts.upload(c->m_counts, s);
     c->d_qraw.upload(q, nlocal, s);
     c->d_typeraw.upload(type, nlocal, s);
     c->d_idx.upload(c->h_idx, s);
     c->d_xraw.reserve(3 * (size_t)std::max(nlocal, 1));
-    const size_t m = std::max(tot, 1);
-    c->d_packed.reserve(m); c->d_sorted.reserve(m); c->d_sortedf.reserve(m);
-    c->d_ptype.reserve(m); c->d_stype.reserve(m); c->d_ssrc.reserve(m);
+    const size_t m = std::max(c->m_slots, 1);
+    c->d_packed.zero(m, s);
+    c->d_ptype.zero(m, s);
+    c->d_sorted.reserve(m); c->d_sortedf.reserve(m);
+    c->d_stype.reserve(m); c->d_ssrc.reserve(m);
     c->d_cellof.reserve(m); c->d_slot.reserve(m);
     c->d_nearlist.reserve(m);
+    if (c->nranks > 1) {  // static per-charge data: types of every rank's block, once per reneighbouring
+      std::vector<int> ht(c->mpad, 0);
+      for (int j = 0; j < c->m_local; ++j) ht[j] = type[c->h_idx[j]];
+      int *own = c->d_ptype.p + c->m_offsets[c->rank];
+      CUDA_CHECK(cudaMemcpyAsync(own, ht.data(), sizeof(int) * c->mpad, cudaMemcpyHostToDevice, s));
+      comm_allgather(c->comm, own, c->d_ptype.p, sizeof(int) * (size_t)c->mpad, s);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
     ensure_static_cells(c);
     c->d_cellcount.zero((size_t)c->grid_b.ncells + 8, s);
     c->d_cellstart.zero((size_t)c->grid_b.ncells + 8, s);
@@ -1170,22 +1189,22 @@ int conp_post_force(conp_ctx *c, double qqrd2e, double *f_out, double *energies_
     cudaStream_t s = c->stream;
     const int N = c->N;
     CUDA_CHECK(cudaMemsetAsync(c->scal(4), 0, sizeof(double) * 8, s));
-    c->d_fpacked.zero(3 * (size_t)std::max(c->m_total, 1), s);
+    c->d_fpacked.zero(3 * (size_t)std::max(c->m_slots, 1), s);
     if (c->rc_f > 0.0 && c->m_total > 0 && c->r1 > c->r0) {
       CellGrid g = c->grid_b;  // same electrode binning, smaller search radius
       g.rc = c->rc_f;
       for (int a = 0; a < 3; ++a) g.smax[a] = g.periodic[a] ? (int)std::ceil(g.rc / g.prd[a]) + 1 : 0;
       CUDA_CHECK(cudaMemsetAsync(c->d_nearcount.p, 0, sizeof(int), s));
-      c->launches += launch_near_list(s, c->grid_b, c->m_total, c->d_packed.p, c->d_nearmask.p, c->d_nearlist.p,
+      c->launches += launch_near_list(s, c->grid_b, c->m_slots, c->d_packed.p, c->d_nearmask.p, c->d_nearlist.p,
                                       c->d_nearcount.p);
       c->launches += launch_pair_postforce(s, g, pair_tables(c, c->d_cuteff_b.p), qqrd2e, c->d_esorted.p,
                                            c->d_ecellstart.p, c->d_q.p, c->d_packed.p, c->d_ptype.p,
-                                           c->d_nearlist.p, c->d_nearcount.p, c->m_total, c->d_cutsq_listed.p,
+                                           c->d_nearlist.p, c->d_nearcount.p, c->m_slots, c->d_cutsq_listed.p,
                                            c->d_fpacked.p, c->scal(4), c->num_sms);
     }
     if (c->nranks > 1) {
       comm_allreduce_sum_f64(c->comm, c->scal(4), 8, s);
-      if (f_out) comm_allreduce_sum_f64(c->comm, c->d_fpacked.p, 3 * (size_t)c->m_total, s);
+      if (f_out) comm_allreduce_sum_f64(c->comm, c->d_fpacked.p, 3 * (size_t)c->m_slots, s);
     }
     std::vector<double> q(N), en(8), fp;
     CUDA_CHECK(cudaMemcpyAsync(q.data(), c->d_q.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));

@@ -46,7 +46,8 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 // with zeros to multiples of the tile, so loads need no bounds checks.
 __global__ void __launch_bounds__(THREADS, 1)
 gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, const double *__restrict__ panel_a,
-            size_t ld, double *__restrict__ Cmat, size_t pitch) {
+            size_t ld, double *__restrict__ Cmat, size_t pitch, int lower_only) {
+  if (lower_only && blockIdx.x > blockIdx.y) return;  // tile strictly above the diagonal: mirrored later
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GramSmem &sm = *reinterpret_cast<GramSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -122,10 +123,35 @@ gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, cons
   }
 }
 
+// C[i][j] = C[j][i] for j > i (square matrix held whole on this GPU)
+__global__ void __launch_bounds__(256)
+mirror_kernel(int n, double *__restrict__ C, size_t pitch) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;  // handle (bi, bj) with bj >= bi: write the upper tile from the lower one
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;  // read lower tile element (i, j), i >= j region
+    tile[r][tx] = (i < n && j < n) ? C[(size_t)i * pitch + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;  // upper element (i, j) = lower (j, i)
+    if (i < n && j < n && j > i) C[(size_t)i * pitch + j] = tile[tx][r];
+  }
+}
+
 }  // namespace
 
+int launch_gram_mirror(cudaStream_t s, int n, double *C, size_t pitch) {
+  dim3 grid((n + 31) / 32, (n + 31) / 32);
+  mirror_kernel<<<grid, 256, 0, s>>>(n, C, pitch);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
-                           const double *panel_all, size_t ld, double *C, size_t pitch) {
+                           const double *panel_all, size_t ld, double *C, size_t pitch, int lower_only) {
   if (nrows <= 0 || n <= 0 || kdim <= 0) return 0;
   if (kdim % BK) CONP_THROW(CONP_ERR_ARG, "gram: kdim must be a multiple of %d", BK);
   static bool attr_set = false;
@@ -134,7 +160,8 @@ int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const dou
     attr_set = true;
   }
   dim3 grid((n + BN - 1) / BN, (nrows + BM - 1) / BM);
-  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, C, pitch);
+  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, C, pitch,
+                                                      lower_only);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

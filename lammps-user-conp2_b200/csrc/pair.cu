@@ -131,11 +131,18 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
   }
 }
 
+// multi-GPU: the gathered charges sit in `nranks` blocks of `mpad` slots; block r holds
+// counts[r] charges, the rest is padding (the last slot carries that rank's sum(q z))
 __global__ void __launch_bounds__(256)
-bin_positions_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, int *__restrict__ cell_of,
-                     int *__restrict__ slot, int *__restrict__ cell_count) {
+bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts,
+                     const PosQ *__restrict__ packed, int *__restrict__ cell_of, int *__restrict__ slot,
+                     int *__restrict__ cell_count) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
+  if (j % mpad >= counts[j / mpad]) {
+    cell_of[j] = -1;
+    return;
+  }
   const PosQ p = packed[j];
   const int cell = (cell_coord(g, 2, p.z) * g.nc[1] + cell_coord(g, 1, p.y)) * g.nc[0] + cell_coord(g, 0, p.x);
   cell_of[j] = cell;
@@ -146,10 +153,16 @@ bin_positions_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, int *__
 // histogram in coalesced int4 tiles of 4096 cells (cell_count is padded with
 // zeros to a multiple of 4)
 __global__ void __launch_bounds__(1024, 1)
-cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict__ cell_start) {
+cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict__ cell_start,
+                 const PosQ *__restrict__ packed, int mpad, int nranks, double *__restrict__ qz_sum) {
   __shared__ int wsum[32];
   __shared__ int tile_total;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (qz_sum && t == 0) {  // multi-GPU: sum(q z) partials ride in the last slot of every rank's block
+    double v = 0.0;
+    for (int r = 0; r < nranks; ++r) v += packed[(size_t)r * mpad + mpad - 1].x;
+    *qz_sum = v;
+  }
   int carry = 0;
   for (int base = 0; base < ncells; base += 4096) {
     const int idx = base + 4 * t;
@@ -197,6 +210,7 @@ cell_scatter_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, const in
                     float4 *__restrict__ sorted_f) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
+  if (cell_of[j] < 0) return;  // padding slot
   const int d = cell_start[cell_of[j]] + slot[j];
   const PosQ p = packed[j];
   sorted[d] = p;
@@ -562,16 +576,17 @@ int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_
   return 1;
 }
 
-int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, int *cell_of, int *slot,
-                         int *cell_count) {
+int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, int mpad, const int *counts,
+                         const PosQ *packed, int *cell_of, int *slot, int *cell_count) {
   if (m <= 0) return 0;
-  bin_positions_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, packed, cell_of, slot, cell_count);
+  bin_positions_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, mpad, counts, packed, cell_of, slot, cell_count);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start) {
-  cell_scan_kernel<<<1, 1024, 0, s>>>(ncells, cell_count, cell_start);
+int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start, const PosQ *packed,
+                     int mpad, int nranks, double *qz_sum) {
+  cell_scan_kernel<<<1, 1024, 0, s>>>(ncells, cell_count, cell_start, packed, mpad, nranks, qz_sum);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
