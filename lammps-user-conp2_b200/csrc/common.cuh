@@ -168,6 +168,8 @@ struct PPPMGeom {
   // compact output planes zmap[mz] (device array of nz ints, -1 if the plane is not needed)
   int nzi, zin_lo, nzo;
   const int *zmap;
+  // multi-GPU: this rank owns the slab of input planes [zs_lo, zs_lo + zs_n) (all of them on one GPU)
+  int zs_lo, zs_n;
 };
 
 // ---------------------------------------------------------------------------
@@ -243,11 +245,14 @@ int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &p
                           int num_sms);
 
 // pppm.cu ------------------------------------------------------------------
-int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m, const PosQ *atoms,
-                       double *brick, int *range_flag);
+// spreads the sorted charges of cells [cell_lo, cell_hi) (all of them if cell_start == nullptr) onto the
+// rank's slab of input planes; m_bound = upper bound of the number of charges in that range
+int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
+                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
-int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
-                      const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
+// rhat: spectra of the rank's nzl input planes (compact planes zs_lo..); uhat: (partial) output-plane spectra
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
+                      const int *zout_list, const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
                       const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
                          const double *compact, double *full);

@@ -272,13 +272,32 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   // ---- k-space part of b --------------------------------------------------------
   const double spref = slab_pref(c);
   if (kspace_mode == CONP_KSPACE_PPPM) {
-    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)c->pg.nzi * c->plane, s));
+    const PPPMGeom &pg = c->pg;
+    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)std::max(pg.zs_n, 1) * c->plane, s));
     CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
-    c->launches += launch_pppm_spread(s, c->pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_brick.p, c->d_flag.p);
-    CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
-    c->launches += launch_pppm_zconv(s, (int)c->ncol, c->pg.nz, c->pg.nzi, c->pg.zin_lo, c->pg.nzo, c->d_zout.p,
+    if (!multi || c->periodic[2]) {
+      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
+                                        c->d_flag.p);
+    } else {
+      // cells (z-major order => one contiguous range of sorted charges) whose stencils can reach the slab
+      const double zlo = c->boxlo[2] + (pg.zin_lo + pg.zs_lo - pg.order - 1) / pg.delinv[2];
+      const double zhi = c->boxlo[2] + (pg.zin_lo + pg.zs_lo + pg.zs_n + pg.order + 1) / pg.delinv[2];
+      int cz_lo = (int)std::floor((zlo - g.lo[2]) * g.cinv[2]) - 1, cz_hi = (int)std::floor((zhi - g.lo[2]) * g.cinv[2]) + 1;
+      cz_lo = std::max(0, std::min(cz_lo, g.nc[2] - 1));
+      cz_hi = std::max(0, std::min(cz_hi, g.nc[2] - 1));
+      const int cell_lo = cz_lo * g.nc[1] * g.nc[0], cell_hi = (cz_hi + 1) * g.nc[1] * g.nc[0];
+      // upper bound of the charges in the range: uniform share + 50 %, the kernel grid-strides beyond it
+      const long long bound = (long long)c->m_total * (cz_hi - cz_lo + 1) / g.nc[2] * 3 / 2 + 1024;
+      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, (int)std::min<long long>(bound, c->m_total),
+                                        c->d_sorted.p, c->d_cellstart.p, cell_lo, cell_hi, c->d_brick.p,
+                                        c->d_flag.p);
+    }
+    if (pg.zs_n > 0) CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
+    c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.zin_lo, pg.nzo, c->d_zout.p,
                                      c->d_krad.p, c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p,
                                      c->d_uhat.p);
+    // every rank holds the partial sum over its slab: one small all-reduce completes the spectra
+    if (multi) comm_allreduce_sum_f64(c->comm, (double *)c->d_uhat.p, 2 * (size_t)pg.nzo * c->ncol, s);
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
@@ -777,16 +796,20 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
         c->d_Kc.release();
       }
     }
+    // ---- this rank's slab of input planes (all of them on one GPU) ------------------
+    g.zs_lo = (int)(((long long)g.nzi * c->rank) / c->nranks);
+    g.zs_n = (int)(((long long)g.nzi * (c->rank + 1)) / c->nranks) - g.zs_lo;
     // ---- compact bricks and batched 2-D plans -------------------------------------
-    c->d_brick.zero((size_t)g.nzi * c->plane, s);
+    c->d_brick.zero((size_t)std::max(g.zs_n, 1) * c->plane, s);
     c->d_ubrick.zero((size_t)g.nzo * c->plane, s);
     c->d_ebrick.zero((size_t)g.nzo * c->plane, s);
-    c->d_rhat.reserve((size_t)g.nzi * ncol);
+    c->d_rhat.reserve((size_t)std::max(g.zs_n, 1) * ncol);
     c->d_uhat.reserve((size_t)g.nzo * ncol);
     c->d_flag.zero(1, s);
     if (c->plans) { cufftDestroy(c->plan_f); cufftDestroy(c->plan_b); c->plans = false; }
     int n2[2] = {g.ny, g.nx}, er[2] = {g.ny, g.nx}, ec[2] = {g.ny, (int)nxh};
-    CUFFT_CHECK(cufftPlanMany(&c->plan_f, 2, n2, er, 1, (int)c->plane, ec, 1, (int)ncol, CUFFT_D2Z, g.nzi));
+    CUFFT_CHECK(cufftPlanMany(&c->plan_f, 2, n2, er, 1, (int)c->plane, ec, 1, (int)ncol, CUFFT_D2Z,
+                              std::max(g.zs_n, 1)));
     CUFFT_CHECK(cufftPlanMany(&c->plan_b, 2, n2, ec, 1, (int)ncol, er, 1, (int)c->plane, CUFFT_Z2D, g.nzo));
     CUFFT_CHECK(cufftSetStream(c->plan_f, s));
     CUFFT_CHECK(cufftSetStream(c->plan_b, s));
@@ -1140,8 +1163,12 @@ int conp_get_density(conp_ctx *c, int which, double *brick_out) {
     // the solver keeps only the planes that can be non-zero; expand to the full mesh here
     DevBuf<double> full;
     full.zero(c->ngrid, s);
-    if (which == 0 || which == 2)
-      c->launches += launch_expand_planes(s, c->plane, g.nzi, g.nz, g.zin_lo, nullptr, c->d_brick.p, full.p);
+    if (which == 0 || which == 2) {
+      // every rank holds its slab of the electrolyte density; the sum of the expanded slabs is the brick
+      c->launches += launch_expand_planes(s, c->plane, g.zs_n, g.nz, g.zin_lo + g.zs_lo, nullptr, c->d_brick.p,
+                                          full.p);
+      if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);
+    }
     if (which == 1) c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, full.p);
     if (which == 2) {
       DevBuf<double> fe;
@@ -1167,7 +1194,8 @@ int conp_get_potential_brick(conp_ctx *c, double *brick_out) {
     full.zero(c->ngrid, s);
     work.reserve(c->nhalf);
     gd.upload(c->h_ghalf, s);
-    c->launches += launch_expand_planes(s, c->plane, g.nzi, g.nz, g.zin_lo, nullptr, c->d_brick.p, full.p);
+    c->launches += launch_expand_planes(s, c->plane, g.zs_n, g.nz, g.zin_lo + g.zs_lo, nullptr, c->d_brick.p, full.p);
+    if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);
     cufftHandle pf, pb;
     CUFFT_CHECK(cufftPlan3d(&pf, g.nz, g.ny, g.nx, CUFFT_D2Z));
     CUFFT_CHECK(cufftPlan3d(&pb, g.nz, g.ny, g.nx, CUFFT_Z2D));

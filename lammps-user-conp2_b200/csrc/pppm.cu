@@ -51,46 +51,54 @@ __device__ __forceinline__ double rho1d(const double *__restrict__ rc, int order
 // slower: same-sector atomics of one warp instruction serialise in L2.)
 __global__ void __launch_bounds__(256)
 spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, const PosQ *__restrict__ atoms,
-              double *__restrict__ brick, int *__restrict__ range_flag) {
+              const int *__restrict__ cell_start, int cell_lo, int cell_hi, double *__restrict__ brick,
+              int *__restrict__ range_flag) {
   __shared__ double rc[MAXORDER * MAXORDER];
   const int order = g.order;
   for (int t = threadIdx.x; t < order * order; t += blockDim.x) rc[t] = rho_coeff[t];
   __syncthreads();
+  // charges of the cell range (multi-GPU: the cells whose stencils can reach this rank's slab)
+  const int jb = cell_start ? cell_start[cell_lo] : 0;
+  const int je = cell_start ? cell_start[cell_hi] : m_atoms;
   const int per_atom = order * order;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = (int)(gid / per_atom);
-  if (j >= m_atoms) return;
-  const int nm = (int)(gid - (long long)j * per_atom);
-  const int n = nm / order, m = nm - n * order;
-  const PosQ p = atoms[j];
-  if (p.q == 0.0) return;  // pppm_conp.cpp:161
-  const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
-  const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
-  const double fz = (p.z - g.boxlo[2]) * g.delinv[2];
-  if (!(fabs(fx) < OFFSET / 2 && fabs(fy) < OFFSET / 2 && fabs(fz) < OFFSET / 2)) {
-    *range_flag = 1;  // "Out of range atoms - cannot compute PPPM", pppm_conp.cpp:167
-    return;
-  }
-  const int nx = (int)(fx + g.shift) - OFFSET;  // :146-148
-  const int ny = (int)(fy + g.shift) - OFFSET;
-  const int nz = (int)(fz + g.shift) - OFFSET;
-  const double dx = nx + g.shiftone - fx;  // :199-201
-  const double dy = ny + g.shiftone - fy;
-  const double dz = nz + g.shiftone - fz;
-  const double z0 = g.delvolinv * p.q;  // :205
-  const double y0 = z0 * rho1d(rc, order, n, dz);
-  const double x0 = y0 * rho1d(rc, order, m, dy);
-  const int zi = wrapi(n + g.nlower + nz - g.zin_lo, g.nz);  // compact input plane
-  if (zi >= g.nzi) {
-    *range_flag = 1;  // outside the planes the box can reach: "Out of range atoms"
-    return;
-  }
-  const int my = wrapi(m + g.nlower + ny, g.ny);
-  double *row = brick + ((size_t)zi * g.ny + my) * g.nx;
-  int mx = wrapi(g.nlower + nx, g.nx);
-  for (int l = 0; l < order; ++l) {
-    atomicAdd(row + mx, x0 * rho1d(rc, order, l, dx));
-    mx = (mx + 1 == g.nx) ? 0 : mx + 1;
+  const long long work = (long long)(je - jb) * per_atom;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < work;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int j = jb + (int)(gid / per_atom);
+    const int nm = (int)(gid % per_atom);
+    const int n = nm / order, m = nm - n * order;
+    const PosQ p = atoms[j];
+    if (p.q == 0.0) continue;  // pppm_conp.cpp:161
+    const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
+    const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
+    const double fz = (p.z - g.boxlo[2]) * g.delinv[2];
+    if (!(fabs(fx) < OFFSET / 2 && fabs(fy) < OFFSET / 2 && fabs(fz) < OFFSET / 2)) {
+      *range_flag = 1;  // "Out of range atoms - cannot compute PPPM", pppm_conp.cpp:167
+      continue;
+    }
+    const int nx = (int)(fx + g.shift) - OFFSET;  // :146-148
+    const int ny = (int)(fy + g.shift) - OFFSET;
+    const int nz = (int)(fz + g.shift) - OFFSET;
+    const int zi = wrapi(n + g.nlower + nz - g.zin_lo, g.nz);  // compact input plane
+    if (zi >= g.nzi) {
+      *range_flag = 1;  // outside the planes the box can reach: "Out of range atoms"
+      continue;
+    }
+    const int t = zi - g.zs_lo;  // plane inside this rank's slab?
+    if (t < 0 || t >= g.zs_n) continue;
+    const double dx = nx + g.shiftone - fx;  // :199-201
+    const double dy = ny + g.shiftone - fy;
+    const double dz = nz + g.shiftone - fz;
+    const double z0 = g.delvolinv * p.q;  // :205
+    const double y0 = z0 * rho1d(rc, order, n, dz);
+    const double x0 = y0 * rho1d(rc, order, m, dy);
+    const int my = wrapi(m + g.nlower + ny, g.ny);
+    double *row = brick + ((size_t)t * g.ny + my) * g.nx;
+    int mx = wrapi(g.nlower + nx, g.nx);
+    for (int l = 0; l < order; ++l) {
+      atomicAdd(row + mx, x0 * rho1d(rc, order, l, dx));
+      mx = (mx + 1 == g.nx) ? 0 : mx + 1;
+    }
   }
 }
 
@@ -114,30 +122,49 @@ __device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
 
 template <bool REALK>
 __global__ void __launch_bounds__(ZC_THREADS)
-zconv_kernel(int ncol, int cols, int nz, int nzi, int zin_lo, int nzo, const int *__restrict__ zout_list,
+zconv_kernel(int ncol, int cols, int nz, int nzl, int zs_lo, int zin_lo, int nzo, const int *__restrict__ zout_list,
              const int *__restrict__ krad, const double2 *__restrict__ rhat, const double *__restrict__ Kr,
              const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
+  // rhat: spectra of this rank's nzl input planes (compact planes zs_lo .. zs_lo+nzl-1); on several
+  // GPUs uhat is this rank's partial sum and is all-reduced afterwards
   extern __shared__ __align__(16) unsigned char zc_smem[];
-  double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzi][cols]
+  double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzl][cols]
   const int kstride = REALK ? (nz | 1) : nz;            // odd row pitch: conflict-free across columns
-  double *ksr = reinterpret_cast<double *>(rh + (size_t)nzi * cols);  // REALK: [cols][kstride]
+  double *ksr = reinterpret_cast<double *>(rh + (size_t)nzl * cols);  // REALK: [cols][kstride]
   double2 *ksc = reinterpret_cast<double2 *>(ksr);                     // else:  [cols][nz]
+  __shared__ int s_rblock;
   const int c0 = blockIdx.x * cols;
-  // staging with cp.async: every load of the block is in flight at once (the kernel is
-  // latency-bound otherwise); columns past ncol are clamped to the last one and never stored
-  for (int idx = threadIdx.x; idx < nzi * cols; idx += blockDim.x) {
-    const int zi = idx / cols, cc = idx - zi * cols;
-    const int c = min(c0 + cc, ncol - 1);
-    cp_async<16>(&rh[idx], &rhat[(size_t)zi * ncol + c]);
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int cc = 0; cc < cols; ++cc) r = max(r, krad[min(c0 + cc, ncol - 1)]);
+    s_rblock = r;
+  }
+  __syncthreads();
+  const int rblock = s_rblock;
+  const bool all = 2 * rblock + 1 >= nz;
+  // staging with cp.async: every load of the block is in flight at once (the kernel is latency-bound
+  // otherwise).  Only planes / table entries inside the block's largest window are fetched.
+  for (int t = threadIdx.x; t < nzl; t += blockDim.x) {
+    bool need = all;
+    for (int zo = 0; zo < nzo && !need; ++zo) {
+      int d = (zout_list[zo] - zin_lo - zs_lo - t) % nz;
+      if (d < 0) d += nz;
+      need = min(d, nz - d) <= rblock;
+    }
+    if (need)
+      for (int cc = 0; cc < cols; ++cc)
+        cp_async<16>(&rh[t * cols + cc], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
   }
   for (int cc = 0; cc < cols; ++cc) {
     const int c = min(c0 + cc, ncol - 1);
     if (REALK) {
       const double *src = Kr + (size_t)c * nz;
-      for (int d = threadIdx.x; d < nz; d += blockDim.x) cp_async<8>(&ksr[cc * kstride + d], src + d);
+      for (int d = threadIdx.x; d < nz; d += blockDim.x)
+        if (all || min(d, nz - d) <= rblock) cp_async<8>(&ksr[cc * kstride + d], src + d);
     } else {
       const double2 *src = Kc + (size_t)c * nz;
-      for (int d = threadIdx.x; d < nz; d += blockDim.x) cp_async<16>(&ksc[cc * kstride + d], src + d);
+      for (int d = threadIdx.x; d < nz; d += blockDim.x)
+        if (all || min(d, nz - d) <= rblock) cp_async<16>(&ksc[cc * kstride + d], src + d);
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -147,19 +174,19 @@ zconv_kernel(int ncol, int cols, int nz, int nzi, int zin_lo, int nzo, const int
     const int c = c0 + cc;
     if (c >= ncol) continue;
     const int R = krad[c];
-    // a = position of the output plane on the ring, in input-plane coordinates
+    // a = position of the output plane on the ring, in compact input-plane coordinates
     int a = (zout_list[zo] - zin_lo) % nz;
     if (a < 0) a += nz;
     double ar = 0.0, ai = 0.0;
-    // input planes z0..z1 (inclusive); table index d = (a - zi) mod nz
+    // compact input planes z0..z1 (inclusive), clipped to this rank's slab; table index d = (a - zi) mod nz
     auto run = [&](int z0, int z1) {
-      z0 = max(z0, 0);
-      z1 = min(z1, nzi - 1);
+      z0 = max(z0, zs_lo);
+      z1 = min(z1, zs_lo + nzl - 1);
       int d = a - z0;
       d += (d < 0) ? nz : 0;
       d -= (d >= nz) ? nz : 0;
       for (int zi = z0; zi <= z1; ++zi) {
-        const double2 r = rh[zi * cols + cc];
+        const double2 r = rh[(zi - zs_lo) * cols + cc];
         if (REALK) {
           const double k = ksr[cc * kstride + d];
           ar = fma(k, r.x, ar);
@@ -173,7 +200,7 @@ zconv_kernel(int ncol, int cols, int nz, int nzi, int zin_lo, int nzo, const int
       }
     };
     if (2 * R + 1 >= nz) {
-      run(0, nzi - 1);
+      run(0, nz - 1);
     } else {
       run(a - R, a + R);                        // main window
       if (a - R < 0) run(a - R + nz, nz - 1);   // wrapped from below
@@ -304,11 +331,12 @@ add_bricks_kernel(size_t n, const double *__restrict__ a, const double *__restri
 
 }  // namespace
 
-int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m, const PosQ *atoms,
-                       double *brick, int *range_flag) {
-  if (m <= 0) return 0;
-  const long long threads = (long long)m * g.order * g.order;
-  spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, rho_coeff, m, atoms, brick, range_flag);
+int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
+                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag) {
+  if (m_bound <= 0 || g.zs_n <= 0) return 0;
+  const long long threads = (long long)m_bound * g.order * g.order;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  spread_kernel<<<grid, 256, 0, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, brick, range_flag);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -319,15 +347,15 @@ int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, co
   return 1;
 }
 
-int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int nzo, const int *zout_list,
-                      const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
+                      const int *zout_list, const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
                       const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
   // widest column group whose rho^ + K rows fit in shared memory
   const size_t kbytes = Kr ? sizeof(double) * (size_t)(nz | 1) : sizeof(double2) * (size_t)nz;
   int cols = 8;
   size_t smem = 0;
   for (; cols >= 1; cols >>= 1) {
-    smem = (sizeof(double2) * (size_t)nzi + kbytes) * cols;
+    smem = (sizeof(double2) * (size_t)nzl + kbytes) * cols;
     if (smem <= 200 * 1024) break;
   }
   if (cols < 1) CONP_THROW(CONP_ERR_ARG, "PPPM mesh too deep in z for the z-convolution kernel (nz = %d)", nz);
@@ -338,14 +366,14 @@ int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzi, int zin_lo, int
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set_r = smem;
     }
-    zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzi, zin_lo, nzo, zout_list, krad,
+    zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad,
                                                       (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
   } else {
     if (smem > smem_set_c) {
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set_c = smem;
     }
-    zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzi, zin_lo, nzo, zout_list, krad,
+    zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad,
                                                        (const double2 *)rhat, nullptr, (const double2 *)Kc,
                                                        (double2 *)uhat);
   }
