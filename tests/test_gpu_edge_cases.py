@@ -1,0 +1,144 @@
+"""Edge cases of the hot path, CUDA (through the C ABI) vs the oracle:
+empty / uncharged electrolyte, charges that left the periodic box between
+reneighbourings, cut-off larger than half the box (several periodic images
+per pair), minimal electrodes, other PPPM stencil orders, ragged row counts."""
+import numpy as np
+import pytest
+
+import conp_oracle as O
+from cases import dilute, synthetic
+from conp_b200 import MockLammps, load_reference_case
+from conp_b200.fix_conp import make_fix
+from conp_b200.system import System
+
+pytestmark = pytest.mark.gpu
+
+
+def both(lmp_factory, arg_extra=()):
+    lmp, arg = lmp_factory()
+    lmp2, arg2 = lmp_factory()
+    fix = make_fix(lmp, list(arg) + list(arg_extra))
+    ref = O.OracleFixConp(lmp2, list(arg2) + list(arg_extra))
+    fix.setup()
+    ref.setup()
+    return fix, ref, fix.pre_force(), ref.pre_force()
+
+
+def close(q, qr):
+    assert np.abs(q - qr).max() <= 1e-9 * np.abs(qr).max() + 1e-12
+    assert abs(q.sum()) < 1e-12
+
+
+@pytest.mark.parametrize("pppm", [False, True])
+def test_no_charged_electrolyte(pppm):
+    """b == 0: the charges are dV * S.d exactly (fix_conp.cpp:1156)."""
+    def case():
+        lmp, arg = dilute(2, pppm=pppm)
+        ele = np.isin(lmp.system.mol, (81, 82))
+        lmp.system.q[~ele] = 0.0
+        return lmp, arg
+    fix, ref, q, qr = both(case)
+    close(q, qr)
+    b, bk = fix.ctx.get_b()
+    assert np.abs(b).max() == 0.0 and np.abs(bk).max() == 0.0
+    fix.close()
+
+
+def test_electrode_only_system():
+    def case():
+        s = load_reference_case("dilute")
+        keep = np.isin(s.mol, (81, 82))
+        s2 = System(s.boxlo, s.boxhi, s.id[keep], s.mol[keep], s.type[keep], s.q[keep], s.x[keep], s.ntypes)
+        lmp = MockLammps(s2, "p p p")
+        lmp.pair_style_coul_long(4.0)
+        lmp.kspace("pppm", 1e-6, 0.77236341)
+        lmp.group_molecule("eleleft", 81)
+        lmp.group_molecule("eleright", 82)
+        return lmp, "e eleleft conp 1 eleright 1.979 1.0 log ffield".split()
+    fix, ref, q, qr = both(case)
+    close(q, qr)
+    fix.close()
+
+
+@pytest.mark.parametrize("pppm", [False, True])
+def test_charges_outside_the_periodic_box(pppm):
+    """LAMMPS remaps atoms only at reneighbouring; images must give identical results."""
+    def case(shifted):
+        lmp, arg = dilute(2, pppm=pppm)
+        if shifted:
+            s = lmp.system
+            oth = np.nonzero(~np.isin(s.mol, (81, 82)))[0]
+            rng = np.random.default_rng(1)
+            k = rng.integers(-1, 2, (len(oth), 3))
+            s.x[oth] += k * s.prd[None, :]
+        return lmp, arg
+    fix, ref, q, qr = both(lambda: case(True))
+    close(q, qr)
+    _, _, q0, _ = both(lambda: case(False))
+    assert np.abs(q - q0).max() <= 2e-9 * np.abs(q0).max() + 1e-12
+    fix.close()
+
+
+def test_cutoff_beyond_half_box_sums_all_images():
+    """cut 9 A in the 9.8 x 8.5 A dilute cell: every pair has several images (and self images in A)."""
+    def case():
+        lmp, arg = dilute(5)
+        lmp.pair_style_coul_long(9.0)
+        return lmp, arg
+    fix, ref, q, qr = both(case)
+    assert np.abs(fix.ctx.get_matrix() - ref.S).max() <= 1e-10 * np.abs(ref.S).max()
+    b, _ = fix.ctx.get_b()
+    assert np.abs(b - ref.bbb_all).max() <= 5e-12 * max(1.0, np.abs(ref.bbb_all).max())
+    close(q, qr)
+    fix.close()
+
+
+def test_two_atom_electrodes():
+    def case():
+        lmp, arg = dilute(2)
+        s = lmp.system
+        left = np.nonzero(s.mol == 81)[0]
+        right = np.nonzero(s.mol == 82)[0]
+        s.mol[left[1:]] = 999
+        s.mol[right[1:]] = 998
+        lmp.group_molecule("eleleft", 81)
+        lmp.group_molecule("eleright", 82)
+        return lmp, [a for a in arg if a not in ("etypes", "1", "3")][:8] + ["ffield"]
+    fix, ref, q, qr = both(case)
+    assert fix.N == 2
+    close(q, qr)
+    assert abs(q[0] + q[1]) < 1e-14
+    fix.close()
+
+
+@pytest.mark.parametrize("order", [3, 4, 7])
+def test_other_pppm_orders(order):
+    def case():
+        lmp, arg = dilute(2, pppm=True)
+        lmp.kspace("pppm/conp", 1e-6, 0.77236341, mesh=(27, 24, 144), order=order)
+        return lmp, arg
+    fix, ref, q, qr = both(case)
+    b, bk = fix.ctx.get_b()
+    assert np.abs(bk - ref.b_kspace).max() <= 5e-12 * max(1.0, np.abs(ref.b_kspace).max())
+    close(q, qr)
+    fix.close()
+
+
+def test_gemv_row_tails_many_sizes():
+    """S.b through the TMA GEMV for row/column counts that are not multiples of the tile
+    (ragged strips, partial column chunks): totsetq = sum_left (S.d) vs numpy."""
+    from conp_b200 import abi
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 15, 17, 148, 149, 511, 513, 1031, 2500):
+        ctx = abi.Context()
+        ctx.set_cell([0, 0, -50], [60, 100, 100], [1, 1, 0], 1, 3.0, 0)
+        ctx.set_ewald(0.26, 1e-2, 1000.0, 1000)
+        ctx.set_pair(0, 1.979, 12.0, 1, np.full((2, 2), 144.0))
+        side = np.where(np.arange(n) % 2 == 0, 1, -1)
+        ctx.set_electrodes(np.arange(1, n + 1), np.ones(n), side, rng.uniform(0, 50, (n, 3)))
+        S = rng.standard_normal((n, n))
+        ctx.load_matrix(S, True)
+        tot = ctx.set_unit_voltage(0.0694)
+        ref = (S @ (-0.5 * 0.0694 * side))[side == 1].sum()
+        assert abs(tot - ref) <= 1e-12 * max(1.0, np.abs(S).sum() * 0.0694)
+        ctx.close()
