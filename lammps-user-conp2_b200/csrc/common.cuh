@@ -260,8 +260,11 @@ int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho
                             const double *ey, const double *ez, int *part2grid, double *weights);
 // wrapped stencil indices [n][3][order] (x, y, compact z plane) of the static electrode atoms; needs g.zmap
 int launch_pppm_ele_index(cudaStream_t s, const PPPMGeom &g, int n, const int *part2grid, int *widx);
-int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *widx,
-                         const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
+// flat stencil table [n][order^3]: offset into the compact potential brick, weight product
+int launch_pppm_point_table(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,
+                            int *poff, double *pw);
+int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *poff,
+                         const double *pw, const double *u_brick, const double *ez, const double *qz_sum,
                          double slab_pref /* 4 pi / V or 0 */, const double *b_real, double *b_kspace, double *b);
 // electrode re-spread; forms q_i = sb_i + potdiff*setq_i (+qinit_i) on the fly and stores it to q_out
 int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,

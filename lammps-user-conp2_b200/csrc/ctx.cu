@@ -90,7 +90,8 @@ struct conp_ctx {
   std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
   std::vector<int> h_zout;              // output planes (sorted)
   DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
-  DevBuf<int> d_part2grid, d_widx, d_flag, d_zmap, d_zout, d_krad;
+  DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad;
+  DevBuf<double> d_pw;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
   bool plans = false, k_real = true;
@@ -301,7 +302,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
-    c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_widx.p, c->d_weights.p, c->d_ubrick.p,
+    c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_poff.p, c->d_pw.p, c->d_ubrick.p,
                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
   } else {
     const EwaldHost &e = c->ew;
@@ -733,6 +734,9 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     g.zmap = c->d_zmap.p;
     c->d_widx.reserve(3 * (size_t)c->N * order);
     c->launches += launch_pppm_ele_index(s, g, c->N, c->d_part2grid.p, c->d_widx.p);
+    c->d_poff.reserve((size_t)c->N * order * order * order);
+    c->d_pw.reserve((size_t)c->N * order * order * order);
+    c->launches += launch_pppm_point_table(s, g, c->N, c->d_widx.p, c->d_weights.p, c->d_poff.p, c->d_pw.p);
     // ---- input planes: what the box can reach (all of them if z is periodic) ----
     if (c->periodic[2]) {
       g.zin_lo = 0;

@@ -143,17 +143,10 @@ zconv_kernel(int ncol, int cols, int nz, int nzl, int zs_lo, int zin_lo, int nzo
   const int rblock = s_rblock;
   const bool all = 2 * rblock + 1 >= nz;
   // staging with cp.async: every load of the block is in flight at once (the kernel is latency-bound
-  // otherwise).  Only planes / table entries inside the block's largest window are fetched.
-  for (int t = threadIdx.x; t < nzl; t += blockDim.x) {
-    bool need = all;
-    for (int zo = 0; zo < nzo && !need; ++zo) {
-      int d = (zout_list[zo] - zin_lo - zs_lo - t) % nz;
-      if (d < 0) d += nz;
-      need = min(d, nz - d) <= rblock;
-    }
-    if (need)
-      for (int cc = 0; cc < cols; ++cc)
-        cp_async<16>(&rh[t * cols + cc], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
+  // otherwise).  Only the table entries inside the block's largest window are fetched.
+  for (int idx = threadIdx.x; idx < nzl * cols; idx += blockDim.x) {
+    const int t = idx / cols, cc = idx - t * cols;
+    cp_async<16>(&rh[idx], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
   }
   for (int cc = 0; cc < cols; ++cc) {
     const int c = min(c0 + cc, ncol - 1);
@@ -265,28 +258,40 @@ ele_index_kernel(PPPMGeom g, int n_ele, const int *__restrict__ part2grid, int *
     }
 }
 
+// flat per-point stencil table of the static electrode atoms: offset into the compact potential
+// brick and the weight product w_z w_y w_x (same multiplication order as pppm_conp.cpp:287-293)
+__global__ void __launch_bounds__(128)
+ele_point_table_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, const double *__restrict__ weights,
+                       int *__restrict__ poff, double *__restrict__ pw) {
+  const int order = g.order, npts = order * order * order;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gid / npts);
+  if (i >= n_ele) return;
+  const int t = (int)(gid - (long long)i * npts);
+  const int n = t / (order * order);
+  const int r = t - n * order * order;
+  const int m = r / order, l = r - m * order;
+  const double *w = weights + (size_t)i * 3 * order;
+  const int *wi = widx + (size_t)i * 3 * order;
+  poff[gid] = (wi[2 * order + n] * g.ny + wi[order + m]) * g.nx + wi[l];
+  pw[gid] = w[2 * order + n] * w[order + m] * w[l];
+}
+
 // one warp per electrode row: b_k = -sum w u (pppm_conp.cpp:285-298), slab
 // term (:301-313), then b = b_k + b_real
 __global__ void __launch_bounds__(256)
-gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ widx,
-                const double *__restrict__ weights, const double *__restrict__ u_brick,
+gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ poff,
+                const double *__restrict__ pw, const double *__restrict__ u_brick,
                 const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
                 const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
   if (i >= row_end) return;
-  const int order = g.order;
-  const double *w = weights + (size_t)i * 3 * order;
-  const int *wi = widx + (size_t)i * 3 * order;
-  const int npts = order * order * order;
+  const int npts = g.order * g.order * g.order;
+  const int *po = poff + (size_t)i * npts;
+  const double *w = pw + (size_t)i * npts;
   double acc = 0.0;
-  for (int t = lane; t < npts; t += 32) {
-    const int n = t / (order * order);
-    const int r = t - n * order * order;
-    const int m = r / order, l = r - m * order;
-    const double x0 = w[2 * order + n] * w[order + m] * w[l];
-    acc = fma(x0, u_brick[((size_t)wi[2 * order + n] * g.ny + wi[order + m]) * g.nx + wi[l]], acc);
-  }
+  for (int t = lane; t < npts; t += 32) acc = fma(w[t], u_brick[po[t]], acc);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
@@ -404,12 +409,21 @@ int launch_pppm_ele_index(cudaStream_t s, const PPPMGeom &g, int n, const int *p
   return 1;
 }
 
-int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *widx,
-                         const double *weights, const double *u_brick, const double *ez, const double *qz_sum,
+int launch_pppm_point_table(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,
+                            int *poff, double *pw) {
+  if (n <= 0) return 0;
+  const long long threads = (long long)n * g.order * g.order * g.order;
+  ele_point_table_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(g, n, widx, weights, poff, pw);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *poff,
+                         const double *pw, const double *u_brick, const double *ez, const double *qz_sum,
                          double slab_pref, const double *b_real, double *b_kspace, double *b) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
-  gather_b_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, row_begin, row_end, widx, weights, u_brick, ez, qz_sum,
+  gather_b_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez, qz_sum,
                                               slab_pref, b_real, b_kspace, b);
   CUDA_CHECK(cudaGetLastError());
   return 1;

@@ -103,7 +103,7 @@ def test_two_atom_electrodes():
         s.mol[right[1:]] = 998
         lmp.group_molecule("eleleft", 81)
         lmp.group_molecule("eleright", 82)
-        return lmp, [a for a in arg if a not in ("etypes", "1", "3")][:8] + ["ffield"]
+        return lmp, "e eleleft conp 1 eleright 1.979 1.0 log_conp ffield".split()
     fix, ref, q, qr = both(case)
     assert fix.N == 2
     close(q, qr)
