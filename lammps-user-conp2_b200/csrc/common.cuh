@@ -267,9 +267,10 @@ int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int r
                          const double *pw, const double *u_brick, const double *ez, const double *qz_sum,
                          double slab_pref /* 4 pi / V or 0 */, const double *b_real, double *b_kspace, double *b);
 // electrode re-spread; forms q_i = sb_i + potdiff*setq_i (+qinit_i) on the fly and stores it to q_out
-int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,
-                           const double *sb, const double *setq, const double *qinit, const double *scal,
-                           double *q_out, double *brick);
+// (spreads rows [row_begin,row_end) only; all n charges are written to q_out)
+int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, int row_begin, int row_end, const int *widx,
+                           const double *weights, const double *sb, const double *setq, const double *qinit,
+                           const double *scal, double *q_out, double *brick);
 int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out);
 
 // ewald.cu -----------------------------------------------------------------

@@ -335,7 +335,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   const double *qinit = c->have_qinit ? c->d_qinit.p : nullptr;
   if (kspace_mode == CONP_KSPACE_PPPM) {  // charges + kspmod->update_charge() -> ele_make_rho
     CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, s));
-    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->d_widx.p, c->d_weights.p, c->d_sb.p,
+    c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->r0, c->r1, c->d_widx.p, c->d_weights.p, c->d_sb.p,
                                           c->d_setq.p, qinit, c->scal(0), c->d_q.p, c->d_ebrick.p);
   } else {
     c->launches += launch_finalize_q(s, c->N, c->d_sb.p, c->d_setq.p, qinit, c->scal(0), c->d_q.p);
@@ -1173,11 +1173,15 @@ int conp_get_density(conp_ctx *c, int which, double *brick_out) {
                                           full.p);
       if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);
     }
-    if (which == 1) c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, full.p);
+    if (which == 1) {
+      c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, full.p);
+      if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);  // ranks spread their own rows
+    }
     if (which == 2) {
       DevBuf<double> fe;
       fe.zero(c->ngrid, s);
       c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, fe.p);
+      if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, fe.p, c->ngrid, s);
       c->launches += launch_add_bricks(s, c->ngrid, full.p, fe.p, full.p);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }

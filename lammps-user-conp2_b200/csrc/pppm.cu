@@ -306,15 +306,18 @@ gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ 
 // The new charge q_i = (S.b)_i + potdiff*setq_i (+qinit_i) (fix_conp.cpp:1153-1158)
 // is formed here from the epilogue scalars and stored by the atom's first thread.
 __global__ void __launch_bounds__(256)
-ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, const double *__restrict__ weights,
-                  const double *__restrict__ sb, const double *__restrict__ setq,
-                  const double *__restrict__ qinit, const double *__restrict__ scal, double *__restrict__ q_out,
-                  double *__restrict__ brick) {
+ele_spread_kernel(PPPMGeom g, int n_ele, int row_begin, int row_end, const int *__restrict__ widx,
+                  const double *__restrict__ weights, const double *__restrict__ sb,
+                  const double *__restrict__ setq, const double *__restrict__ qinit,
+                  const double *__restrict__ scal, double *__restrict__ q_out, double *__restrict__ brick) {
   const int order = g.order;
   const int per_atom = order * order;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(gid / per_atom);
   if (i >= n_ele) return;
+  // every rank forms all charges (the host scatters them to local + ghost atoms) but spreads only
+  // its own rows; the bricks are summed across ranks when the host asks for the density
+  const bool mine = i >= row_begin && i < row_end;
   const int nm = (int)(gid - (long long)i * per_atom);
   const int n = nm / order, m = nm - n * order;
   const double *w = weights + (size_t)i * 3 * order;
@@ -322,6 +325,7 @@ ele_spread_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, const dou
   double qi = sb[i] + scal[1] * setq[i];
   if (qinit) qi += qinit[i];
   if (nm == 0) q_out[i] = qi;
+  if (!mine) return;
   const double z0 = g.delvolinv * qi;  // pppm_conp.cpp:411
   const double x0 = z0 * w[2 * order + n] * w[order + m];
   double *row = brick + ((size_t)wi[2 * order + n] * g.ny + wi[order + m]) * g.nx;
@@ -429,13 +433,13 @@ int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int r
   return 1;
 }
 
-int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, const int *widx, const double *weights,
-                           const double *sb, const double *setq, const double *qinit, const double *scal,
-                           double *q_out, double *brick) {
+int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, int row_begin, int row_end, const int *widx,
+                           const double *weights, const double *sb, const double *setq, const double *qinit,
+                           const double *scal, double *q_out, double *brick) {
   if (n <= 0) return 0;
   const long long threads = (long long)n * g.order * g.order;
-  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, widx, weights, sb, setq, qinit,
-                                                                     scal, q_out, brick);
+  ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, row_begin, row_end, widx, weights, sb,
+                                                                     setq, qinit, scal, q_out, brick);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

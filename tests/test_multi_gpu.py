@@ -44,8 +44,11 @@ def _worker(rank, world, uid_file, case_name, out_file):
     f, ecoul, eself, vir = fix.post_force()
     b, bk = fix.ctx.get_b()
     info = fix.ctx.info()
+    extra = {}
+    if case_name == "small_pppm":  # bricks are sharded (electrolyte by z-slab, electrode by rows): gathered on demand
+        extra = dict(rho=fix.ctx.get_density(0), rho_e=fix.ctx.get_density(1), u=fix.ctx.get_potential_brick())
     np.savez(out_file % rank, q=q, q2=q2, scalar=fix.scalar_output, b=b, rows=[info.row_begin, info.row_end],
-             eself=eself, ecoul=ecoul)
+             eself=eself, ecoul=ecoul, **extra)
     fix.close()
 
 
@@ -90,3 +93,8 @@ def test_two_ranks_match_oracle(tmp_path, case_name):
         assert np.abs(r["b"] - ref.bbb_all).max() <= 5e-12 * max(np.abs(ref.bbb_all).max(), 1.0)
         assert abs(float(r["scalar"]) - ref.scalar_output) <= 1e-9 * abs(ref.scalar_output) + 1e-12
     assert np.array_equal(res[0]["q2"], res[1]["q2"])  # replicated epilogue is bitwise identical
+    if case_name == "small_pppm":
+        for r in res:
+            assert np.abs(r["rho"] - ref.elyte_density).max() <= 1e-12 * np.abs(ref.elyte_density).max()
+            assert np.abs(r["rho_e"] - ref.ele_density).max() <= 1e-9 * np.abs(ref.ele_density).max() + 1e-15
+            assert np.abs(r["u"] - ref.u_brick).max() <= 1e-11 * np.abs(ref.u_brick).max()
