@@ -79,7 +79,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -167,8 +167,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--kspace", default="pppm", choices=["pppm", "ewald"])
@@ -304,8 +304,11 @@ def main():
     b_update = (8.0 * nrows * N + 8.0 * N + 16.0 * nrows + 32.0 * M
                 + ((24.0 * G + 24.0 * order * nrows) if kmode == 1 else
                    (16.0 * info.kcount + 16.0 * info.kcount_flat * nrows)))
+    # dram__bytes_read.sum + dram__bytes_write.sum of one gemv_tma_kernel launch, ncu --set full capture of
+    # this workload (profiles/r01_ncu_full_prof_r1a.txt: 800.11 MB read + 3.30 MB written); other shapes: null
+    traffic = 803.41e6 if (name == "cfg4" and world == 1) else None
     roofline = {"bound": "hbm", "kernel": "gemv_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": gemv_bytes, "launch_ms_in_pipeline": gemv_ms, "launch_ms_alone": gemv_alone_ms,
                 "update_bytes": b_update, "update_achieved_gbs": b_update / (ms_step * 1e-3) / 1e9,
                 "update_frac": b_update / (ms_step * 1e-3) / 1e9 / peak,

@@ -130,6 +130,12 @@ struct __align__(32) EPos {
   int idx, type;
 };
 
+// one x-contiguous run of cells [c0, c1) seen through the periodic image shift (sx, sy, sz)
+struct PairRun {
+  int c0, c1;
+  short sx, sy, sz, pad;
+};
+
 // ---------------------------------------------------------------------------
 // geometry of the uniform cell grid used to bin point charges
 // ---------------------------------------------------------------------------
@@ -215,6 +221,8 @@ CellGrid make_cell_grid(const double lo[3], const double prd[3], const int perio
 void build_electrode_cells(const CellGrid &g, int begin, int end, const double *xyz, const int *type,
                            std::vector<EPos> &sorted, std::vector<int> &cell_start);
 void build_near_mask(const CellGrid &g, int begin, int end, const double *xyz, std::vector<unsigned char> &mask);
+void build_pair_runs(const CellGrid &g, int begin, int end, const double *xyz, std::vector<int> &run_start,
+                     std::vector<PairRun> &runs);
 // per-step counting sort of the point charges: pack (+histogram, + sum q z), scan, scatter
 int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
                       const double *q, const int *type, PosQ *packed, int *packed_type, int *cell_of, int *slot,
@@ -233,11 +241,13 @@ int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packe
                      int *near_list, int *near_count);
 // b_real[i] = -sum_j q_j dudq(r_ij), rows [row_begin,row_end), against the cell-sorted point charges
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
-                  const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const float4 *sorted_f, const int *cell_start, double *b_real);
+                  const double *ex, const double *ey, const double *ez, const int *etype, const int *run_start,
+                  const PairRun *runs, const PosQ *sorted, const int *sorted_type, const float4 *sorted_f,
+                  const int *cell_start, double *b_real);
 int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
                   const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
-                  const double *ez, const int *etype, double *A_rows, size_t pitch);
+                  const double *ez, const int *etype, const int *run_start, const PairRun *runs, double *A_rows,
+                  size_t pitch);
 int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e,
                           const EPos *esorted, const int *cell_start, const double *q_ele, const PosQ *packed,
                           const int *packed_type, const int *near_list, const int *near_count, int max_near,

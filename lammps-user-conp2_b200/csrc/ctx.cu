@@ -81,7 +81,8 @@ struct conp_ctx {
   CellGrid grid_b;
   bool static_cells = false;
   DevBuf<EPos> d_esorted;
-  DevBuf<int> d_ecellstart;
+  DevBuf<int> d_ecellstart, d_runstart;
+  DevBuf<PairRun> d_runs;
   DevBuf<unsigned char> d_nearmask;
 
   // pppm ---------------------------------------------------------------------------
@@ -173,6 +174,11 @@ void ensure_static_cells(conp_ctx *c) {
   build_electrode_cells(c->grid_b, c->r0, c->r1, c->h_xyz.data(), c->h_type.data(), sorted, cs);
   build_near_mask(c->grid_b, c->r0, c->r1, c->h_xyz.data(), mask);
   if (sorted.empty()) sorted.resize(1);
+  std::vector<int> run_start;
+  std::vector<PairRun> runs;
+  build_pair_runs(c->grid_b, c->r0, c->r1, c->h_xyz.data(), run_start, runs);
+  c->d_runstart.upload(run_start, c->stream);
+  c->d_runs.upload(runs, c->stream);
   c->d_esorted.upload(sorted, c->stream);
   c->d_ecellstart.upload(cs, c->stream);
   c->d_nearmask.upload(mask, c->stream);
@@ -263,8 +269,8 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   // ---- real-space part of b (blist_coul_cal) ---------------------------------
   if (c->rc_b > 0.0 && c->m_total > 0 && nr > 0) {
     c->launches += launch_pair_b(s, g, pair_tables(c, c->d_cuteff_b.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
-                                 c->d_ez.p, c->d_etype.p, c->d_sorted.p, c->d_stype.p, c->d_sortedf.p,
-                                 c->d_cellstart.p, c->d_breal.p);
+                                 c->d_ez.p, c->d_etype.p, c->d_runstart.p, c->d_runs.p, c->d_sorted.p,
+                                 c->d_stype.p, c->d_sortedf.p, c->d_cellstart.p, c->d_breal.p);
   } else {
     CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * std::max(nr, 1), s));
   }
@@ -870,12 +876,18 @@ int conp_build_A(conp_ctx *c) {
       std::vector<EPos> sorted;
       std::vector<int> cs;
       build_electrode_cells(g, 0, N, c->h_xyz.data(), c->h_type.data(), sorted, cs);
+      std::vector<int> run_start;
+      std::vector<PairRun> runs;
+      build_pair_runs(g, c->r0, c->r1, c->h_xyz.data(), run_start, runs);
       DevBuf<EPos> dsorted;
-      DevBuf<int> dcs;
+      DevBuf<int> dcs, drs;
+      DevBuf<PairRun> druns;
       dsorted.upload(sorted, s);
       dcs.upload(cs, s);
+      drs.upload(run_start, s);
+      druns.upload(runs, s);
       c->launches += launch_pair_A(s, g, pair_tables(c, c->d_cuteff_a.p), dsorted.p, dcs.p, c->r0, c->r1, c->d_ex.p,
-                                   c->d_ey.p, c->d_ez.p, c->d_etype.p, c->d_mat.p, c->pitch);
+                                   c->d_ey.p, c->d_ez.p, c->d_etype.p, drs.p, druns.p, c->d_mat.p, c->pitch);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
     CUDA_CHECK(cudaEventRecord(c->ev[15], s));

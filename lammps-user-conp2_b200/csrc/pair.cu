@@ -304,17 +304,20 @@ __device__ __forceinline__ void traverse(const CellGrid &g, const int *__restric
   }
 }
 
-// One warp per electrode row i of [row_begin, row_end).
+// One warp per electrode row i of [row_begin, row_end).  Electrode atoms never move, so the
+// x-contiguous runs of cells (and the periodic image shift of each) that the cut-off sphere of
+// row i overlaps are enumerated once on the host (build_pair_runs); the kernel walks that flat list.
 // MODE_B: targets = cell-sorted point charges; b_real[i] = -sum_j q_j dudq (fix_conp.cpp:1339).
 //         Candidates are screened in FP32 (positions relative to the box corner, threshold
-//         widened by 1e-4 so no true pair is lost); survivors are re-tested exactly in FP64
+//         widened so no true pair is lost); survivors are re-tested exactly in FP64
 //         against cutsq / cut_coulsq when they are consumed.
 // MODE_A: targets = cell-sorted electrode atoms; A[i][j] += dudq (fix_conp.cpp:1270), self images kept
 template <int MODE>
 __global__ void __launch_bounds__(PAIR_WARPS * 32, 4)
 pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double *__restrict__ ex,
             const double *__restrict__ ey, const double *__restrict__ ez, const int *__restrict__ etype,
-            const int *__restrict__ cell_start,
+            const int *__restrict__ cell_start, const int *__restrict__ run_start,
+            const PairRun *__restrict__ runs,
             const PosQ *__restrict__ sorted, const int *__restrict__ sorted_type,  // MODE_B targets
             const float4 *__restrict__ sorted_f, float cutmax_f,
             const EPos *__restrict__ esorted,                                      // MODE_A targets
@@ -344,43 +347,49 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
       atomicAdd(A_row + wq.i[e], dudq_pair<MODE_A>(pt, wq.rsq[e], it, wq.t[e]));
     }
   };
-  traverse(g, cell_start, xi, yi, zi, lane, [&](bool valid, int k, double shx, double shy, double shz) {
-    bool pass = false;
-    double rsq = 0.0;
-    int jt = 0, jidx = 0;
-    if (MODE == MODE_B) {
-      if (valid) {
-        const float4 pf = sorted_f[k];
-        const float fx = (float)(xi - shx - g.lo[0]) - pf.x;
-        const float fy = (float)(yi - shy - g.lo[1]) - pf.y;
-        const float fz = (float)(zi - shz - g.lo[2]) - pf.z;
-        pass = fx * fx + fy * fy + fz * fz < cutmax_f;
+  const int r0 = run_start[i - row_begin], r1 = run_start[i - row_begin + 1];
+  for (int r = r0; r < r1; ++r) {
+    const PairRun run = runs[r];
+    const double shx = run.sx * g.prd[0], shy = run.sy * g.prd[1], shz = run.sz * g.prd[2];
+    const float fxi = (float)(xi - shx - g.lo[0]), fyi = (float)(yi - shy - g.lo[1]), fzi = (float)(zi - shz - g.lo[2]);
+    const int jb = __ldg(cell_start + run.c0), je = __ldg(cell_start + run.c1);
+    for (int j0 = jb; j0 < je; j0 += 32) {
+      const int k = j0 + lane;
+      bool pass = false;
+      double rsq = 0.0;
+      int jt = 0, jidx = 0;
+      if (k < je) {
+        if (MODE == MODE_B) {
+          const float4 pf = sorted_f[k];
+          const float fx = fxi - pf.x, fy = fyi - pf.y, fz = fzi - pf.z;
+          pass = fx * fx + fy * fy + fz * fz < cutmax_f;
+        } else {
+          const EPos e = esorted[k];
+          jt = e.type; jidx = e.idx;
+          const double dx = xi - (e.x + shx), dy = yi - (e.y + shy), dz = zi - (e.z + shz);
+          rsq = dx * dx + dy * dy + dz * dz;
+          pass = rsq < __ldg(cut_row + jt);
+          if (jidx == i && run.sx == 0 && run.sy == 0 && run.sz == 0) pass = false;
+        }
       }
-    } else if (valid) {
-      const EPos e = esorted[k];
-      jt = e.type; jidx = e.idx;
-      const double dx = xi - (e.x + shx), dy = yi - (e.y + shy), dz = zi - (e.z + shz);
-      rsq = dx * dx + dy * dy + dz * dz;
-      pass = rsq < __ldg(cut_row + jt);
-      if (jidx == i && shx == 0.0 && shy == 0.0 && shz == 0.0) pass = false;
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, pass);
-    if (pass) {
-      const int pos = qn + __popc(mask & lt_mask);
-      if (MODE == MODE_B) {
-        wq.rsq[pos] = shx; wq.aux[pos] = shy; wq.shz[pos] = shz; wq.i[pos] = k;
-      } else {
-        wq.rsq[pos] = rsq; wq.i[pos] = jidx; wq.t[pos] = jt;
+      const unsigned mask = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        const int pos = qn + __popc(mask & lt_mask);
+        if (MODE == MODE_B) {
+          wq.rsq[pos] = shx; wq.aux[pos] = shy; wq.shz[pos] = shz; wq.i[pos] = k;
+        } else {
+          wq.rsq[pos] = rsq; wq.i[pos] = jidx; wq.t[pos] = jt;
+        }
+      }
+      qn += __popc(mask);
+      if (qn >= 32) {
+        __syncwarp();
+        consume(qn - 32 + lane);
+        qn -= 32;
+        __syncwarp();
       }
     }
-    qn += __popc(mask);
-    if (qn >= 32) {
-      __syncwarp();
-      consume(qn - 32 + lane);
-      qn -= 32;
-      __syncwarp();
-    }
-  });
+  }
   __syncwarp();
   if (lane < qn) consume(lane);
   if (MODE == MODE_B) {
@@ -507,6 +516,68 @@ inline int h_cell(const CellGrid &g, int a, double x) {
 }
 }  // namespace
 
+// Static traversal lists: for every electrode row of [begin, end) the x-contiguous runs of cells
+// (as a [c0, c1) range of cell indices) and image shifts its cut-off sphere overlaps -- the same
+// enumeration as the device-side traverse(), done once because electrodes never move.  Runs that
+// are adjacent in cell order and share a shift are merged.
+void build_pair_runs(const CellGrid &g, int begin, int end, const double *xyz, std::vector<int> &run_start,
+                     std::vector<PairRun> &runs) {
+  run_start.assign((size_t)std::max(end - begin, 0) + 1, 0);
+  runs.clear();
+  const double rc = g.rc;
+  const double csy = g.prd[1] / g.nc[1], csz = g.prd[2] / g.nc[2];
+  const double rc2 = rc * rc * 1.0001;
+  for (int i = begin; i < end; ++i) {
+    const double xi = xyz[3 * (size_t)i], yi = xyz[3 * (size_t)i + 1], zi = xyz[3 * (size_t)i + 2];
+    for (int sz = -g.smax[2]; sz <= g.smax[2]; ++sz) {
+      const double shz = sz * g.prd[2];
+      int lz = (int)std::floor((zi - shz - rc - g.lo[2]) * g.cinv[2]);
+      int hz = (int)std::floor((zi - shz + rc - g.lo[2]) * g.cinv[2]);
+      if (g.periodic[2] && (hz < 0 || lz > g.nc[2] - 1)) continue;
+      lz = std::max(0, std::min(lz, g.nc[2] - 1));
+      hz = std::max(0, std::min(hz, g.nc[2] - 1));
+      for (int sy = -g.smax[1]; sy <= g.smax[1]; ++sy) {
+        const double shy = sy * g.prd[1];
+        int ly = (int)std::floor((yi - shy - rc - g.lo[1]) * g.cinv[1]);
+        int hy = (int)std::floor((yi - shy + rc - g.lo[1]) * g.cinv[1]);
+        if (g.periodic[1] && (hy < 0 || ly > g.nc[1] - 1)) continue;
+        ly = std::max(0, std::min(ly, g.nc[1] - 1));
+        hy = std::max(0, std::min(hy, g.nc[1] - 1));
+        for (int sx = -g.smax[0]; sx <= g.smax[0]; ++sx) {
+          const double shx = sx * g.prd[0];
+          int lx = (int)std::floor((xi - shx - rc - g.lo[0]) * g.cinv[0]);
+          int hx = (int)std::floor((xi - shx + rc - g.lo[0]) * g.cinv[0]);
+          if (g.periodic[0] && (hx < 0 || lx > g.nc[0] - 1)) continue;
+          lx = std::max(0, std::min(lx, g.nc[0] - 1));
+          hx = std::max(0, std::min(hx, g.nc[0] - 1));
+          const double fy = yi - shy - g.lo[1], fz = zi - shz - g.lo[2];
+          for (int cz = lz; cz <= hz; ++cz) {
+            double dz = std::max(std::max(cz * csz - fz, fz - (cz + 1) * csz), 0.0);
+            if (!g.periodic[2] && (cz == 0 || cz == g.nc[2] - 1)) dz = 0.0;  // edge cells hold clamped atoms
+            for (int cy = ly; cy <= hy; ++cy) {
+              double dy = std::max(std::max(cy * csy - fy, fy - (cy + 1) * csy), 0.0);
+              if (!g.periodic[1] && (cy == 0 || cy == g.nc[1] - 1)) dy = 0.0;
+              if (dy * dy + dz * dz > rc2) continue;
+              const int base = (cz * g.nc[1] + cy) * g.nc[0];
+              PairRun run;
+              run.c0 = base + lx; run.c1 = base + hx + 1;
+              run.sx = (short)sx; run.sy = (short)sy; run.sz = (short)sz; run.pad = 0;
+              const size_t first = (size_t)run_start[i - begin];
+              if (runs.size() > first && runs.back().c1 == run.c0 && runs.back().sx == run.sx &&
+                  runs.back().sy == run.sy && runs.back().sz == run.sz)
+                runs.back().c1 = run.c1;  // contiguous in cell order: merge
+              else
+                runs.push_back(run);
+            }
+          }
+        }
+      }
+    }
+    run_start[(size_t)(i - begin) + 1] = (int)runs.size();
+  }
+  if (runs.empty()) runs.resize(1);
+}
+
 // Counting sort of electrode rows [begin, end) into grid g (host; electrodes are static).
 void build_electrode_cells(const CellGrid &g, int begin, int end, const double *xyz, const int *type,
                            std::vector<EPos> &sorted, std::vector<int> &cell_start) {
@@ -610,8 +681,9 @@ int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packe
 }
 
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
-                  const double *ex, const double *ey, const double *ez, const int *etype, const PosQ *sorted,
-                  const int *sorted_type, const float4 *sorted_f, const int *cell_start, double *b_real) {
+                  const double *ex, const double *ey, const double *ez, const int *etype, const int *run_start,
+                  const PairRun *runs, const PosQ *sorted, const int *sorted_type, const float4 *sorted_f,
+                  const int *cell_start, double *b_real) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
   // FP32 screen radius: the grid's search radius widened so that rounding cannot reject a true pair.
@@ -621,20 +693,21 @@ int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int r
   const double slack = 2.0 * (2.0 * std::sqrt(3.0) * g.rc * 4.0 * extent * 1.1920929e-7) + 1e-4 * g.rc * g.rc;
   const float cutmax_f = (float)(g.rc * g.rc + slack);
   pair_kernel<MODE_B><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, sorted, sorted_type, sorted_f, cutmax_f, nullptr,
-      b_real, 0);
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, run_start, runs, sorted, sorted_type, sorted_f,
+      cutmax_f, nullptr, b_real, 0);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
 int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
                   const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
-                  const double *ez, const int *etype, double *A_rows, size_t pitch) {
+                  const double *ez, const int *etype, const int *run_start, const PairRun *runs, double *A_rows,
+                  size_t pitch) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
   pair_kernel<MODE_A><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
-      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, nullptr, nullptr, nullptr, 0.0f, esorted, A_rows,
-      pitch);
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, run_start, runs, nullptr, nullptr, nullptr, 0.0f,
+      esorted, A_rows, pitch);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
