@@ -65,6 +65,22 @@ def make_case(name, kspace):
     return lmp, arg
 
 
+DEFAULT_WORKLOAD = "cfg5"  # BASELINE configs[4]: the configuration the 1/2/4/8-GPU metric is quoted on; fits one GPU
+
+
+def synthetic_matrix(n):
+    """Row-neutral random stand-in for S (profiling / reference-arm timing only): a random
+    n x 256 block tiled across the columns, cheap to build even at n = 40 000 (12.8 GB)."""
+    rng = np.random.default_rng(1234)
+    blk = rng.standard_normal((n, 256)) * 1e-3
+    blk -= blk.mean(axis=1, keepdims=True)
+    S = np.empty((n, n))
+    for c0 in range(0, n, 256):
+        w = min(256, n - c0)
+        S[:, c0:c0 + w] = blk[:, :w]
+    return S
+
+
 def jitter_sets(x, nsets, seed):
     rng = np.random.default_rng(seed)
     return [x + rng.normal(0.0, JITTER, x.shape) for _ in range(nsets)]
@@ -140,15 +156,12 @@ def run_reference(args, rank, world):
     """Reference arm: CPU port of the reference's per-step path, all host cores."""
     if rank != 0:
         return
-    name = args.workload or ("cfg4" if world == 1 else "cfg5")
+    name = args.workload or DEFAULT_WORKLOAD
     lmp, arg = make_case(name, args.kspace)
     n_ele = int((lmp.system.mol > 0).sum())
-    rng = np.random.default_rng(1234)
     # S only feeds the O(N^2) matvec, whose cost does not depend on its values; the
     # true S needs the O(N^2 K) A build, which no CPU finishes in minutes at this size.
-    S = rng.standard_normal((n_ele, n_ele)) * 1e-3
-    S = 0.5 * (S + S.T)
-    S -= S.mean(axis=1, keepdims=True)
+    S = synthetic_matrix(n_ele)
     per_step_budget = 8.0
     ups, n, cores = cpu_port_updates_per_s(lmp, arg, S, per_step_budget * max(1, min(args.steps, 3)), args.kspace)
     line = {
@@ -157,7 +170,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": describe(name), "kspace": args.kspace},
         "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} full updates of the same workload (random symmetric S, true b path)"},
+                         "sample": f"{n} full updates of the same workload (random stand-in S, true b path)"},
         "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference algorithm (oracle/), not the reference binary: LAMMPS is not available",
     }
@@ -167,8 +180,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--kspace", default="pppm", choices=["pppm", "ewald"])
@@ -205,16 +218,13 @@ def main():
         dist.broadcast(buf, 0)
         uid = bytes(buf.cpu().numpy().tobytes())
 
-    name = args.workload or ("cfg4" if world == 1 else "cfg5")
+    name = args.workload or DEFAULT_WORKLOAD
     lmp, arg = make_case(name, args.kspace)
     t0 = time.perf_counter()
     fix = make_fix(lmp, arg, device=local_rank, rank=rank, nranks=world, unique_id=uid)
     if args.fast_setup:
         fix.setup_post_neighbor()
-        n_ele = fix.N
-        rng = np.random.default_rng(1234)
-        Sr = rng.standard_normal((n_ele, n_ele)) * 1e-3
-        Sr -= Sr.mean(axis=1, keepdims=True)
+        Sr = synthetic_matrix(fix.N)
         fix.ctx.load_matrix(Sr, True)
         del Sr
         fix.totsetq = fix.ctx.set_unit_voltage(fix.evscale)
@@ -304,9 +314,10 @@ def main():
     b_update = (8.0 * nrows * N + 8.0 * N + 16.0 * nrows + 32.0 * M
                 + ((24.0 * G + 24.0 * order * nrows) if kmode == 1 else
                    (16.0 * info.kcount + 16.0 * info.kcount_flat * nrows)))
-    # dram__bytes_read.sum + dram__bytes_write.sum of one gemv_tma_kernel launch, ncu --set full capture of
-    # this workload (profiles/r01_ncu_full_prof_r1a.txt: 800.11 MB read + 3.30 MB written); other shapes: null
-    traffic = 803.41e6 if (name == "cfg4" and world == 1) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one gemv_tma_kernel launch from the ncu --set full
+    # captures of these workloads on one GPU (profiles/r01_ncu_full_gemv_cfg5.txt: 12.801121 GB read +
+    # 6.87 MB written; profiles/r01_ncu_full_prof_r1a.txt: 800.11 MB + 3.30 MB); other shapes: null
+    traffic = {"cfg5": 12.801121e9 + 6.872832e6, "cfg4": 800.11392e6 + 3.297536e6}.get(name) if world == 1 else None
     roofline = {"bound": "hbm", "kernel": "gemv_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": gemv_bytes, "launch_ms_in_pipeline": gemv_ms, "launch_ms_alone": gemv_alone_ms,

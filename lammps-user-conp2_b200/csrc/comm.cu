@@ -10,7 +10,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstddef>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace conp {
 
@@ -128,6 +132,265 @@ void comm_allgatherv(Comm *c, const void *send, void *recv, const size_t *bytes,
 void comm_allreduce_sum_f64(Comm *c, double *buf, size_t n, cudaStream_t s) {
   if (!c || c->nranks == 1) return;
   NCCL_CHECK(api().AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, s));
+}
+
+// ===========================================================================
+// direct peer-to-peer exchanges
+// ===========================================================================
+struct PeerArena {
+  Comm *comm = nullptr;
+  int rank = 0, nranks = 1;
+  size_t bytes = 0;
+  char *local = nullptr;
+  std::vector<char *> peer;        // mapped base of every rank's arena (peer[rank] == local)
+  char **d_peer = nullptr;         // device copy
+  // control block at the start of every arena: flags[chan][rank] (written by peers), then local-only
+  // epoch[chan] and an error word
+  static constexpr size_t CTRL_BYTES = 4096;
+};
+
+namespace {
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct ArenaCtl {  // layout of the control block
+  unsigned long long flags[P2P_CHANNELS][16];
+  unsigned long long epoch[P2P_CHANNELS];
+  int error;
+};
+static_assert(sizeof(ArenaCtl) <= PeerArena::CTRL_BYTES, "control block too large");
+
+// grid = (blocks_per_peer, nranks-1); peer index p = (rank + 1 + blockIdx.y) % nranks
+__global__ void __launch_bounds__(256)
+p2p_push_kernel(char *const *__restrict__ arena, int rank, int nranks, size_t off, size_t bytes, int chan) {
+  const int p = (rank + 1 + blockIdx.y) % nranks;
+  const uint4 *src = reinterpret_cast<const uint4 *>(arena[rank] + off);
+  uint4 *dst = reinterpret_cast<uint4 *>(arena[p] + off);
+  const size_t n16 = bytes / 16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  // last block of this peer's column raises the flag once all of the column's stores are out
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(arena[rank]);
+  if (threadIdx.x == 0) {
+    // per-peer arrival counter lives in the (local-only) tail of my control block
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(arena[rank] + sizeof(ArenaCtl)) + chan * 16 + p;
+    const unsigned int t = atomicAdd(cnt, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *cnt = 0u;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    const unsigned long long e = mine->epoch[chan] + 1ull;  // bumped by the wait kernel that follows
+    ArenaCtl *theirs = reinterpret_cast<ArenaCtl *>(arena[p]);
+    __threadfence_system();
+    st_release_sys(&theirs->flags[chan][rank], e);
+  }
+}
+
+__global__ void __launch_bounds__(32)
+p2p_wait_kernel(char *const *__restrict__ arena, int rank, int nranks, int chan) {
+  ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(arena[rank]);
+  const unsigned long long e = mine->epoch[chan] + 1ull;
+  const int r = threadIdx.x;
+  if (r < nranks && r != rank) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flags[chan][r]) < e) {
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer is gone; fail instead of hanging the GPU
+        mine->error = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  if (r == 0) mine->epoch[chan] = e;
+}
+
+// reduce-scatter stage 2 + all-gather: I own slice `rank` of the vector.  Sum the nranks partial
+// slices (mine from the vector itself, the others from the staging area, in rank order so the result
+// is deterministic), store it into my vector and into every peer's vector, then signal chan.
+__global__ void __launch_bounds__(256)
+p2p_reduce_bcast_kernel(char *const *__restrict__ arena, int rank, int nranks, size_t off, size_t n, size_t slice,
+                        size_t stage_off, int chan) {
+  const size_t lo = (size_t)rank * slice;
+  const size_t cnt = lo < n ? (n - lo < slice ? n - lo : slice) : 0;
+  double *vec = reinterpret_cast<double *>(arena[rank] + off);
+  const double *stage = reinterpret_cast<const double *>(arena[rank] + stage_off);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int r = 0; r < nranks; ++r) v += (r == rank) ? vec[lo + i] : stage[(size_t)r * slice + i];
+    for (int p = 0; p < nranks; ++p) reinterpret_cast<double *>(arena[p] + off)[lo + i] = v;
+  }
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(arena[rank]);
+  if (threadIdx.x == 0) {
+    unsigned int *c2 = reinterpret_cast<unsigned int *>(arena[rank] + sizeof(ArenaCtl)) + chan * 16 + 15;
+    const unsigned int t = atomicAdd(c2, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *c2 = 0u;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < nranks && (int)threadIdx.x != rank) {
+    const unsigned long long e = mine->epoch[chan] + 1ull;
+    ArenaCtl *theirs = reinterpret_cast<ArenaCtl *>(arena[threadIdx.x]);
+    __threadfence_system();
+    st_release_sys(&theirs->flags[chan][rank], e);
+  }
+}
+
+// reduce-scatter stage 1: send slice o of my partial vector to owner o's staging row `rank`
+__global__ void __launch_bounds__(256)
+p2p_scatter_kernel(char *const *__restrict__ arena, int rank, int nranks, size_t off, size_t n, size_t slice,
+                   size_t stage_off, int chan) {
+  const int o = (rank + 1 + blockIdx.y) % nranks;
+  const size_t lo = (size_t)o * slice;
+  const size_t cnt = lo < n ? (n - lo < slice ? n - lo : slice) : 0;
+  const double *vec = reinterpret_cast<const double *>(arena[rank] + off);
+  double *dst = reinterpret_cast<double *>(arena[o] + stage_off) + (size_t)rank * slice;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = vec[lo + i];
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(arena[rank]);
+  if (threadIdx.x == 0) {
+    unsigned int *c2 = reinterpret_cast<unsigned int *>(arena[rank] + sizeof(ArenaCtl)) + chan * 16 + o;
+    const unsigned int t = atomicAdd(c2, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *c2 = 0u;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    const unsigned long long e = mine->epoch[chan] + 1ull;
+    ArenaCtl *theirs = reinterpret_cast<ArenaCtl *>(arena[o]);
+    __threadfence_system();
+    st_release_sys(&theirs->flags[chan][rank], e);
+  }
+}
+
+}  // namespace
+
+PeerArena *p2p_create(Comm *c, size_t bytes, cudaStream_t s) {
+  if (!c || c->nranks == 1 || c->nranks > 16) return nullptr;
+  if (getenv("CONP_P2P") && atoi(getenv("CONP_P2P")) == 0) return nullptr;
+  PeerArena *a = new PeerArena;
+  a->comm = c; a->rank = c->rank; a->nranks = c->nranks;
+  a->bytes = (bytes + PeerArena::CTRL_BYTES + 255) / 256 * 256;
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  if (cudaMalloc((void **)&a->local, a->bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(a->local, 0, a->bytes, s) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, a->local) != cudaSuccess) ok = 0;
+  // exchange the handles (and everybody's ok flag) through NCCL
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  std::vector<char> h((size_t)c->nranks * rec, 0);
+  char *d = nullptr;
+  cudaMalloc((void **)&d, h.size());
+  std::memcpy(h.data() + (size_t)c->rank * rec, &mine, sizeof(mine));
+  h[(size_t)c->rank * rec + sizeof(mine)] = (char)ok;
+  cudaMemcpyAsync(d + (size_t)c->rank * rec, h.data() + (size_t)c->rank * rec, rec, cudaMemcpyHostToDevice, s);
+  comm_allgather(c, d + (size_t)c->rank * rec, d, rec, s);
+  cudaMemcpyAsync(h.data(), d, h.size(), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  cudaFree(d);
+  for (int r = 0; r < c->nranks; ++r) ok = ok && h[(size_t)r * rec + sizeof(mine)];
+  a->peer.assign(c->nranks, nullptr);
+  if (ok) {
+    for (int r = 0; r < c->nranks && ok; ++r) {
+      if (r == c->rank) { a->peer[r] = a->local; continue; }
+      cudaIpcMemHandle_t hd;
+      std::memcpy(&hd, h.data() + (size_t)r * rec, sizeof(hd));
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+      a->peer[r] = (char *)ptr;
+    }
+  }
+  // agree on the outcome: everybody falls back to NCCL unless every mapping worked
+  {
+    double *flag = nullptr;
+    cudaMalloc((void **)&flag, sizeof(double));
+    const double v = ok ? 0.0 : 1.0;
+    cudaMemcpyAsync(flag, &v, sizeof(double), cudaMemcpyHostToDevice, s);
+    comm_allreduce_sum_f64(c, flag, 1, s);
+    double tot = 0;
+    cudaMemcpyAsync(&tot, flag, sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(flag);
+    if (tot != 0.0) ok = 0;
+  }
+  if (!ok) {
+    p2p_destroy(a);
+    return nullptr;
+  }
+  cudaMalloc((void **)&a->d_peer, sizeof(char *) * c->nranks);
+  cudaMemcpyAsync(a->d_peer, a->peer.data(), sizeof(char *) * c->nranks, cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+  return a;
+}
+
+void p2p_destroy(PeerArena *a) {
+  if (!a) return;
+  for (int r = 0; r < (int)a->peer.size(); ++r)
+    if (r != a->rank && a->peer[r]) cudaIpcCloseMemHandle(a->peer[r]);
+  if (a->d_peer) cudaFree(a->d_peer);
+  if (a->local) cudaFree(a->local);
+  delete a;
+}
+
+char *p2p_local(PeerArena *a) { return a->local + PeerArena::CTRL_BYTES; }
+
+static inline size_t arena_off(size_t off) { return off + PeerArena::CTRL_BYTES; }
+
+int p2p_push(PeerArena *a, size_t off, size_t bytes, int chan, cudaStream_t s) {
+  if (bytes % 16) CONP_THROW(CONP_ERR_ARG, "p2p_push: size must be a multiple of 16 bytes");
+  unsigned bx = (unsigned)std::min<size_t>(32, std::max<size_t>(1, bytes / (16 * 256 * 4)));
+  dim3 grid(bx, a->nranks - 1);
+  p2p_push_kernel<<<grid, 256, 0, s>>>(a->d_peer, a->rank, a->nranks, arena_off(off), bytes, chan);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int p2p_wait(PeerArena *a, int chan, cudaStream_t s) {
+  p2p_wait_kernel<<<1, 32, 0, s>>>(a->d_peer, a->rank, a->nranks, chan);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int p2p_allgather(PeerArena *a, size_t off, size_t stride_bytes, size_t block_bytes, int chan, cudaStream_t s) {
+  int n = p2p_push(a, off + (size_t)a->rank * stride_bytes, block_bytes, chan, s);
+  return n + p2p_wait(a, chan, s);
+}
+
+int p2p_allreduce_f64(PeerArena *a, size_t off, size_t n, size_t stage_off, int chan, cudaStream_t s) {
+  const size_t slice = (n + a->nranks - 1) / a->nranks;
+  unsigned bx = (unsigned)std::min<size_t>(32, std::max<size_t>(1, slice / (256 * 4)));
+  dim3 grid(bx, a->nranks - 1);
+  p2p_scatter_kernel<<<grid, 256, 0, s>>>(a->d_peer, a->rank, a->nranks, arena_off(off), n, slice,
+                                          arena_off(stage_off), chan);
+  CUDA_CHECK(cudaGetLastError());
+  p2p_wait(a, chan, s);
+  p2p_reduce_bcast_kernel<<<bx, 256, 0, s>>>(a->d_peer, a->rank, a->nranks, arena_off(off), n, slice,
+                                             arena_off(stage_off), chan + 1);
+  CUDA_CHECK(cudaGetLastError());
+  p2p_wait(a, chan + 1, s);
+  return 4;
+}
+
+int p2p_error(PeerArena *a) {
+  int e = 0;
+  cudaMemcpy(&e, a->local + offsetof(ArenaCtl, error), sizeof(int), cudaMemcpyDeviceToHost);
+  return e;
 }
 
 }  // namespace conp

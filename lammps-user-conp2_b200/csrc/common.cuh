@@ -70,14 +70,23 @@ template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t cap = 0;
+  bool owned = true;
   ~DevBuf() { release(); }
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
+  }
+  // view into memory owned elsewhere (the peer-to-peer exchange arena)
+  void attach(T *ptr, size_t n) {
+    release();
+    p = ptr;
+    cap = n;
+    owned = false;
   }
   void reserve(size_t n) {
     if (n <= cap) return;
@@ -189,6 +198,26 @@ void comm_allgather(Comm *, const void *send, void *recv, size_t bytes_per_rank,
 void comm_allgatherv(Comm *, const void *send, void *recv, const size_t *bytes, const size_t *offsets,
                      int rank, int nranks, cudaStream_t);
 void comm_allreduce_sum_f64(Comm *, double *buf, size_t n, cudaStream_t);
+
+// ---- direct NVLink exchanges over CUDA-IPC mapped arenas (comm.cu) -------------------------
+// Every rank allocates one arena of the same size; all ranks map each other's arena.  Buffers
+// that are exchanged live at the same offset in every arena.  push = copy my block into every
+// peer's arena and raise my flag there; wait = spin until every peer's flag for that channel has
+// reached the current epoch.  Replaces the small latency-bound NCCL collectives of the step.
+struct PeerArena;
+constexpr int P2P_CHANNELS = 8;
+PeerArena *p2p_create(Comm *, size_t bytes, cudaStream_t);          // collective; nullptr if IPC is unavailable
+void p2p_destroy(PeerArena *);
+char *p2p_local(PeerArena *);
+// copy [off, off+bytes) of my arena to the same place in every peer's arena, then signal `chan`
+int p2p_push(PeerArena *, size_t off, size_t bytes, int chan, cudaStream_t);
+// all-gather with per-rank blocks at off + r*stride: pushes my block and waits for everyone's
+int p2p_allgather(PeerArena *, size_t off, size_t stride_bytes, size_t block_bytes, int chan, cudaStream_t);
+int p2p_wait(PeerArena *, int chan, cudaStream_t);
+// deterministic sum over ranks of n doubles at `off` (result in place on every rank); `stage_off` is
+// scratch of nranks * ceil(n/nranks) doubles; uses channels chan and chan+1
+int p2p_allreduce_f64(PeerArena *, size_t off, size_t n, size_t stage_off, int chan, cudaStream_t);
+int p2p_error(PeerArena *);  // non-zero after a wait timed out
 
 // ---------------------------------------------------------------------------
 // kernel launchers (one .cu per group); all take the context's stream and

@@ -24,6 +24,10 @@ struct conp_ctx {
   int device = 0, rank = 0, nranks = 1, num_sms = 148;
   cudaStream_t stream = nullptr;
   Comm *comm = nullptr;
+  // direct NVLink exchanges (multi-GPU): b, S.b, the output-plane spectra and the packed charges live
+  // in an IPC-mapped arena that every peer writes into; nullptr => NCCL collectives
+  PeerArena *p2p = nullptr;
+  size_t p2p_bytes = 0, off_b = 0, off_sb = 0, off_uhat = 0, off_stage = 0, off_packed = 0;
   std::string err;
   long long launches = 0;
 
@@ -220,6 +224,40 @@ ChargeEpilogue make_epilogue(conp_ctx *c, int variant, bool fused) {
   return ep;
 }
 
+// (Re)build the peer-to-peer arena when the exchanged buffers changed size.  Collective: every rank
+// sees the same sizes, so every rank takes the same branch.
+void ensure_p2p(conp_ctx *c) {
+  if (c->nranks == 1) return;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t n_u = c->have_pppm ? 2 * (size_t)c->pg.nzo * c->ncol : 0;  // doubles in the spectra
+  const size_t slice = (n_u + c->nranks - 1) / c->nranks;
+  const size_t b_bytes = up(sizeof(double) * c->vlen);
+  const size_t u_bytes = up(sizeof(double) * std::max<size_t>(n_u, 2));
+  const size_t st_bytes = up(sizeof(double) * std::max<size_t>(slice * c->nranks, 2));
+  const size_t pk_bytes = up(sizeof(PosQ) * (size_t)std::max(c->m_slots, 1));
+  const size_t need = 2 * b_bytes + u_bytes + st_bytes + pk_bytes;
+  if (c->p2p && need == c->p2p_bytes) return;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->p2p) {
+    c->d_b.release(); c->d_sb.release(); c->d_uhat.release(); c->d_packed.release();
+    p2p_destroy(c->p2p);
+    c->p2p = nullptr;
+  }
+  c->p2p = p2p_create(c->comm, need, c->stream);
+  c->p2p_bytes = need;
+  if (!c->p2p) return;  // IPC not available: stay on NCCL
+  c->off_b = 0;
+  c->off_sb = b_bytes;
+  c->off_uhat = 2 * b_bytes;
+  c->off_stage = c->off_uhat + u_bytes;
+  c->off_packed = c->off_stage + st_bytes;
+  char *base = p2p_local(c->p2p);
+  c->d_b.attach((double *)(base + c->off_b), c->vlen);
+  c->d_sb.attach((double *)(base + c->off_sb), c->vlen);
+  if (c->have_pppm) c->d_uhat.attach((cufftDoubleComplex *)(base + c->off_uhat), n_u / 2);
+  c->d_packed.attach((PosQ *)(base + c->off_packed), (size_t)std::max(c->m_slots, 1));
+}
+
 void stage_mark(conp_ctx *c, int i) {
   if (c->stage_timing) CUDA_CHECK(cudaEventRecord(c->sev[i], c->stream));
 }
@@ -256,7 +294,11 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     // gathered in conp_post_neighbor.
     CUDA_CHECK(cudaMemcpyAsync(&packed_local[c->mpad - 1].x, c->scal(2), sizeof(double), cudaMemcpyDeviceToDevice,
                                s));
-    comm_allgather(c->comm, packed_local, c->d_packed.p, sizeof(PosQ) * (size_t)c->mpad, s);
+    if (c->p2p)
+      c->launches += p2p_allgather(c->p2p, c->off_packed, sizeof(PosQ) * (size_t)c->mpad,
+                                   sizeof(PosQ) * (size_t)c->mpad, 0, s);
+    else
+      comm_allgather(c->comm, packed_local, c->d_packed.p, sizeof(PosQ) * (size_t)c->mpad, s);
     c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, c->d_mcounts.p, c->d_packed.p, c->d_cellof.p,
                                         c->d_slot.p, c->d_cellcount.p);
   }
@@ -304,7 +346,12 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                      c->d_krad.p, c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p,
                                      c->d_uhat.p);
     // every rank holds the partial sum over its slab: one small all-reduce completes the spectra
-    if (multi) comm_allreduce_sum_f64(c->comm, (double *)c->d_uhat.p, 2 * (size_t)pg.nzo * c->ncol, s);
+    if (multi) {
+      if (c->p2p)
+        c->launches += p2p_allreduce_f64(c->p2p, c->off_uhat, 2 * (size_t)pg.nzo * c->ncol, c->off_stage, 1, s);
+      else
+        comm_allreduce_sum_f64(c->comm, (double *)c->d_uhat.p, 2 * (size_t)pg.nzo * c->ncol, s);
+    }
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
@@ -324,7 +371,12 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   stage_mark(c, 5);
 
   // ---- exchange b, GEMV (+ fused epilogue on one GPU), exchange S.b ------------------
-  if (multi) comm_allgather(c->comm, c->d_b.p + c->r0, c->d_b.p, sizeof(double) * c->rpr, s);
+  if (multi) {
+    if (c->p2p)
+      c->launches += p2p_allgather(c->p2p, c->off_b, sizeof(double) * c->rpr, sizeof(double) * c->rpr, 3, s);
+    else
+      comm_allgather(c->comm, c->d_b.p + c->r0, c->d_b.p, sizeof(double) * c->rpr, s);
+  }
   stage_mark(c, 6);
   if (!multi) {
     const ChargeEpilogue ep = make_epilogue(c, variant, true);
@@ -334,7 +386,10 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   } else {
     c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
                                nullptr);
-    comm_allgather(c->comm, c->d_sb.p + c->r0, c->d_sb.p, sizeof(double) * c->rpr, s);
+    if (c->p2p)
+      c->launches += p2p_allgather(c->p2p, c->off_sb, sizeof(double) * c->rpr, sizeof(double) * c->rpr, 4, s);
+    else
+      comm_allgather(c->comm, c->d_sb.p + c->r0, c->d_sb.p, sizeof(double) * c->rpr, s);
     stage_mark(c, 7);
     c->launches += launch_update_charge(s, make_epilogue(c, variant, false));
   }
@@ -525,6 +580,10 @@ void conp_destroy(conp_ctx *c) {
   }
   if (c->solver) cusolverDnDestroy(c->solver);
   if (c->blas) cublasDestroy(c->blas);
+  if (c->p2p) {
+    c->d_b.release(); c->d_sb.release(); c->d_uhat.release(); c->d_packed.release();
+    p2p_destroy(c->p2p);
+  }
   comm_destroy(c->comm);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->sev) cudaEventDestroy(ev);
@@ -1096,7 +1155,9 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     c->d_idx.upload(c->h_idx, s);
     c->d_xraw.reserve(3 * (size_t)std::max(nlocal, 1));
     const size_t m = std::max(c->m_slots, 1);
-    c->d_packed.zero(m, s);
+    ensure_p2p(c);
+    if (c->p2p) CUDA_CHECK(cudaMemsetAsync(c->d_packed.p, 0, sizeof(PosQ) * m, s));
+    else c->d_packed.zero(m, s);
     c->d_ptype.zero(m, s);
     c->d_sorted.reserve(m); c->d_sortedf.reserve(m);
     c->d_stype.reserve(m); c->d_ssrc.reserve(m);
@@ -1154,6 +1215,7 @@ int conp_pre_force(conp_ctx *c, const double *x, int kspace_mode, int variant, d
       CUDA_CHECK(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (flag) CONP_THROW(CONP_ERR_RANGE, "Out of range atoms - cannot compute PPPM");
+    if (c->p2p && p2p_error(c->p2p)) CONP_THROW(CONP_ERR_COMM, "peer-to-peer exchange timed out (a rank is missing)");
     if (scalar_out) *scalar_out = sc[0];
   });
 }
