@@ -65,19 +65,20 @@ def make_case(name, kspace):
     return lmp, arg
 
 
+# measured DRAM bytes per launch (ncu --set full, profiles/): (workload, kernel) -> read + written
+TRAFFIC = {("cfg5", "gemv"): 12.801121e9 + 6.872832e6, ("cfg4", "gemv"): 800.11392e6 + 3.297536e6}
+
 DEFAULT_WORKLOAD = "cfg5"  # BASELINE configs[4]: the configuration the 1/2/4/8-GPU metric is quoted on; fits one GPU
 
 
 def synthetic_matrix(n):
-    """Row-neutral random stand-in for S (profiling / reference-arm timing only): a random
-    n x 256 block tiled across the columns, cheap to build even at n = 40 000 (12.8 GB)."""
+    """Symmetric random stand-in for S (profiling / reference-arm timing only): u_i u_j-type low-rank
+    blocks, cheap to build even at n = 40 000 (12.8 GB) and symmetric to the last bit, like the
+    projected inverse the library builds itself."""
     rng = np.random.default_rng(1234)
-    blk = rng.standard_normal((n, 256)) * 1e-3
-    blk -= blk.mean(axis=1, keepdims=True)
-    S = np.empty((n, n))
-    for c0 in range(0, n, 256):
-        w = min(256, n - c0)
-        S[:, c0:c0 + w] = blk[:, :w]
+    u = rng.standard_normal((n, 4)) * 3e-2
+    S = u @ u.T
+    S = np.minimum(S, S.T)  # BLAS may not return an exactly symmetric product
     return S
 
 
@@ -302,7 +303,12 @@ def main():
     stage_names = ["pack", "bin", "pair", "kspace", "gather", "exchange_b", "gemv", "epilogue"]
     gemv_ms = max_over_ranks(float(st[6]))
     nrows = info.row_end - info.row_begin
-    gemv_bytes = 8.0 * nrows * N + 8.0 * N + 8.0 * nrows
+    sym = bool(ctx.info().symmetric_matvec)
+    # Algorithmic bytes of the matvec launch.  General kernel: the row block of S once.
+    # Symmetric kernel: S = S^T, so the half band of every row (N/2 + 1 columns) is all the product
+    # needs; the same work expressed in the 8d figure (full rows) is reported as gemv_equivalent_gbs.
+    full_bytes = 8.0 * nrows * N + 8.0 * N + 8.0 * nrows
+    gemv_bytes = (8.0 * nrows * (N // 2 + 1) + 8.0 * N + 8.0 * N) if sym else full_bytes
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
@@ -311,19 +317,27 @@ def main():
     achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
     G = int(np.prod(lmp.mesh)) if lmp.mesh else 0
     order = lmp.order
-    b_update = (8.0 * nrows * N + 8.0 * N + 16.0 * nrows + 32.0 * M
-                + ((24.0 * G + 24.0 * order * nrows) if kmode == 1 else
-                   (16.0 * info.kcount + 16.0 * info.kcount_flat * nrows)))
-    # dram__bytes_read.sum + dram__bytes_write.sum of one gemv_tma_kernel launch from the ncu --set full
-    # captures of these workloads on one GPU (profiles/r01_ncu_full_gemv_cfg5.txt: 12.801121 GB read +
-    # 6.87 MB written; profiles/r01_ncu_full_prof_r1a.txt: 800.11 MB + 3.30 MB); other shapes: null
-    traffic = {"cfg5": 12.801121e9 + 6.872832e6, "cfg4": 800.11392e6 + 3.297536e6}.get(name) if world == 1 else None
-    roofline = {"bound": "hbm", "kernel": "gemv_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    rest = (8.0 * N + 16.0 * nrows + 32.0 * M
+            + ((24.0 * G + 24.0 * order * nrows) if kmode == 1 else
+               (16.0 * info.kcount + 16.0 * info.kcount_flat * nrows)))
+    b_contract = 8.0 * nrows * N + rest                       # SURVEY 8d contract figure
+    b_update = (gemv_bytes - 16.0 * N if sym else 8.0 * nrows * N) + rest
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the
+    # ncu --set full captures under profiles/ (one GPU); other shapes: null
+    traffic = TRAFFIC.get((name, "symv" if sym else "gemv")) if world == 1 else None
+    roofline = {"bound": "hbm", "kernel": "symv_tma_kernel (+symv_reduce_kernel)" if sym else "gemv_tma_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": gemv_bytes, "launch_ms_in_pipeline": gemv_ms, "launch_ms_alone": gemv_alone_ms,
+                "symmetric_matvec": sym, "matrix_asymmetry": ctx.info().asymmetry,
+                "gemv_equivalent_gbs": full_bytes / (gemv_ms * 1e-3) / 1e9,
                 "update_bytes": b_update, "update_achieved_gbs": b_update / (ms_step * 1e-3) / 1e9,
                 "update_frac": b_update / (ms_step * 1e-3) / 1e9 / peak,
-                "stage_ms": {n_: float(v) for n_, v in zip(stage_names, st)}}
+                "update_contract_bytes": b_contract,
+                "update_contract_gbs": b_contract / (ms_step * 1e-3) / 1e9,
+                "stage_ms": {n_: float(v) for n_, v in zip(stage_names, st)},
+                "stage_note": "stages timed one after another (eager, no overlap); in the timed run the pair "
+                              "kernel and the brick clears run beside the k-space chain in the CUDA graph"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -65,6 +65,9 @@ typedef struct conp_info {
   double setup_build_ms, setup_invert_ms; /* last conp_build_A / conp_invert_project */
   double ee, dd;          /* "<e,e>" and "<d,d>" log values, fix_conp.cpp:1006-1009, 458-461 */
   double totsetq;
+  int symmetric_matvec;   /* 1: S is symmetric and the per-step product reads half of it (symv) */
+  int reserved0;
+  double asymmetry;       /* max|S - S^T| / max|S| measured before use (-1: not measured)      */
 } conp_info;
 
 /* ---- lifetime ---------------------------------------------------------- */
@@ -210,6 +213,10 @@ int conp_stage_times(conp_ctx *ctx, int enable, double *out8);
  *   conp_bench_gemv: one q = S.b pass on the resident row block.
  *   conp_bench_dgemm_tflops: cuBLAS DGEMM n^3 ceiling for the Gram. */
 int conp_bench_gemv(conp_ctx *ctx, int reps, float *ms_per_rep_out);
+/* out[N] = S.v for a host vector v[N] through the same kernel the step uses (the
+ * ddot_ loop of get_setq, fix_conp.cpp:1090-1096, applied to any vector): lets a
+ * host check the resident matrix, e.g. S.e = 0 after the projection. [collective] */
+int conp_matvec(conp_ctx *ctx, const double *v, double *out);
 int conp_bench_dgemm_tflops(conp_ctx *ctx, int n, double *tflops_out);
 
 #ifdef __cplusplus

@@ -28,6 +28,7 @@ SYMBOLS = [
     "conp_pre_force", "conp_solve_device", "conp_get_charges", "conp_get_b", "conp_get_density",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
+    "conp_matvec",
 ]
 
 
@@ -41,6 +42,7 @@ class ConpInfo(C.Structure):
         ("matrix_pitch", C.c_longlong), ("launches", C.c_longlong),
         ("setup_build_ms", C.c_double), ("setup_invert_ms", C.c_double),
         ("ee", C.c_double), ("dd", C.c_double), ("totsetq", C.c_double),
+        ("symmetric_matvec", C.c_int), ("reserved0", C.c_int), ("asymmetry", C.c_double),
     ]
 
 
@@ -101,6 +103,7 @@ def load_library(path: str | None = None):
     L.conp_stage_times.argtypes = [vp, C.c_int, c_dp]
     L.conp_bench_gemv.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.conp_bench_dgemm_tflops.argtypes = [vp, C.c_int, c_dp]
+    L.conp_matvec.argtypes = [vp, c_dp, c_dp]
     if path is None:
         _lib = L
     return L
@@ -296,6 +299,13 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.L.conp_bench_gemv(self.h, int(reps), C.byref(ms)))
         return ms.value
+
+    def matvec(self, v) -> np.ndarray:
+        """S.v through the kernel the step uses (symmetric or general)."""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.zeros_like(v)
+        self._ck(self.L.conp_matvec(self.h, _dp(v), _dp(out)))
+        return out
 
     def bench_dgemm_tflops(self, n=8192) -> float:
         t = C.c_double(0)

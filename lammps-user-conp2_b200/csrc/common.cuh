@@ -240,6 +240,18 @@ struct ChargeEpilogue {
 // With ep != nullptr the charge epilogue runs in the tail of the same kernel (single-GPU path).
 int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int ncols_pad, const double *b,
                 double *out, int num_sms, const ChargeEpilogue *ep);
+// Symmetric S: out[c] (c < out_len, zero beyond N) = this GPU's share of S.b from the half band of its
+// rows [row0, row0+nrows) -- the complete product on one GPU, a partial sum to be all-reduced on
+// several.  rowpart: >= N doubles, colpart: nstrips*L doubles of scratch.  See symv_tma_kernel.
+struct SymvPlan {
+  bool usable = false;
+  int grid = 0, nstrips = 0, L = 0;
+  const int2 *strips = nullptr;  // device: [a, bnd) global row range of every strip
+};
+SymvPlan plan_symv(int N, int row0, int nrows, int num_sms, std::vector<int2> &strips);
+int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, int nrows, const double *b,
+                const SymvPlan &plan, double *rowpart, double *colpart, double *out, int out_len,
+                const ChargeEpilogue *ep);
 int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep);
 int launch_finalize_q(cudaStream_t s, int n, const double *sb, const double *setq, const double *qinit,
                       const double *scal /* [1] = potdiff */, double *q_out);
@@ -290,9 +302,22 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
                        const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
 // rhat: spectra of the rank's nzl input planes (compact planes zs_lo..); uhat: (partial) output-plane spectra
+// Launch plan of the z-convolution (built once by plan_pppm_zconv): column groups whose window is
+// short ("narrow": only the input planes near an output plane and the matching slice of the kernel
+// table are staged, several blocks per SM) and the few small-|k_xy| groups that need every plane.
+struct ZconvPlan {
+  const int *narrow = nullptr;  // device list of 8-column group indices
+  const int *wide = nullptr;    // device list of cols_w-column block indices
+  int n_narrow = 0, n_wide = 0;
+  int cols_w = 8;               // columns per block of the wide kernel
+  int rcap = 0, npcap = 0;      // narrow kernel: largest window radius / staged planes it is sized for
+};
+void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, int nzl, int zin_lo,
+                     const std::vector<int> &zout, bool real_k, std::vector<int> &narrow, std::vector<int> &wide,
+                     ZconvPlan &plan);
 int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
-                      const int *zout_list, const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
-                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
+                      const int *zout_list, const int *krad, const ZconvPlan &plan, const cufftDoubleComplex *rhat,
+                      const double *Kr, const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
                          const double *compact, double *full);
 int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
@@ -348,5 +373,7 @@ int launch_project(cudaStream_t s, int n, double *S, size_t pitch, const int *su
 int launch_d_vector(cudaStream_t s, int n, const double *ez, const int *side, int ff_flag, double evscale,
                     double zlo, double zprd, double *d, double *setz);
 int launch_pad_identity(cudaStream_t s, int n, double *B, size_t ld);
+int launch_asymmetry(cudaStream_t s, int n, const double *S, size_t ld, double *out2);
+int launch_symmetrise(cudaStream_t s, int n, double *S, size_t ld);
 
 }  // namespace conp

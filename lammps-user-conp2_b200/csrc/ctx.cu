@@ -23,6 +23,11 @@ size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 struct conp_ctx {
   int device = 0, rank = 0, nranks = 1, num_sms = 148;
   cudaStream_t stream = nullptr;
+  // side stream of the step's fork/join: buffer clears and the real-space pair kernel run beside the
+  // sort -> spread -> FFT chain (they meet again at the b gather); captured into the same CUDA graph
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_cleared = nullptr, ev_sorted = nullptr, ev_pair = nullptr;
+  bool overlap = true;
   Comm *comm = nullptr;
   // direct NVLink exchanges (multi-GPU): b, S.b, the output-plane spectra and the packed charges live
   // in an IPC-mapped arena that every peer writes into; nullptr => NCCL collectives
@@ -64,6 +69,12 @@ struct conp_ctx {
 
   // matrix / vectors ---------------------------------------------------------
   DevBuf<double> d_mat, d_fullS;
+  // symmetric S: the matvec reads half of the matrix (symv_tma_kernel in gemv.cu)
+  bool sym = false, sym_allowed = true, sym_plan_ok = false;
+  double asym_rel = -1.0;  // measured max |S - S^T| / max |S| before symmetrising (-1: not measured)
+  SymvPlan sy;
+  DevBuf<double> d_rowpart, d_colpart;
+  DevBuf<int2> d_strips;
   DevBuf<double> d_b, d_bk, d_breal, d_sb, d_q, d_setq, d_dvec, d_setz, d_qinit, d_scal;
   bool have_qinit = false;
   double totsetq = 0, vmult = 0, evscale = 0, ee = 0, dd = 0;
@@ -95,7 +106,8 @@ struct conp_ctx {
   std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
   std::vector<int> h_zout;              // output planes (sorted)
   DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
-  DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad;
+  DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad, d_zc_narrow, d_zc_wide;
+  ZconvPlan zplan;
   DevBuf<double> d_pw;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
@@ -205,7 +217,7 @@ ChargeEpilogue make_epilogue(conp_ctx *c, int variant, bool fused) {
   ep.enabled = 1;
   ep.variant = variant;
   ep.n = c->N;
-  ep.row_offset = fused ? c->r0 : 0;
+  ep.row_offset = (fused && !c->sym) ? c->r0 : 0;
   ep.one_electrode = c->one_electrode;
   ep.totsetq = c->totsetq;
   ep.lz = c->prd[2];
@@ -230,7 +242,7 @@ void ensure_p2p(conp_ctx *c) {
   if (c->nranks == 1) return;
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t n_u = c->have_pppm ? 2 * (size_t)c->pg.nzo * c->ncol : 0;  // doubles in the spectra
-  const size_t slice = (n_u + c->nranks - 1) / c->nranks;
+  const size_t slice = (std::max(n_u, c->vlen) + c->nranks - 1) / c->nranks;
   const size_t b_bytes = up(sizeof(double) * c->vlen);
   const size_t u_bytes = up(sizeof(double) * std::max<size_t>(n_u, 2));
   const size_t st_bytes = up(sizeof(double) * std::max<size_t>(slice * c->nranks, 2));
@@ -262,6 +274,48 @@ void stage_mark(conp_ctx *c, int i) {
   if (c->stage_timing) CUDA_CHECK(cudaEventRecord(c->sev[i], c->stream));
 }
 
+// q-side matvec out = S.b.  `out` is a full-length (vlen) vector: this rank's rows on return of the
+// GEMV branch, the complete product (one GPU) or this rank's partial sum (to be all-reduced) on return
+// of the symmetric branch.  The epilogue can only be fused on one GPU.
+int enqueue_matvec(conp_ctx *c, cudaStream_t s, const double *b, double *out, const ChargeEpilogue *ep) {
+  const int nr = c->r1 - c->r0;
+  if (c->sym) {
+    if (c->sy.usable)
+      return launch_symv(s, c->d_mat.p, c->pitch, c->N, c->r0, nr, b, c->sy, c->d_rowpart.p, c->d_colpart.p, out,
+                         (int)c->vlen, ep);
+    CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * c->vlen, s));  // rank without rows
+    return 0;
+  }
+  return launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, b, out + c->r0, c->num_sms, ep);
+}
+
+// Decide whether the symmetric matvec may be used for the matrix `full` (N x N, ld = N, the complete
+// inverse on this GPU).  own_inverse: the matrix was inverted here from a symmetric A, so an asymmetry
+// at the rounding level (x condition number) is noise and is averaged away; a matrix read from a file
+// is used exactly as given, and takes the symmetric path only if it is symmetric to the last bit.
+void decide_symmetry(conp_ctx *c, double *full, bool own_inverse) {
+  c->sym = false;
+  if (!c->sym_allowed || !c->sym_plan_ok) return;
+  cudaStream_t s = c->stream;
+  DevBuf<double> m;
+  m.zero(2, s);
+  c->launches += launch_asymmetry(s, c->N, full, c->N, m.p);
+  double h[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(h, m.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  c->asym_rel = h[1] > 0 ? h[0] / h[1] : 0.0;
+  double bad = own_inverse ? (c->asym_rel <= 1e-9 ? 0.0 : 1.0) : (h[0] == 0.0 ? 0.0 : 1.0);
+  if (c->nranks > 1) {  // agree across ranks
+    CUDA_CHECK(cudaMemcpyAsync(m.p, &bad, sizeof(double), cudaMemcpyHostToDevice, s));
+    comm_allreduce_sum_f64(c->comm, m.p, 1, s);
+    CUDA_CHECK(cudaMemcpyAsync(&bad, m.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  if (bad != 0.0) return;
+  if (own_inverse && h[0] != 0.0) c->launches += launch_symmetrise(s, c->N, full, c->N);
+  c->sym = true;
+}
+
 // --------------------------------------------------------------------------
 // the per-step pipeline (device side, asynchronous on c->stream).  Inputs:
 // positions in c->d_xraw, the variant's value in scal(12).  Everything here is
@@ -273,7 +327,20 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   const bool multi = c->nranks > 1;
   const double *x_dev = c->d_xraw.p;
 
+  // fork: `t` runs beside the main stream (t == s when the overlap is off or stages are being timed)
+  const bool fork = c->overlap && !c->stage_timing;
+  cudaStream_t t = fork ? c->side : s;
   stage_mark(c, 0);
+  if (fork) {
+    CUDA_CHECK(cudaEventRecord(c->ev_begin, s));
+    CUDA_CHECK(cudaStreamWaitEvent(t, c->ev_begin, 0));
+  }
+  if (kspace_mode == CONP_KSPACE_PPPM) {  // clears of the step's bricks, off the critical path
+    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)std::max(c->pg.zs_n, 1) * c->plane, t));
+    CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), t));
+    CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, t));
+    if (fork) CUDA_CHECK(cudaEventRecord(c->ev_cleared, t));
+  }
   // ---- counting sort of the point charges: pack (+histogram, sum q z), scan, scatter ----
   CUDA_CHECK(cudaMemsetAsync(c->scal(2), 0, sizeof(double), s));
   const CellGrid &g = c->grid_b;
@@ -308,22 +375,26 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                      c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p, c->d_sortedf.p);
   stage_mark(c, 2);
 
-  // ---- real-space part of b (blist_coul_cal) ---------------------------------
+  // ---- real-space part of b (blist_coul_cal), beside the k-space chain -----------
+  if (fork) {
+    CUDA_CHECK(cudaEventRecord(c->ev_sorted, s));
+    CUDA_CHECK(cudaStreamWaitEvent(t, c->ev_sorted, 0));
+  }
   if (c->rc_b > 0.0 && c->m_total > 0 && nr > 0) {
-    c->launches += launch_pair_b(s, g, pair_tables(c, c->d_cuteff_b.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
+    c->launches += launch_pair_b(t, g, pair_tables(c, c->d_cuteff_b.p), c->r0, c->r1, c->d_ex.p, c->d_ey.p,
                                  c->d_ez.p, c->d_etype.p, c->d_runstart.p, c->d_runs.p, c->d_sorted.p,
                                  c->d_stype.p, c->d_sortedf.p, c->d_cellstart.p, c->d_breal.p);
   } else {
-    CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * std::max(nr, 1), s));
+    CUDA_CHECK(cudaMemsetAsync(c->d_breal.p + c->r0, 0, sizeof(double) * std::max(nr, 1), t));
   }
+  if (fork) CUDA_CHECK(cudaEventRecord(c->ev_pair, t));
   stage_mark(c, 3);
 
   // ---- k-space part of b --------------------------------------------------------
   const double spref = slab_pref(c);
   if (kspace_mode == CONP_KSPACE_PPPM) {
     const PPPMGeom &pg = c->pg;
-    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)std::max(pg.zs_n, 1) * c->plane, s));
-    CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
+    if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
     if (!multi || c->periodic[2]) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
                                         c->d_flag.p);
@@ -343,8 +414,8 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     }
     if (pg.zs_n > 0) CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
     c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.zin_lo, pg.nzo, c->d_zout.p,
-                                     c->d_krad.p, c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p,
-                                     c->d_uhat.p);
+                                     c->d_krad.p, c->zplan, c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr,
+                                     c->d_Kc.p, c->d_uhat.p);
     // every rank holds the partial sum over its slab: one small all-reduce completes the spectra
     if (multi) {
       if (c->p2p)
@@ -355,6 +426,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
+    if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
     c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_poff.p, c->d_pw.p, c->d_ubrick.p,
                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
   } else {
@@ -364,6 +436,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     c->launches += launch_ewald_sfac(s, c->m_total, c->d_sorted.p, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
                                      c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
     stage_mark(c, 4);
+    if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
     c->launches += launch_ewald_bextract(s, c->r0, c->r1, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
                                          c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, c->d_sfac.p, c->d_ez.p,
                                          c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
@@ -380,22 +453,25 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   stage_mark(c, 6);
   if (!multi) {
     const ChargeEpilogue ep = make_epilogue(c, variant, true);
-    c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
-                               &ep);
+    c->launches += enqueue_matvec(c, s, c->d_b.p, c->d_sb.p, &ep);
     stage_mark(c, 7);
   } else {
-    c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
-                               nullptr);
-    if (c->p2p)
+    c->launches += enqueue_matvec(c, s, c->d_b.p, c->d_sb.p, nullptr);
+    if (c->sym) {  // every rank holds a partial sum over its half band: all-reduce instead of all-gather
+      if (c->p2p)
+        c->launches += p2p_allreduce_f64(c->p2p, c->off_sb, c->vlen, c->off_stage, 4, s);
+      else
+        comm_allreduce_sum_f64(c->comm, c->d_sb.p, c->vlen, s);
+    } else if (c->p2p) {
       c->launches += p2p_allgather(c->p2p, c->off_sb, sizeof(double) * c->rpr, sizeof(double) * c->rpr, 4, s);
-    else
+    } else {
       comm_allgather(c->comm, c->d_sb.p + c->r0, c->d_sb.p, sizeof(double) * c->rpr, s);
+    }
     stage_mark(c, 7);
     c->launches += launch_update_charge(s, make_epilogue(c, variant, false));
   }
   const double *qinit = c->have_qinit ? c->d_qinit.p : nullptr;
   if (kspace_mode == CONP_KSPACE_PPPM) {  // charges + kspmod->update_charge() -> ele_make_rho
-    CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, s));
     c->launches += launch_pppm_ele_spread(s, c->pg, c->N, c->r0, c->r1, c->d_widx.p, c->d_weights.p, c->d_sb.p,
                                           c->d_setq.p, qinit, c->scal(0), c->d_q.p, c->d_ebrick.p);
   } else {
@@ -494,7 +570,8 @@ void project_full(conp_ctx *c, double *S, int nullneutral, int zneutr) {
   }
 }
 
-void store_rows_from_full(conp_ctx *c, const double *full) {
+void store_rows_from_full(conp_ctx *c, double *full) {
+  decide_symmetry(c, full, true);
   const int nr = c->r1 - c->r0;
   c->d_mat.zero((size_t)std::max(nr, 1) * c->pitch, c->stream);
   if (nr > 0)
@@ -546,7 +623,15 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     c->rank = rank;
     c->nranks = nranks;
     c->num_sms = prop.multiProcessorCount;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {  // the k-space chain is the critical path of the step: main stream at the highest priority
+      int prio_lo = 0, prio_hi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_lo));
+    }
+    for (cudaEvent_t *e : {&c->ev_begin, &c->ev_cleared, &c->ev_sorted, &c->ev_pair})
+      CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    c->overlap = getenv("CONP_NO_OVERLAP") == nullptr;
     for (auto &ev : c->ev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
     c->d_scal.zero(16, c->stream);
@@ -554,6 +639,7 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     c->d_counter.zero(1, c->stream);
     c->h_value.reserve(64);
     c->use_graph = getenv("CONP_NO_GRAPH") == nullptr;
+    c->sym_allowed = getenv("CONP_NO_SYMV") == nullptr;
     c->comm = comm_create(rank, nranks, unique_id);
     CUSOLVER_CHECK(cusolverDnCreate(&c->solver));
     CUSOLVER_CHECK(cusolverDnSetStream(c->solver, c->stream));
@@ -587,6 +673,9 @@ void conp_destroy(conp_ctx *c) {
   comm_destroy(c->comm);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->sev) cudaEventDestroy(ev);
+  for (cudaEvent_t e : {c->ev_begin, c->ev_cleared, c->ev_sorted, c->ev_pair})
+    if (e) cudaEventDestroy(e);
+  if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -606,6 +695,8 @@ int conp_get_info(const conp_ctx *c, conp_info *o) {
   o->launches = c->launches;
   o->setup_build_ms = c->build_ms; o->setup_invert_ms = c->invert_ms;
   o->ee = c->ee; o->dd = c->dd; o->totsetq = c->totsetq;
+  o->symmetric_matvec = c->sym ? 1 : 0;
+  o->asymmetry = c->asym_rel;
   return CONP_OK;
 }
 
@@ -717,6 +808,22 @@ int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type,
     c->ncols_pad = (int)round_up(N, 16);
     c->pitch = c->ncols_pad;
     c->vlen = std::max((size_t)c->nranks * c->rpr, (size_t)c->ncols_pad) + 16;
+    // symmetric matvec: every rank must take the same branch, so the decision uses the largest block
+    c->sym = false;
+    c->asym_rel = -1.0;
+    {
+      std::vector<int2> strips;
+      c->sym_plan_ok = plan_symv(N, 0, std::min(c->rpr, N), c->num_sms, strips).usable;
+      c->sy = plan_symv(N, c->r0, c->r1 - c->r0, c->num_sms, strips);
+      if (c->sym_plan_ok) {
+        c->d_rowpart.zero(c->vlen, c->stream);
+        if (c->sy.usable) {
+          c->d_colpart.zero((size_t)c->sy.nstrips * c->sy.L, c->stream);
+          c->d_strips.upload(strips, c->stream);
+          c->sy.strips = c->d_strips.p;
+        }
+      }
+    }
     std::vector<double> hx(N), hy(N), hz(N);
     for (int i = 0; i < N; ++i) { hx[i] = xyz[3 * i]; hy[i] = xyz[3 * i + 1]; hz[i] = xyz[3 * i + 2]; }
     cudaStream_t s = c->stream;
@@ -761,6 +868,7 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     c->ncol = nxh * ny;
     const size_t ncol = c->ncol;
     cudaStream_t s = c->stream;
+    std::vector<int> h_krad;
     c->d_rho.upload(rho_coeff, (size_t)order * order, s);
     // half-spectrum Green's function, symmetrised and pre-scaled by 1/(nx ny nz):
     // Re IFFT(G rho^) of the reference's complex transform (pppm_conp.cpp:235-266)
@@ -836,7 +944,8 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
       // is read off at the 1e-13 level, where the table is still clean, and extended by 20 % + 2
       // planes (a Gaussian that is 1e-13 at R is < 1e-18 at 1.2 R).
       {
-        std::vector<int> krad(ncol, 0);
+        std::vector<int> &krad = h_krad;
+        krad.assign(ncol, 0);
         for (size_t col = 0; col < ncol; ++col) {
           const cufftDoubleComplex *row = gc.data() + col * nz;
           double kmax = 0;
@@ -868,6 +977,20 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     // ---- this rank's slab of input planes (all of them on one GPU) ------------------
     g.zs_lo = (int)(((long long)g.nzi * c->rank) / c->nranks);
     g.zs_n = (int)(((long long)g.nzi * (c->rank + 1)) / c->nranks) - g.zs_lo;
+    {  // split the (kx,ky) column groups between the windowed and the full z-convolution kernels
+      std::vector<int> narrow, wide;
+      plan_pppm_zconv(h_krad, (int)ncol, (int)nz, g.nzi, g.zs_n, g.zin_lo, c->h_zout, c->k_real, narrow, wide,
+                      c->zplan);
+      if (getenv("CONP_DEBUG"))
+        fprintf(stderr, "[conp] zconv plan: %d narrow groups (R <= %d, <= %d planes staged), %d wide blocks of %d cols\n",
+                c->zplan.n_narrow, c->zplan.rcap, c->zplan.npcap, c->zplan.n_wide, c->zplan.cols_w);
+      if (narrow.empty()) narrow.push_back(0);
+      if (wide.empty()) wide.push_back(0);
+      c->d_zc_narrow.upload(narrow, s);
+      c->d_zc_wide.upload(wide, s);
+      c->zplan.narrow = c->d_zc_narrow.p;
+      c->zplan.wide = c->d_zc_wide.p;
+    }
     // ---- compact bricks and batched 2-D plans -------------------------------------
     c->d_brick.zero((size_t)std::max(g.zs_n, 1) * c->plane, s);
     c->d_ubrick.zero((size_t)g.nzo * c->plane, s);
@@ -965,11 +1088,25 @@ int conp_load_matrix(conp_ctx *c, const double *full, int is_inverse) {
     if (!full) CONP_THROW(CONP_ERR_ARG, "Invalid fix conp command (Cannot open A matrix file)");
     const int N = c->N, nr = c->r1 - c->r0;
     c->d_mat.zero((size_t)std::max(nr, 1) * c->pitch, c->stream);
-    if (nr > 0)
+    c->sym = false;
+    c->asym_rel = -1.0;
+    if (is_inverse && c->sym_allowed && c->sym_plan_ok) {
+      // a ready-made inverse: look at the whole matrix once to see whether the symmetric product applies
+      DevBuf<double> F;
+      F.upload(full, (size_t)N * N, c->stream);
+      decide_symmetry(c, F.p, false);
+      if (nr > 0)
+        CUDA_CHECK(cudaMemcpy2DAsync(c->d_mat.p, c->pitch * sizeof(double), F.p + (size_t)c->r0 * N,
+                                     (size_t)N * sizeof(double), (size_t)N * sizeof(double), nr,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else if (nr > 0) {
       CUDA_CHECK(cudaMemcpy2DAsync(c->d_mat.p, c->pitch * sizeof(double), full + (size_t)c->r0 * N,
                                    (size_t)N * sizeof(double), (size_t)N * sizeof(double), nr,
                                    cudaMemcpyHostToDevice, c->stream));
+    }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
     c->have_A = true;
     c->inverted = is_inverse != 0;
   });
@@ -1062,14 +1199,16 @@ int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int
   return guard(c, [&] {
     need(c->have_A && c->inverted, "conp_set_unit_voltage: matrix not inverted (conp_invert_project)");
     cudaStream_t s = c->stream;
-    const int N = c->N, nr = c->r1 - c->r0;
+    const int N = c->N;
     c->evscale = evscale;
     c->launches += launch_d_vector(s, N, c->d_ez.p, c->d_eside.p, c->ff_flag, evscale, c->boxlo[2], c->prd[2],
                                    c->d_dvec.p, c->d_setz.p);
     // get_setq: elesetq = S.d (fix_conp.cpp:1090-1096)
-    c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_dvec.p, c->d_setq.p + c->r0,
-                               c->num_sms, nullptr);
-    if (c->nranks > 1) comm_allgather(c->comm, c->d_setq.p + c->r0, c->d_setq.p, sizeof(double) * c->rpr, s);
+    c->launches += enqueue_matvec(c, s, c->d_dvec.p, c->d_setq.p, nullptr);
+    if (c->nranks > 1) {
+      if (c->sym) comm_allreduce_sum_f64(c->comm, c->d_setq.p, c->vlen, s);
+      else comm_allgather(c->comm, c->d_setq.p + c->r0, c->d_setq.p, sizeof(double) * c->rpr, s);
+    }
     std::vector<double> setq(N), setz(N);
     CUDA_CHECK(cudaMemcpyAsync(setq.data(), c->d_setq.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(setz.data(), c->d_setz.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
@@ -1387,18 +1526,37 @@ int conp_stage_times(conp_ctx *c, int enable, double *out8) {
 int conp_bench_gemv(conp_ctx *c, int reps, float *ms_per_rep_out) {
   return guard(c, [&] {
     need(c->have_A, "conp_bench_gemv: no matrix resident");
-    const int nr = c->r1 - c->r0;
     cudaStream_t s = c->stream;
-    launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms, nullptr);
+    // the matvec the step would launch (symmetric or general), into scratch so S.b stays intact
+    DevBuf<double> scratch;
+    scratch.zero(c->vlen, s);
+    enqueue_matvec(c, s, c->d_b.p, scratch.p, nullptr);
     CUDA_CHECK(cudaEventRecord(c->ev[12], s));
-    for (int r = 0; r < reps; ++r)
-      c->launches += launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, c->d_b.p, c->d_sb.p + c->r0, c->num_sms,
-                                 nullptr);
+    for (int r = 0; r < reps; ++r) c->launches += enqueue_matvec(c, s, c->d_b.p, scratch.p, nullptr);
     CUDA_CHECK(cudaEventRecord(c->ev[13], s));
     CUDA_CHECK(cudaEventSynchronize(c->ev[13]));
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[12], c->ev[13]));
     if (ms_per_rep_out) *ms_per_rep_out = ms / std::max(reps, 1);
+  });
+}
+
+int conp_matvec(conp_ctx *c, const double *v, double *out) {
+  return guard(c, [&] {
+    need(c->have_A && c->have_ele, "conp_matvec: no matrix resident");
+    if (!v || !out) CONP_THROW(CONP_ERR_ARG, "conp_matvec: null vector");
+    cudaStream_t s = c->stream;
+    DevBuf<double> in, res;
+    in.zero(c->vlen, s);
+    res.zero(c->vlen, s);
+    CUDA_CHECK(cudaMemcpyAsync(in.p, v, sizeof(double) * c->N, cudaMemcpyHostToDevice, s));
+    c->launches += enqueue_matvec(c, s, in.p, res.p, nullptr);
+    if (c->nranks > 1) {
+      if (c->sym) comm_allreduce_sum_f64(c->comm, res.p, c->vlen, s);
+      else comm_allgather(c->comm, res.p + c->r0, res.p, sizeof(double) * c->rpr, s);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, res.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
   });
 }
 

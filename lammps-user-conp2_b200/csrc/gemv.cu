@@ -14,6 +14,7 @@
 // in flight per SM, enough to cover HBM latency at 6.5 TB/s / 148 SMs.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstring>
 
 namespace conp {
@@ -304,6 +305,293 @@ finalize_q_kernel(int n, const double *__restrict__ sb, const double *__restrict
   q_out[i] = q;
 }
 
+
+// ---------------------------------------------------------------------------
+// Symmetric variant.  S = A^-1 - w w^T/(e^T w) is symmetric (fix_conp.cpp:982-1020 applies the
+// projection to the inverse of the symmetric A), so q = S.b needs every unordered pair {i,j} only
+// once: streaming S_ij gives both S_ij b_j (to row i) and S_ij b_i (to row j), and the kernel reads
+// half of the matrix.  Pair {i,j} is taken from row i iff (j - i) mod N is in [1, H], H = N/2 (for
+// even N the distance-H pairs come from the smaller index): a cyclic half band, so every row has
+// the same amount of work for any row partition -- one GPU or a row block per GPU alike.
+//
+// A CTA owns strips of consecutive rows.  For a strip [a, bnd) the band is the unwrapped column
+// range [a & ~1, bnd + H); it is cut into chunks of C columns (two segments when it wraps past N).
+// Loop order: chunk outer, row groups (R rows) inner, so the two column sums a thread owns stay in
+// registers for the whole strip and are stored once per chunk into the strip's private slice of
+// `colpart` (no atomics, deterministic).  Row sums are reduced per stage inside the warp and
+// accumulated in a per-warp shared array.  symv_reduce_kernel then adds, per column, the strip
+// slices in a fixed order, and runs the charge epilogue in its tail.
+// Same TMA ring as gemv_tma_kernel; only the interior of the band takes the unmasked fast path.
+// ---------------------------------------------------------------------------
+constexpr int SY_STAGES = 5;
+constexpr int SY_HMAX = 512;  // rows per strip (per-warp row sums live in shared memory)
+
+struct __align__(128) SyStage {
+  double tile[R][C];
+};
+struct SySmem {
+  SyStage st[SY_STAGES];
+  double yrow[CONSUMER_WARPS][SY_HMAX];
+  double bstrip[SY_HMAX];
+  unsigned long long full[SY_STAGES];
+  unsigned long long empty[SY_STAGES];
+};
+
+struct SyChunk {
+  int cb;    // first column, unwrapped (segment 2: N + actual column)
+  int cev;   // end of the columns any row of the strip can use (exclusive, unwrapped)
+  int w;     // columns copied (even)
+  int cact;  // actual first column in S and b
+  int joff;  // offset of the chunk in the strip's colpart slice
+  bool seg2;
+};
+
+__device__ __forceinline__ bool sy_chunk(int k, int a, int bnd, int N, int H, SyChunk &ch) {
+  const int CS = a & ~1, CE = bnd + H;
+  const int end1 = min(CE, N), len1 = end1 - CS;
+  const int n1 = (len1 + C - 1) / C;
+  const int len2 = max(CE - N, 0);
+  const int n2 = (len2 + C - 1) / C;
+  if (k < n1) {
+    ch.cb = CS + k * C;
+    ch.cev = min(ch.cb + C, end1);
+    ch.seg2 = false;
+    ch.cact = ch.cb;
+    ch.joff = k * C;
+  } else if (k < n1 + n2) {
+    const int kk = k - n1;
+    ch.cb = N + kk * C;
+    ch.cev = min(ch.cb + C, CE);
+    ch.seg2 = true;
+    ch.cact = kk * C;
+    ch.joff = ((len1 + 1) & ~1) + kk * C;
+  } else {
+    return false;
+  }
+  ch.w = (ch.cev - ch.cb + 1) & ~1;
+  return true;
+}
+// does any row of the group [rg, rg+nr) use a column of the chunk?
+__device__ __forceinline__ bool sy_in_band(int rg, int nr, const SyChunk &ch, int H) {
+  return rg <= ch.cev - 1 && rg + nr - 1 + H >= ch.cb;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+symv_tma_kernel(const double *__restrict__ S, size_t pitch, int N, int row0, const int2 *__restrict__ strips,
+                int nstrips, int L, const double *__restrict__ b, double *__restrict__ rowpart,
+                double *__restrict__ colpart) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SySmem &sm = *reinterpret_cast<SySmem *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int H = N / 2;
+  const bool tie = (N & 1) == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < SY_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == CONSUMER_WARPS) {
+    // ===== producer =====
+    if (lane == 0) {
+      const uint64_t pol_s = policy_evict_first();
+      for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+        const int a = strips[s].x, bnd = strips[s].y;
+        if (a >= bnd) continue;
+        const int ngroups = (bnd - a + R - 1) / R;
+        SyChunk ch;
+        for (int k = 0; sy_chunk(k, a, bnd, N, H, ch); ++k) {
+          const uint32_t row_bytes = (uint32_t)ch.w * 8u;
+          for (int g = 0; g < ngroups; ++g) {
+            const int rg = a + g * R;
+            const int nr = min(R, bnd - rg);
+            if (!sy_in_band(rg, nr, ch, H)) continue;
+            mbar_wait(&sm.empty[stage], phase ^ 1);
+            mbar_expect_tx(&sm.full[stage], row_bytes * (uint32_t)nr);
+            for (int r = 0; r < nr; ++r)
+              tma_bulk_g2s(sm.st[stage].tile[r], S + (size_t)(rg - row0 + r) * pitch + ch.cact, row_bytes,
+                           &sm.full[stage], pol_s);
+            if (++stage == SY_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+    const int a = strips[s].x, bnd = strips[s].y;
+    if (a >= bnd) continue;
+    const int h = bnd - a;
+    const int ngroups = (h + R - 1) / R;
+    for (int t = lane; t < h; t += 32) sm.yrow[warp][t] = 0.0;
+    for (int t = tid; t < h; t += CONSUMERS) sm.bstrip[t] = b[a + t];
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+    double *cp = colpart + (size_t)s * L;
+    SyChunk ch;
+    for (int k = 0; sy_chunk(k, a, bnd, N, H, ch); ++k) {
+      const bool active = 2 * tid < ch.w;
+      double2 bv = make_double2(0.0, 0.0);
+      if (active) bv = *reinterpret_cast<const double2 *>(b + ch.cact + 2 * tid);
+      const int cu0 = ch.cb + 2 * tid;  // unwrapped column of this thread's first element
+      double col0 = 0.0, col1 = 0.0;
+      for (int g = 0; g < ngroups; ++g) {
+        const int rg = a + g * R;
+        const int nr = min(R, bnd - rg);
+        if (!sy_in_band(rg, nr, ch, H)) continue;
+        mbar_wait(&sm.full[stage], phase);
+        double acc[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) acc[i] = 0.0;
+        if (active) {
+          // interior of the band for all R rows: every element is a distinct pair with 1 <= d < H
+          const bool fast = ch.cb - (rg + nr - 1) >= 1 && (ch.cb + ch.w - 1) - rg <= H - 1 &&
+                            (ch.seg2 || ch.cb + ch.w <= N);
+          if (fast) {
+            // two interleaved column-sum chains per element so the FP64 latency of one hides the other
+            double c0b = 0.0, c1b = 0.0;
+#pragma unroll
+            for (int i = 0; i < R; i += 2) {
+              if (i < nr) {
+                const double2 sv = *reinterpret_cast<const double2 *>(&sm.st[stage].tile[i][2 * tid]);
+                const double br = sm.bstrip[rg - a + i];
+                acc[i] = fma(sv.y, bv.y, sv.x * bv.x);
+                col0 = fma(sv.x, br, col0);
+                col1 = fma(sv.y, br, col1);
+              }
+              if (i + 1 < nr) {
+                const double2 sv = *reinterpret_cast<const double2 *>(&sm.st[stage].tile[i + 1][2 * tid]);
+                const double br = sm.bstrip[rg - a + i + 1];
+                acc[i + 1] = fma(sv.y, bv.y, sv.x * bv.x);
+                c0b = fma(sv.x, br, c0b);
+                c1b = fma(sv.y, br, c1b);
+              }
+            }
+            col0 += c0b;
+            col1 += c1b;
+          } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              if (i < nr) {
+                const int r = rg + i;
+                const double2 sv = *reinterpret_cast<const double2 *>(&sm.st[stage].tile[i][2 * tid]);
+                const double br = sm.bstrip[r - a];
+                const int d0 = cu0 - r, d1 = d0 + 1;
+                const bool ok0 = d0 >= 0 && d0 <= H && !(tie && d0 == H && r >= H) && (ch.seg2 || cu0 < N);
+                const bool ok1 = d1 >= 0 && d1 <= H && !(tie && d1 == H && r >= H) && (ch.seg2 || cu0 + 1 < N);
+                const double x0 = ok0 ? sv.x : 0.0, x1 = ok1 ? sv.y : 0.0;
+                acc[i] = fma(x1, bv.y, x0 * bv.x);
+                if (d0 >= 1) col0 = fma(x0, br, col0);  // d == 0 is the diagonal: row part only
+                if (d1 >= 1) col1 = fma(x1, br, col1);
+              }
+            }
+          }
+        }
+        // recursive-halving reduction of the R = 8 row partials over the warp: afterwards lane
+        // 4*j holds the warp total of row (bit4, bit3, bit2 of the lane)
+        {
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double send = h16 ? acc[i] : acc[i + 4];
+            const double keep = h16 ? acc[i + 4] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = h8 ? acc[i] : acc[i + 2];
+            const double keep = h8 ? acc[i + 2] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          {
+            const double send = h4 ? acc[0] : acc[1];
+            const double keep = h4 ? acc[1] : acc[0];
+            acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+          const int row = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+          if ((lane & 3) == 0 && row < nr) sm.yrow[warp][rg - a + row] += acc[0];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (++stage == SY_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (active) *reinterpret_cast<double2 *>(cp + ch.joff + 2 * tid) = make_double2(col0, col1);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+    for (int t = tid; t < h; t += CONSUMERS) {
+      double v = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < CONSUMER_WARPS; ++wv) v += sm.yrow[wv][t];
+      rowpart[a + t] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+  }
+}
+
+// out[c] = row part (own rows) + sum over strips of the strip's column slice.  A block owns tiles of
+// 32 columns; warp w adds the strips s = w, w+8, ... for its lane's column, the eight partial sums
+// are then added in warp order: a fixed summation shape, so the product is reproducible bit for
+// bit.  The charge epilogue (single GPU) runs in the tail.
+constexpr int SR_THREADS = 256;
+
+__global__ void __launch_bounds__(SR_THREADS)
+symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restrict__ strips, int nstrips, int L,
+                   const double *__restrict__ rowpart, const double *__restrict__ colpart,
+                   double *__restrict__ out, ChargeEpilogue ep) {
+  __shared__ double sh[SR_THREADS];
+  __shared__ double part[SR_THREADS / 32][32];
+  __shared__ int flag;
+  const int H = N / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (out_len + 31) / 32;
+  double pa = 0.0, pz = 0.0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int c = tile * 32 + lane;
+    double v = 0.0;
+    if (c < N) {
+#pragma unroll 4
+      for (int s = warp; s < nstrips; s += SR_THREADS / 32) {
+        const int2 ab = strips[s];
+        const int CS = ab.x & ~1, CE = ab.y + H;
+        const int end1 = min(CE, N);
+        const bool in1 = c >= CS && c < end1;
+        const bool in2 = !in1 && c < CE - N;
+        const int j = in1 ? c - CS : ((end1 - CS + 1) & ~1) + c;
+        if (ab.x < ab.y && (in1 || in2)) v += colpart[(size_t)s * L + j];
+      }
+    }
+    part[warp][lane] = v;
+    __syncthreads();
+    if (warp == 0 && c < out_len) {
+      double t = 0.0;
+      if (c < N) {
+        t = (c >= row0 && c < row0 + nrows) ? rowpart[c] : 0.0;
+#pragma unroll
+        for (int wv = 0; wv < SR_THREADS / 32; ++wv) t += part[wv][lane];
+        if (ep.enabled) {
+          if (ep.side[c] == 1) pa += t;
+          pz = fma(ep.setz[c], t, pz);
+        }
+      }
+      out[c] = t;
+    }
+    __syncthreads();
+  }
+  if (ep.enabled) charge_epilogue(ep, pa, pz, threadIdx.x, SR_THREADS, 0, sh, &flag);
+}
+
 }  // namespace
 
 int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int ncols_pad, const double *b,
@@ -322,6 +610,49 @@ int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int nc
   gemv_tma_kernel<<<grid, THREADS, smem, s>>>(S, pitch, nrows, ncols_pad, b, out, e);
   CUDA_CHECK(cudaGetLastError());
   return 1;
+}
+
+SymvPlan plan_symv(int N, int row0, int nrows, int num_sms, std::vector<int2> &strips) {
+  SymvPlan p;
+  strips.clear();
+  if (N < 64 || nrows <= 0) return p;
+  const int grid = std::min(num_sms, nrows);
+  const int nstrips = std::max(grid, (nrows + SY_HMAX - 1) / SY_HMAX);
+  const int hmax = (nrows + nstrips - 1) / nstrips;
+  const int H = N / 2;
+  if (hmax > SY_HMAX || hmax + H + 2 > N) return p;  // the unwrapped band of a strip must not lap itself
+  for (int s = 0; s < nstrips; ++s)
+    strips.push_back(make_int2(row0 + (int)(((long long)nrows * s) / nstrips),
+                               row0 + (int)(((long long)nrows * (s + 1)) / nstrips)));
+  p.usable = true;
+  p.grid = grid;
+  p.nstrips = nstrips;
+  p.L = (hmax + H + 8 + 1) & ~1;
+  return p;
+}
+
+int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, int nrows, const double *b,
+                const SymvPlan &plan, double *rowpart, double *colpart, double *out, int out_len,
+                const ChargeEpilogue *ep) {
+  if (!plan.usable || !plan.strips) CONP_THROW(CONP_ERR_STATE, "launch_symv: no plan");
+  static bool attr_set = false;
+  const size_t smem = sizeof(SySmem);
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(symv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  symv_tma_kernel<<<plan.grid, THREADS, smem, s>>>(S, pitch, N, row0, plan.strips, plan.nstrips, plan.L, b, rowpart,
+                                                  colpart);
+  CUDA_CHECK(cudaGetLastError());
+  ChargeEpilogue e;
+  if (ep) e = *ep;
+  else memset(&e, 0, sizeof(e));
+  int grid = (out_len + 31) / 32;
+  grid = grid < 1 ? 1 : (grid > 1024 ? 1024 : grid);  // epilogue partials: 2 per block, 1024 blocks max
+  symv_reduce_kernel<<<grid, SR_THREADS, 0, s>>>(N, out_len, row0, nrows, plan.strips, plan.nstrips, plan.L, rowpart,
+                                                 colpart, out, e);
+  CUDA_CHECK(cudaGetLastError());
+  return 2;
 }
 
 int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep) {

@@ -104,6 +104,68 @@ identity_kernel(int n, double *__restrict__ B, size_t ld) {
   B[idx] = (i == j) ? 1.0 : 0.0;
 }
 
+// Symmetry of the (projected) inverse.  asym_kernel: out[0] = max |S_ij - S_ji|, out[1] = max |S_ij|
+// (non-negative doubles order like their bit patterns, so atomicMax on the bits is exact);
+// symmetrise_kernel: S_ij = S_ji = (S_ij + S_ji)/2.  32x32 tiles through shared memory so that both
+// triangles are read and written with unit stride.
+__global__ void __launch_bounds__(256)
+asym_kernel(int n, const double *__restrict__ S, size_t ld, unsigned long long *__restrict__ out) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;  // tile (bj, bi), transposed on the way out
+    t[r][tx] = (i < n && j < n) ? S[(size_t)i * ld + j] : 0.0;
+  }
+  __syncthreads();
+  double da = 0.0, ma = 0.0;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < n && j < n) {
+      const double v = S[(size_t)i * ld + j];
+      da = fmax(da, fabs(v - t[tx][r]));
+      ma = fmax(ma, fmax(fabs(v), fabs(t[tx][r])));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    da = fmax(da, __shfl_xor_sync(0xffffffffu, da, o));
+    ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+  }
+  if (tx == 0) {
+    atomicMax(out, (unsigned long long)__double_as_longlong(da));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(ma));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+symmetrise_kernel(int n, double *__restrict__ S, size_t ld) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;
+    t[r][tx] = (i < n && j < n) ? S[(size_t)i * ld + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < n && j < n) {
+      const double v = 0.5 * (S[(size_t)i * ld + j] + t[tx][r]);
+      S[(size_t)i * ld + j] = v;
+      t[tx][r] = v;
+    }
+  }
+  __syncthreads();
+  if (bj == bi) return;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;
+    if (i < n && j < n) S[(size_t)i * ld + j] = t[r][tx];
+  }
+}
+
 }  // namespace
 
 int launch_a_finish(cudaStream_t s, int row_begin, int row_end, int n, double *A_rows, size_t pitch,
@@ -135,6 +197,24 @@ int launch_project(cudaStream_t s, int n, double *S, size_t pitch, const int *su
 int launch_d_vector(cudaStream_t s, int n, const double *ez, const int *side, int ff_flag, double evscale,
                     double zlo, double zprd, double *d, double *setz) {
   d_vector_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, ez, side, ff_flag, evscale, zlo, zprd, d, setz);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+// out2 (device, 2 doubles): max |S - S^T| and max |S| of the n x n matrix
+int launch_asymmetry(cudaStream_t s, int n, const double *S, size_t ld, double *out2) {
+  CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(double), s));
+  if (n <= 0) return 0;
+  const unsigned nb = (unsigned)((n + 31) / 32);
+  asym_kernel<<<dim3(nb, nb), 256, 0, s>>>(n, S, ld, reinterpret_cast<unsigned long long *>(out2));
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_symmetrise(cudaStream_t s, int n, double *S, size_t ld) {
+  if (n <= 0) return 0;
+  const unsigned nb = (unsigned)((n + 31) / 32);
+  symmetrise_kernel<<<dim3(nb, nb), 256, 0, s>>>(n, S, ld);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

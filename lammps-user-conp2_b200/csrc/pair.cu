@@ -149,57 +149,64 @@ bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts
   slot[j] = atomicAdd(&cell_count[cell], 1);
 }
 
-// exclusive scan of cell_count -> cell_start[ncells+1]; one block walks the
-// histogram in coalesced int4 tiles of 4096 cells (cell_count is padded with
-// zeros to a multiple of 4)
+// exclusive scan of cell_count -> cell_start[ncells+1] by one block: every thread sums a
+// contiguous chunk of the histogram (int4 loads, all in flight at once), one block-wide scan of the
+// 1024 chunk totals, then the chunk is walked again to write the prefixes (cell_count is padded
+// with zeros to a multiple of 4 and both arrays are 16-byte aligned)
 __global__ void __launch_bounds__(1024, 1)
 cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict__ cell_start,
                  const PosQ *__restrict__ packed, int mpad, int nranks, double *__restrict__ qz_sum) {
   __shared__ int wsum[32];
-  __shared__ int tile_total;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (qz_sum && t == 0) {  // multi-GPU: sum(q z) partials ride in the last slot of every rank's block
     double v = 0.0;
     for (int r = 0; r < nranks; ++r) v += packed[(size_t)r * mpad + mpad - 1].x;
     *qz_sum = v;
   }
-  int carry = 0;
-  for (int base = 0; base < ncells; base += 4096) {
-    const int idx = base + 4 * t;
-    int4 v = make_int4(0, 0, 0, 0);
-    if (idx < ncells) v = *reinterpret_cast<const int4 *>(cell_count + idx);
-    const int s1 = v.x + v.y, s2 = s1 + v.z, tsum = s2 + v.w;
-    int incl = tsum;
+  const int nvec = (ncells + 3) >> 2;            // int4 groups in the histogram
+  const int per = (nvec + 1023) >> 10;           // groups per thread
+  const int v0 = t * per, v1 = min(v0 + per, nvec);
+  const int4 *cnt4 = reinterpret_cast<const int4 *>(cell_count);
+  int tsum = 0;
+  for (int v = v0; v < v1; ++v) {
+    const int4 c = cnt4[v];
+    tsum += (c.x + c.y) + (c.z + c.w);
+  }
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = wsum[lane];
+    int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
+      const int u = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += u;
     }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const int w = wsum[lane];
-      int wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += u;
-      }
-      wsum[lane] = wi - w;
-      if (lane == 31) tile_total = wi;
-    }
-    __syncthreads();
-    const int excl = carry + wsum[warp] + incl - tsum;
-    if (idx < ncells) {
-      cell_start[idx] = excl;
-      if (idx + 1 < ncells) cell_start[idx + 1] = excl + v.x;
-      if (idx + 2 < ncells) cell_start[idx + 2] = excl + s1;
-      if (idx + 3 < ncells) cell_start[idx + 3] = excl + s2;
-    }
-    carry += tile_total;
-    __syncthreads();
+    wsum[lane] = wi - w;
+    if (lane == 31) cell_start[ncells] = wi;
   }
-  if (t == 0) cell_start[ncells] = carry;
+  __syncthreads();
+  int run = wsum[warp] + incl - tsum;
+  int4 *out4 = reinterpret_cast<int4 *>(cell_start);
+  for (int v = v0; v < v1; ++v) {
+    const int4 c = cnt4[v];
+    const int idx = 4 * v;
+    const int4 o = make_int4(run, run + c.x, run + c.x + c.y, run + c.x + c.y + c.z);
+    if (idx + 3 < ncells) {
+      out4[v] = o;
+    } else {  // tail group: cell_start[ncells] belongs to the grand total
+      cell_start[idx] = o.x;
+      if (idx + 1 < ncells) cell_start[idx + 1] = o.y;
+      if (idx + 2 < ncells) cell_start[idx + 2] = o.z;
+    }
+    run = o.w + c.w;
+  }
 }
 
 __global__ void __launch_bounds__(256)

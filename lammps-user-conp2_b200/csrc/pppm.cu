@@ -123,8 +123,8 @@ __device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
 template <bool REALK>
 __global__ void __launch_bounds__(ZC_THREADS)
 zconv_kernel(int ncol, int cols, int nz, int nzl, int zs_lo, int zin_lo, int nzo, const int *__restrict__ zout_list,
-             const int *__restrict__ krad, const double2 *__restrict__ rhat, const double *__restrict__ Kr,
-             const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
+             const int *__restrict__ krad, const int *__restrict__ blocks, const double2 *__restrict__ rhat,
+             const double *__restrict__ Kr, const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
   // rhat: spectra of this rank's nzl input planes (compact planes zs_lo .. zs_lo+nzl-1); on several
   // GPUs uhat is this rank's partial sum and is all-reduced afterwards
   extern __shared__ __align__(16) unsigned char zc_smem[];
@@ -133,7 +133,7 @@ zconv_kernel(int ncol, int cols, int nz, int nzl, int zs_lo, int zin_lo, int nzo
   double *ksr = reinterpret_cast<double *>(rh + (size_t)nzl * cols);  // REALK: [cols][kstride]
   double2 *ksc = reinterpret_cast<double2 *>(ksr);                     // else:  [cols][nz]
   __shared__ int s_rblock;
-  const int c0 = blockIdx.x * cols;
+  const int c0 = blocks[blockIdx.x] * cols;
   if (threadIdx.x == 0) {
     int r = 0;
     for (int cc = 0; cc < cols; ++cc) r = max(r, krad[min(c0 + cc, ncol - 1)]);
@@ -199,6 +199,117 @@ zconv_kernel(int ncol, int cols, int nz, int nzl, int zs_lo, int zin_lo, int nzo
       if (a - R < 0) run(a - R + nz, nz - 1);   // wrapped from below
       if (a + R >= nz) run(0, a + R - nz);      // wrapped from above
     }
+    uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
+  }
+}
+
+// Narrow variant: for most (kx,ky) the kernel K(d) is negligible beyond a few tens of planes, and
+// the output planes sit in two thin groups at the electrodes, so only the input planes within the
+// block's window of an output plane are staged -- compacted in shared memory through `rowof` --
+// together with the 2 rblock + 1 table entries K[-rblock .. rblock].  The block needs ~15 KB instead
+// of the whole column, several blocks share an SM and the loads of one hide behind the sums of
+// another.  Summation order per output is the same as in zconv_kernel (ascending input plane).
+constexpr int ZC_COLS = 8;
+
+template <bool REALK>
+__global__ void __launch_bounds__(ZC_THREADS)
+zconv_narrow_kernel(int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo, const int *__restrict__ zout_list,
+                    const int *__restrict__ krad, const int *__restrict__ groups, int rcap, int npcap,
+                    const double2 *__restrict__ rhat, const double *__restrict__ Kr,
+                    const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
+  extern __shared__ __align__(16) unsigned char zc_smem[];
+  double2 *rh = reinterpret_cast<double2 *>(zc_smem);                   // [npcap][ZC_COLS]
+  const int kst = 2 * rcap + 1;
+  double *ksr = reinterpret_cast<double *>(rh + (size_t)npcap * ZC_COLS);  // REALK: [ZC_COLS][kst]
+  double2 *ksc = reinterpret_cast<double2 *>(ksr);                          // else:  [ZC_COLS][kst]
+  int *rowof = reinterpret_cast<int *>(zc_smem + sizeof(double2) * (size_t)npcap * ZC_COLS +
+                                       (REALK ? sizeof(double) : sizeof(double2)) * (size_t)ZC_COLS * kst);
+  __shared__ int s_rblock, s_wcount[ZC_THREADS / 32], s_base;
+  const int c0 = groups[blockIdx.x] * ZC_COLS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int cc = 0; cc < ZC_COLS; ++cc) r = max(r, krad[min(c0 + cc, ncol - 1)]);
+    s_rblock = r;
+    s_base = 0;
+  }
+  __syncthreads();
+  const int rblock = s_rblock;
+  // which planes of the slab lie within rblock (on the ring) of an output plane; rowof = compact row
+  for (int t0 = 0; t0 < nzl; t0 += ZC_THREADS) {
+    const int t = t0 + threadIdx.x;
+    bool needed = false;
+    if (t < nzl) {
+      const int zi = zs_lo + t;
+      for (int zo = 0; zo < nzo && !needed; ++zo) {
+        int a = (zout_list[zo] - zin_lo) % nz;
+        if (a < 0) a += nz;
+        const int d = abs(a - zi);
+        needed = min(d, nz - d) <= rblock;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, needed);
+    if (lane == 0) s_wcount[warp] = __popc(m);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_wcount[w];
+    if (t < nzl) rowof[t] = needed ? before + __popc(m & ((1u << lane) - 1u)) : -1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < ZC_THREADS / 32; ++w) tot += s_wcount[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < nzl * ZC_COLS; idx += ZC_THREADS) {
+    const int t = idx / ZC_COLS, cc = idx - t * ZC_COLS;
+    const int row = rowof[t];
+    if (row >= 0) cp_async<16>(&rh[row * ZC_COLS + cc], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
+  }
+  for (int idx = threadIdx.x; idx < ZC_COLS * (2 * rblock + 1); idx += ZC_THREADS) {
+    const int cc = idx / (2 * rblock + 1), j = idx - cc * (2 * rblock + 1);
+    const int c = min(c0 + cc, ncol - 1);
+    int d = j - rblock;  // signed ring distance
+    d += (d < 0) ? nz : 0;
+    if (REALK)
+      cp_async<8>(&ksr[cc * kst + j], Kr + (size_t)c * nz + d);
+    else
+      cp_async<16>(&ksc[cc * kst + j], Kc + (size_t)c * nz + d);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  for (int item = threadIdx.x; item < ZC_COLS * nzo; item += ZC_THREADS) {
+    const int zo = item / ZC_COLS, cc = item - zo * ZC_COLS;
+    const int c = c0 + cc;
+    if (c >= ncol) continue;
+    const int R = krad[c];
+    int a = (zout_list[zo] - zin_lo) % nz;
+    if (a < 0) a += nz;
+    double ar = 0.0, ai = 0.0;
+    // input planes z0..z1 clipped to the slab; signed distance of plane zi is a - zi + shift
+    auto run = [&](int z0, int z1, int shift) {
+      z0 = max(z0, zs_lo);
+      z1 = min(z1, zs_lo + nzl - 1);
+      if (z0 > z1) return;
+      int row = rowof[z0 - zs_lo];           // the planes of one run are consecutive compact rows
+      int j = a - z0 + shift + rblock;
+      for (int zi = z0; zi <= z1; ++zi, ++row, --j) {
+        const double2 r = rh[row * ZC_COLS + cc];
+        if (REALK) {
+          const double k = ksr[cc * kst + j];
+          ar = fma(k, r.x, ar);
+          ai = fma(k, r.y, ai);
+        } else {
+          const double2 k = ksc[cc * kst + j];
+          ar = fma(k.x, r.x, ar); ar = fma(-k.y, r.y, ar);
+          ai = fma(k.x, r.y, ai); ai = fma(k.y, r.x, ai);
+        }
+      }
+    };
+    run(max(a - R, 0), min(a + R, nz - 1), 0);   // main window
+    if (a - R < 0) run(a - R + nz, nz - 1, nz);   // wrapped from below
+    if (a + R >= nz) run(0, a + R - nz, -nz);     // wrapped from above
     uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
   }
 }
@@ -356,38 +467,124 @@ int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, co
   return 1;
 }
 
-int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
-                      const int *zout_list, const int *krad, const cufftDoubleComplex *rhat, const double *Kr,
-                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
+namespace {
+size_t zc_narrow_smem(int npcap, int rcap, int nzl, bool real_k) {
+  return sizeof(double2) * (size_t)npcap * ZC_COLS +
+         (real_k ? sizeof(double) : sizeof(double2)) * (size_t)ZC_COLS * (2 * rcap + 1) + sizeof(int) * (size_t)nzl;
+}
+int zc_wide_cols(int nz, int nzl, bool real_k, size_t *smem_out) {
   // widest column group whose rho^ + K rows fit in shared memory
-  const size_t kbytes = Kr ? sizeof(double) * (size_t)(nz | 1) : sizeof(double2) * (size_t)nz;
-  int cols = 8;
-  size_t smem = 0;
-  for (; cols >= 1; cols >>= 1) {
-    smem = (sizeof(double2) * (size_t)nzl + kbytes) * cols;
-    if (smem <= 200 * 1024) break;
-  }
-  if (cols < 1) CONP_THROW(CONP_ERR_ARG, "PPPM mesh too deep in z for the z-convolution kernel (nz = %d)", nz);
-  static size_t smem_set_r = 0, smem_set_c = 0;
-  const int grid = (ncol + cols - 1) / cols;
-  if (Kr) {
-    if (smem > smem_set_r) {
-      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set_r = smem;
+  const size_t kbytes = real_k ? sizeof(double) * (size_t)(nz | 1) : sizeof(double2) * (size_t)nz;
+  for (int cols = 8; cols >= 1; cols >>= 1) {
+    const size_t smem = (sizeof(double2) * (size_t)nzl + kbytes) * cols;
+    if (smem <= 200 * 1024) {
+      if (smem_out) *smem_out = smem;
+      return cols;
     }
-    zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad,
-                                                      (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
-  } else {
-    if (smem > smem_set_c) {
-      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set_c = smem;
-    }
-    zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad,
-                                                       (const double2 *)rhat, nullptr, (const double2 *)Kc,
-                                                       (double2 *)uhat);
   }
-  CUDA_CHECK(cudaGetLastError());
-  return 1;
+  return 0;
+}
+}  // namespace
+
+// Split the column groups between the two kernels.  The narrow kernel is sized for the largest window
+// radius whose staging still fits ZC_NARROW_SMEM; np(R) = planes of [0, nzi) within R of an output plane.
+void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, int nzl, int zin_lo,
+                     const std::vector<int> &zout, bool real_k, std::vector<int> &narrow, std::vector<int> &wide,
+                     ZconvPlan &plan) {
+  constexpr size_t ZC_NARROW_SMEM = 44 * 1024;
+  narrow.clear();
+  wide.clear();
+  plan = ZconvPlan();
+  plan.cols_w = zc_wide_cols(nz, std::max(nzl, 1), real_k, nullptr);
+  if (plan.cols_w < 1) CONP_THROW(CONP_ERR_ARG, "PPPM mesh too deep in z for the z-convolution kernel (nz = %d)", nz);
+  // distance of every input plane to the nearest output plane (on the ring)
+  std::vector<int> dist(std::max(nzi, 1), nz);
+  for (int zo : zout) {
+    int a = (zo - zin_lo) % nz;
+    if (a < 0) a += nz;
+    for (int zi = 0; zi < nzi; ++zi) {
+      const int d = std::abs(a - zi);
+      dist[zi] = std::min(dist[zi], std::min(d, nz - d));
+    }
+  }
+  std::vector<int> npof(nz + 1, 0);  // np(R), cumulative histogram of dist
+  for (int zi = 0; zi < nzi; ++zi) npof[std::min(dist[zi], nz)]++;
+  for (int r = 1; r <= nz; ++r) npof[r] += npof[r - 1];
+  int rcap = -1;
+  for (int r = 0; 2 * r + 1 < nz; ++r) {
+    if (zc_narrow_smem(npof[r], r, std::max(nzl, 1), real_k) > ZC_NARROW_SMEM) break;
+    rcap = r;
+  }
+  const int ngroups = (ncol + ZC_COLS - 1) / ZC_COLS;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    int rb = 0;
+    for (int cc = 0; cc < ZC_COLS; ++cc) rb = std::max(rb, krad[std::min(gi * ZC_COLS + cc, ncol - 1)]);
+    if (rb <= rcap) {
+      narrow.push_back(gi);
+    } else {
+      const int per = ZC_COLS / plan.cols_w;
+      for (int i = 0; i < per; ++i)
+        if ((gi * per + i) * plan.cols_w < ncol) wide.push_back(gi * per + i);
+    }
+  }
+  plan.n_narrow = (int)narrow.size();
+  plan.n_wide = (int)wide.size();
+  plan.rcap = std::max(rcap, 0);
+  plan.npcap = rcap >= 0 ? std::max(npof[rcap], 1) : 1;
+}
+
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
+                      const int *zout_list, const int *krad, const ZconvPlan &plan, const cufftDoubleComplex *rhat,
+                      const double *Kr, const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
+  int launched = 0;
+  static size_t smem_set_r = 0, smem_set_c = 0, nsmem_set_r = 0, nsmem_set_c = 0;
+  if (plan.n_wide > 0) {
+    size_t smem = 0;
+    const int cols = zc_wide_cols(nz, std::max(nzl, 1), Kr != nullptr, &smem);
+    if (cols != plan.cols_w) CONP_THROW(CONP_ERR_STATE, "z-convolution plan is stale (cols %d vs %d)", cols, plan.cols_w);
+    if (Kr) {
+      if (smem > smem_set_r) {
+        CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set_r = smem;
+      }
+      zconv_kernel<true><<<plan.n_wide, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad,
+                                                               plan.wide, (const double2 *)rhat, Kr, nullptr,
+                                                               (double2 *)uhat);
+    } else {
+      if (smem > smem_set_c) {
+        CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set_c = smem;
+      }
+      zconv_kernel<false><<<plan.n_wide, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list,
+                                                                krad, plan.wide, (const double2 *)rhat, nullptr,
+                                                                (const double2 *)Kc, (double2 *)uhat);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    ++launched;
+  }
+  if (plan.n_narrow > 0) {
+    const size_t smem = zc_narrow_smem(plan.npcap, plan.rcap, std::max(nzl, 1), Kr != nullptr);
+    if (Kr) {
+      if (smem > nsmem_set_r) {
+        CUDA_CHECK(cudaFuncSetAttribute(zconv_narrow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nsmem_set_r = smem;
+      }
+      zconv_narrow_kernel<true><<<plan.n_narrow, ZC_THREADS, smem, s>>>(
+          ncol, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad, plan.narrow, plan.rcap, plan.npcap,
+          (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
+    } else {
+      if (smem > nsmem_set_c) {
+        CUDA_CHECK(cudaFuncSetAttribute(zconv_narrow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nsmem_set_c = smem;
+      }
+      zconv_narrow_kernel<false><<<plan.n_narrow, ZC_THREADS, smem, s>>>(
+          ncol, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad, plan.narrow, plan.rcap, plan.npcap,
+          (const double2 *)rhat, nullptr, (const double2 *)Kc, (double2 *)uhat);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    ++launched;
+  }
+  return launched;
 }
 
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
