@@ -146,26 +146,15 @@ struct PeerArena {
   char **d_peer = nullptr;         // device copy
   // control block at the start of every arena: flags[chan][rank] (written by peers), then local-only
   // epoch[chan] and an error word
-  static constexpr size_t CTRL_BYTES = 4096;
+  static constexpr size_t CTRL_BYTES = P2P_CTRL_BYTES;
 };
 
 namespace {
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { return peer_ld_acquire(p); }
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { peer_st_release(p, v); }
 
-struct ArenaCtl {  // layout of the control block
-  unsigned long long flags[P2P_CHANNELS][16];
-  unsigned long long epoch[P2P_CHANNELS];
-  int error;
-};
-static_assert(sizeof(ArenaCtl) <= PeerArena::CTRL_BYTES, "control block too large");
+static_assert(sizeof(ArenaCtl) + P2P_CHANNELS * 16 * sizeof(unsigned int) <= P2P_CTRL_BYTES, "control block too large");
 
 // grid = (blocks_per_peer, nranks-1); peer index p = (rank + 1 + blockIdx.y) % nranks
 __global__ void __launch_bounds__(256)
@@ -367,6 +356,13 @@ int p2p_wait(PeerArena *a, int chan, cudaStream_t s) {
   return 1;
 }
 
+int p2p_wait_sync(const PeerSync &ps, cudaStream_t s) {
+  if (!ps.arena) return 0;
+  p2p_wait_kernel<<<1, 32, 0, s>>>(ps.arena, ps.rank, ps.nranks, ps.chan);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 int p2p_allgather(PeerArena *a, size_t off, size_t stride_bytes, size_t block_bytes, int chan, cudaStream_t s) {
   int n = p2p_push(a, off + (size_t)a->rank * stride_bytes, block_bytes, chan, s);
   return n + p2p_wait(a, chan, s);
@@ -385,6 +381,16 @@ int p2p_allreduce_f64(PeerArena *a, size_t off, size_t n, size_t stage_off, int 
   CUDA_CHECK(cudaGetLastError());
   p2p_wait(a, chan + 1, s);
   return 4;
+}
+
+PeerSync p2p_sync(PeerArena *a, int chan) {
+  PeerSync ps;
+  if (!a) return ps;
+  ps.arena = a->d_peer;
+  ps.rank = a->rank;
+  ps.nranks = a->nranks;
+  ps.chan = chan;
+  return ps;
 }
 
 int p2p_error(PeerArena *a) {

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/conp_b200.h"
+#include "peer.cuh"
 
 namespace conp {
 
@@ -205,7 +206,6 @@ void comm_allreduce_sum_f64(Comm *, double *buf, size_t n, cudaStream_t);
 // peer's arena and raise my flag there; wait = spin until every peer's flag for that channel has
 // reached the current epoch.  Replaces the small latency-bound NCCL collectives of the step.
 struct PeerArena;
-constexpr int P2P_CHANNELS = 8;
 PeerArena *p2p_create(Comm *, size_t bytes, cudaStream_t);          // collective; nullptr if IPC is unavailable
 void p2p_destroy(PeerArena *);
 char *p2p_local(PeerArena *);
@@ -218,6 +218,9 @@ int p2p_wait(PeerArena *, int chan, cudaStream_t);
 // scratch of nranks * ceil(n/nranks) doubles; uses channels chan and chan+1
 int p2p_allreduce_f64(PeerArena *, size_t off, size_t n, size_t stage_off, int chan, cudaStream_t);
 int p2p_error(PeerArena *);  // non-zero after a wait timed out
+// argument for kernels that do their own exchange (peer.cuh); a null arena gives the no-op value
+PeerSync p2p_sync(PeerArena *, int chan);
+int p2p_wait_sync(const PeerSync &, cudaStream_t);  // stand-alone wait on a PeerSync
 
 // ---------------------------------------------------------------------------
 // kernel launchers (one .cu per group); all take the context's stream and
@@ -249,9 +252,14 @@ struct SymvPlan {
   const int2 *strips = nullptr;  // device: [a, bnd) global row range of every strip
 };
 SymvPlan plan_symv(int N, int row0, int nrows, int num_sms, std::vector<int2> &strips);
+// wait_b: poll the b exchange in the kernel's prologue; push_parts: store the result into slot `rank` of
+// every rank's staging area at off_parts (out_len doubles per slot) instead of `out`, and signal.
 int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, int nrows, const double *b,
                 const SymvPlan &plan, double *rowpart, double *colpart, double *out, int out_len,
-                const ChargeEpilogue *ep);
+                const ChargeEpilogue *ep, const PeerSync &wait_b, const PeerSync &push_parts, size_t off_parts);
+// sum of the nranks staged partial vectors (after their flags are up) -> sb_out, then the epilogue
+int launch_update_charge_sum(cudaStream_t s, const ChargeEpilogue &ep, const PeerSync &ps, const double *parts,
+                             int len, double *sb_out);
 int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep);
 int launch_finalize_q(cudaStream_t s, int n, const double *sb, const double *setq, const double *qinit,
                       const double *scal /* [1] = potdiff */, double *q_out);
@@ -267,10 +275,12 @@ void build_pair_runs(const CellGrid &g, int begin, int end, const double *xyz, s
 // per-step counting sort of the point charges: pack (+histogram, + sum q z), scan, scatter
 int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
                       const double *q, const int *type, PosQ *packed, int *packed_type, int *cell_of, int *slot,
-                      int *cell_count, double *qz_sum);
+                      int *cell_count, double *qz_sum, const PeerSync &ps /* fused all-gather of the block */,
+                      size_t off_block /* arena offset of `packed` */, int mpad);
 // multi-GPU layout: nranks blocks of mpad slots, counts[r] valid charges each; m = nranks*mpad
 int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, int mpad, const int *counts,
-                         const PosQ *packed, int *cell_of, int *slot, int *cell_count);
+                         const PosQ *packed, int *cell_of, int *slot, int *cell_count,
+                         const PeerSync &ps /* wait for the fused all-gather */);
 // qz_sum != nullptr: also sum the per-rank sum(q z) partials stored in the last slot of every block
 int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start, const PosQ *packed,
                      int mpad, int nranks, double *qz_sum);
@@ -302,22 +312,28 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
                        const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
 // rhat: spectra of the rank's nzl input planes (compact planes zs_lo..); uhat: (partial) output-plane spectra
-// Launch plan of the z-convolution (built once by plan_pppm_zconv): column groups whose window is
-// short ("narrow": only the input planes near an output plane and the matching slice of the kernel
-// table are staged, several blocks per SM) and the few small-|k_xy| groups that need every plane.
-struct ZconvPlan {
-  const int *narrow = nullptr;  // device list of 8-column group indices
-  const int *wide = nullptr;    // device list of cols_w-column block indices
-  int n_narrow = 0, n_wide = 0;
-  int cols_w = 8;               // columns per block of the wide kernel
-  int rcap = 0, npcap = 0;      // narrow kernel: largest window radius / staged planes it is sized for
+// Launch plan of the z-convolution (built once per rank by plan_pppm_zconv): narrow column groups stage
+// only the input planes near an output plane; the few small-|k_xy| columns whose kernel spans the mesh
+// take the wide path.  See zconv_kernel.
+struct ZconvGroup {  // 32 ints
+  static constexpr int MAXI = 8;
+  int c0, rblock, nint, np;          // first column, window radius, intervals, staged planes
+  int lo[MAXI], hi[MAXI], base[MAXI];  // slab-local plane interval [lo, hi) -> compact rows base..
+  int pad[4];
 };
-void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, int nzl, int zin_lo,
-                     const std::vector<int> &zout, bool real_k, std::vector<int> &narrow, std::vector<int> &wide,
-                     ZconvPlan &plan);
-int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
-                      const int *zout_list, const int *krad, const ZconvPlan &plan, const cufftDoubleComplex *rhat,
-                      const double *Kr, const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
+struct ZconvPlan {
+  const ZconvGroup *narrow = nullptr;  // device
+  const int *wide = nullptr;           // device list of wide columns
+  const int *aout = nullptr;           // device: ring position of every output plane (compact coordinates)
+  int n_narrow = 0, n_wide = 0;
+  int rcap = 0, npcap = 1;             // narrow path: largest window radius / staged planes it is sized for
+};
+void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, int zs_lo, int nzl, int zin_lo,
+                     const std::vector<int> &zout, bool real_k, std::vector<ZconvGroup> &narrow,
+                     std::vector<int> &wide, std::vector<int> &aout, ZconvPlan &plan);
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int nzo, const int *krad,
+                      const ZconvPlan &plan, const cufftDoubleComplex *rhat, const double *Kr,
+                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
                          const double *compact, double *full);
 int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,
@@ -329,7 +345,8 @@ int launch_pppm_point_table(cudaStream_t s, const PPPMGeom &g, int n, const int 
                             int *poff, double *pw);
 int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *poff,
                          const double *pw, const double *u_brick, const double *ez, const double *qz_sum,
-                         double slab_pref /* 4 pi / V or 0 */, const double *b_real, double *b_kspace, double *b);
+                         double slab_pref, const double *b_real, double *b_kspace, double *b,
+                         const PeerSync &ps /* fused b exchange; null arena: none */, size_t off_b);
 // electrode re-spread; forms q_i = sb_i + potdiff*setq_i (+qinit_i) on the fly and stores it to q_out
 // (spreads rows [row_begin,row_end) only; all n charges are written to q_out)
 int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, int row_begin, int row_end, const int *widx,

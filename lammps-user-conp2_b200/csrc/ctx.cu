@@ -32,7 +32,7 @@ struct conp_ctx {
   // direct NVLink exchanges (multi-GPU): b, S.b, the output-plane spectra and the packed charges live
   // in an IPC-mapped arena that every peer writes into; nullptr => NCCL collectives
   PeerArena *p2p = nullptr;
-  size_t p2p_bytes = 0, off_b = 0, off_sb = 0, off_uhat = 0, off_stage = 0, off_packed = 0;
+  size_t p2p_bytes = 0, off_b = 0, off_sb = 0, off_uhat = 0, off_stage = 0, off_packed = 0, off_parts = 0;
   std::string err;
   long long launches = 0;
 
@@ -106,7 +106,8 @@ struct conp_ctx {
   std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
   std::vector<int> h_zout;              // output planes (sorted)
   DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
-  DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad, d_zc_narrow, d_zc_wide;
+  DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad, d_zc_wide, d_zc_aout;
+  DevBuf<ZconvGroup> d_zc_narrow;
   ZconvPlan zplan;
   DevBuf<double> d_pw;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
@@ -247,7 +248,8 @@ void ensure_p2p(conp_ctx *c) {
   const size_t u_bytes = up(sizeof(double) * std::max<size_t>(n_u, 2));
   const size_t st_bytes = up(sizeof(double) * std::max<size_t>(slice * c->nranks, 2));
   const size_t pk_bytes = up(sizeof(PosQ) * (size_t)std::max(c->m_slots, 1));
-  const size_t need = 2 * b_bytes + u_bytes + st_bytes + pk_bytes;
+  const size_t pt_bytes = up(sizeof(double) * c->vlen * c->nranks);  // one partial S.b per rank
+  const size_t need = 2 * b_bytes + u_bytes + st_bytes + pk_bytes + pt_bytes;
   if (c->p2p && need == c->p2p_bytes) return;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   if (c->p2p) {
@@ -263,6 +265,7 @@ void ensure_p2p(conp_ctx *c) {
   c->off_uhat = 2 * b_bytes;
   c->off_stage = c->off_uhat + u_bytes;
   c->off_packed = c->off_stage + st_bytes;
+  c->off_parts = c->off_packed + pk_bytes;
   char *base = p2p_local(c->p2p);
   c->d_b.attach((double *)(base + c->off_b), c->vlen);
   c->d_sb.attach((double *)(base + c->off_sb), c->vlen);
@@ -279,13 +282,9 @@ void stage_mark(conp_ctx *c, int i) {
 // of the symmetric branch.  The epilogue can only be fused on one GPU.
 int enqueue_matvec(conp_ctx *c, cudaStream_t s, const double *b, double *out, const ChargeEpilogue *ep) {
   const int nr = c->r1 - c->r0;
-  if (c->sym) {
-    if (c->sy.usable)
-      return launch_symv(s, c->d_mat.p, c->pitch, c->N, c->r0, nr, b, c->sy, c->d_rowpart.p, c->d_colpart.p, out,
-                         (int)c->vlen, ep);
-    CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * c->vlen, s));  // rank without rows
-    return 0;
-  }
+  if (c->sym)
+    return launch_symv(s, c->d_mat.p, c->pitch, c->N, c->r0, nr, b, c->sy, c->d_rowpart.p, c->d_colpart.p, out,
+                       (int)c->vlen, ep, PeerSync(), PeerSync(), 0);
   return launch_gemv(s, c->d_mat.p, c->pitch, nr, c->ncols_pad, b, out + c->r0, c->num_sms, ep);
 }
 
@@ -347,27 +346,29 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   CUDA_CHECK(cudaMemsetAsync(c->d_cellcount.p, 0, sizeof(int) * ((size_t)g.ncells + 8), s));
   PosQ *packed_local = c->d_packed.p + c->m_offsets[c->rank];
   int *ptype_local = c->d_ptype.p + c->m_offsets[c->rank];
+  // several GPUs, peer-to-peer path: the exchanges are done by the producing / consuming kernels
+  const bool fused = multi && c->p2p != nullptr;
+  const PeerSync ps_pos = fused ? p2p_sync(c->p2p, 0) : PeerSync();
   if (!multi) {
     c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
-                                     ptype_local, c->d_cellof.p, c->d_slot.p, c->d_cellcount.p, c->scal(2));
+                                     ptype_local, c->d_cellof.p, c->d_slot.p, c->d_cellcount.p, c->scal(2),
+                                     PeerSync(), 0, 0);
   } else {
+    // every rank's positions go to every rank; the sum(q z) partial rides in the block's last (padding)
+    // slot.  Types and charges are static between reneighbourings and were gathered in conp_post_neighbor.
     c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
-                                     ptype_local, nullptr, nullptr, nullptr, c->scal(2));
+                                     ptype_local, nullptr, nullptr, nullptr, c->scal(2), ps_pos,
+                                     c->off_packed + sizeof(PosQ) * (size_t)c->m_offsets[c->rank], c->mpad);
   }
   stage_mark(c, 1);
   if (multi) {
-    // one equal-block allgather moves every rank's positions; the sum(q z) partial rides in the
-    // block's last (padding) slot.  Types and charges are static between reneighbourings and were
-    // gathered in conp_post_neighbor.
-    CUDA_CHECK(cudaMemcpyAsync(&packed_local[c->mpad - 1].x, c->scal(2), sizeof(double), cudaMemcpyDeviceToDevice,
-                               s));
-    if (c->p2p)
-      c->launches += p2p_allgather(c->p2p, c->off_packed, sizeof(PosQ) * (size_t)c->mpad,
-                                   sizeof(PosQ) * (size_t)c->mpad, 0, s);
-    else
+    if (!fused) {
+      CUDA_CHECK(cudaMemcpyAsync(&packed_local[c->mpad - 1].x, c->scal(2), sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s));
       comm_allgather(c->comm, packed_local, c->d_packed.p, sizeof(PosQ) * (size_t)c->mpad, s);
+    }
     c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, c->d_mcounts.p, c->d_packed.p, c->d_cellof.p,
-                                        c->d_slot.p, c->d_cellcount.p);
+                                        c->d_slot.p, c->d_cellcount.p, ps_pos);
   }
   c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p, c->d_packed.p, c->mpad,
                                   c->nranks, multi ? c->scal(2) : nullptr);
@@ -392,6 +393,8 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
 
   // ---- k-space part of b --------------------------------------------------------
   const double spref = slab_pref(c);
+  // PPPM mode on the peer-to-peer path: the gather kernel stores b into every peer itself
+  const bool fused_b = fused && kspace_mode == CONP_KSPACE_PPPM;
   if (kspace_mode == CONP_KSPACE_PPPM) {
     const PPPMGeom &pg = c->pg;
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
@@ -413,9 +416,8 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                         c->d_flag.p);
     }
     if (pg.zs_n > 0) CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
-    c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.zin_lo, pg.nzo, c->d_zout.p,
-                                     c->d_krad.p, c->zplan, c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr,
-                                     c->d_Kc.p, c->d_uhat.p);
+    c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.nzo, c->d_krad.p, c->zplan,
+                                     c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p);
     // every rank holds the partial sum over its slab: one small all-reduce completes the spectra
     if (multi) {
       if (c->p2p)
@@ -428,7 +430,8 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     stage_mark(c, 4);
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
     c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_poff.p, c->d_pw.p, c->d_ubrick.p,
-                                        c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
+                                        c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p,
+                                        fused_b ? p2p_sync(c->p2p, 3) : PeerSync(), c->off_b);
   } else {
     const EwaldHost &e = c->ew;
     c->launches += launch_axis_tables(s, c->m_total, nullptr, nullptr, nullptr, c->d_sorted.p, e.unitk, e.kxmax,
@@ -443,25 +446,40 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   }
   stage_mark(c, 5);
 
-  // ---- exchange b, GEMV (+ fused epilogue on one GPU), exchange S.b ------------------
-  if (multi) {
-    if (c->p2p)
-      c->launches += p2p_allgather(c->p2p, c->off_b, sizeof(double) * c->rpr, sizeof(double) * c->rpr, 3, s);
-    else
+  // ---- exchange b, matvec (+ fused epilogue on one GPU), exchange S.b ------------------
+  // Peer-to-peer path with the symmetric matvec: no stand-alone exchange kernels at all -- b arrives
+  // while symv_tma_kernel is already streaming S (its consumers poll the flags), symv_reduce_kernel
+  // stores this rank's partial product into every rank's staging slot, and update_charge_sum_kernel
+  // waits, adds the slots in rank order and runs the epilogue.
+  const bool fused_mv = fused && c->sym;
+  if (multi && !fused_b) {
+    if (c->p2p) {
+      c->launches += p2p_push(c->p2p, c->off_b + sizeof(double) * (size_t)c->rank * c->rpr,
+                              sizeof(double) * c->rpr, 3, s);
+      if (!fused_mv) c->launches += p2p_wait(c->p2p, 3, s);
+    } else {
       comm_allgather(c->comm, c->d_b.p + c->r0, c->d_b.p, sizeof(double) * c->rpr, s);
+    }
+  } else if (fused_b && !fused_mv) {
+    c->launches += p2p_wait(c->p2p, 3, s);
   }
   stage_mark(c, 6);
   if (!multi) {
     const ChargeEpilogue ep = make_epilogue(c, variant, true);
     c->launches += enqueue_matvec(c, s, c->d_b.p, c->d_sb.p, &ep);
     stage_mark(c, 7);
+  } else if (fused_mv) {
+    c->launches += launch_symv(s, c->d_mat.p, c->pitch, c->N, c->r0, nr, c->d_b.p, c->sy, c->d_rowpart.p,
+                               c->d_colpart.p, c->d_sb.p, (int)c->vlen, nullptr, p2p_sync(c->p2p, 3),
+                               p2p_sync(c->p2p, 4), c->off_parts);
+    stage_mark(c, 7);
+    c->launches += launch_update_charge_sum(s, make_epilogue(c, variant, false), p2p_sync(c->p2p, 4),
+                                            (const double *)(p2p_local(c->p2p) + c->off_parts), (int)c->vlen,
+                                            c->d_sb.p);
   } else {
     c->launches += enqueue_matvec(c, s, c->d_b.p, c->d_sb.p, nullptr);
     if (c->sym) {  // every rank holds a partial sum over its half band: all-reduce instead of all-gather
-      if (c->p2p)
-        c->launches += p2p_allreduce_f64(c->p2p, c->off_sb, c->vlen, c->off_stage, 4, s);
-      else
-        comm_allreduce_sum_f64(c->comm, c->d_sb.p, c->vlen, s);
+      comm_allreduce_sum_f64(c->comm, c->d_sb.p, c->vlen, s);
     } else if (c->p2p) {
       c->launches += p2p_allgather(c->p2p, c->off_sb, sizeof(double) * c->rpr, sizeof(double) * c->rpr, 4, s);
     } else {
@@ -815,13 +833,13 @@ int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type,
       std::vector<int2> strips;
       c->sym_plan_ok = plan_symv(N, 0, std::min(c->rpr, N), c->num_sms, strips).usable;
       c->sy = plan_symv(N, c->r0, c->r1 - c->r0, c->num_sms, strips);
+      c->sym_plan_ok = c->sym_plan_ok && c->sy.usable;
       if (c->sym_plan_ok) {
         c->d_rowpart.zero(c->vlen, c->stream);
-        if (c->sy.usable) {
-          c->d_colpart.zero((size_t)c->sy.nstrips * c->sy.L, c->stream);
-          c->d_strips.upload(strips, c->stream);
-          c->sy.strips = c->d_strips.p;
-        }
+        c->d_colpart.zero(std::max<size_t>((size_t)c->sy.nstrips * c->sy.L, 2), c->stream);
+        if (strips.empty()) strips.push_back(make_int2(0, 0));
+        c->d_strips.upload(strips, c->stream);
+        c->sy.strips = c->d_strips.p;
       }
     }
     std::vector<double> hx(N), hy(N), hz(N);
@@ -977,19 +995,24 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     // ---- this rank's slab of input planes (all of them on one GPU) ------------------
     g.zs_lo = (int)(((long long)g.nzi * c->rank) / c->nranks);
     g.zs_n = (int)(((long long)g.nzi * (c->rank + 1)) / c->nranks) - g.zs_lo;
-    {  // split the (kx,ky) column groups between the windowed and the full z-convolution kernels
-      std::vector<int> narrow, wide;
-      plan_pppm_zconv(h_krad, (int)ncol, (int)nz, g.nzi, g.zs_n, g.zin_lo, c->h_zout, c->k_real, narrow, wide,
-                      c->zplan);
+    {  // split the (kx,ky) column groups between the narrow and the wide z-convolution paths
+      std::vector<ZconvGroup> narrow;
+      std::vector<int> wide, aout;
+      plan_pppm_zconv(h_krad, (int)ncol, (int)nz, g.nzi, g.zs_lo, g.zs_n, g.zin_lo, c->h_zout, c->k_real, narrow,
+                      wide, aout, c->zplan);
       if (getenv("CONP_DEBUG"))
-        fprintf(stderr, "[conp] zconv plan: %d narrow groups (R <= %d, <= %d planes staged), %d wide blocks of %d cols\n",
-                c->zplan.n_narrow, c->zplan.rcap, c->zplan.npcap, c->zplan.n_wide, c->zplan.cols_w);
-      if (narrow.empty()) narrow.push_back(0);
+        fprintf(stderr, "[conp] zconv plan: %d narrow groups (R <= %d, <= %d planes staged), %d wide columns\n",
+                c->zplan.n_narrow, c->zplan.rcap, c->zplan.npcap, c->zplan.n_wide);
+      if (narrow.empty()) narrow.resize(1);
       if (wide.empty()) wide.push_back(0);
+      if (aout.empty()) aout.push_back(0);
       c->d_zc_narrow.upload(narrow, s);
       c->d_zc_wide.upload(wide, s);
+      c->d_zc_aout.upload(aout, s);
       c->zplan.narrow = c->d_zc_narrow.p;
       c->zplan.wide = c->d_zc_wide.p;
+      c->zplan.aout = c->d_zc_aout.p;
+      CUDA_CHECK(cudaStreamSynchronize(s));
     }
     // ---- compact bricks and batched 2-D plans -------------------------------------
     c->d_brick.zero((size_t)std::max(g.zs_n, 1) * c->plane, s);

@@ -294,6 +294,30 @@ update_charge_kernel(ChargeEpilogue ep) {
   charge_epilogue(ep, a, z, threadIdx.x, UC_THREADS, 0, sh, &flag);
 }
 
+// Several GPUs, symmetric matvec, peer-to-peer path: every rank's partial S.b sits in slot r of the
+// local staging area once the flags are up.  Sum the slots in rank order (the same order on every
+// rank: bitwise identical charges everywhere), store S.b and run the epilogue -- the all-reduce of
+// fix_conp.cpp:1140 and the epilogue in one kernel.
+__global__ void __launch_bounds__(UC_THREADS)
+update_charge_sum_kernel(ChargeEpilogue ep, PeerSync ps, const double *__restrict__ parts, int len,
+                         double *__restrict__ sb_out) {
+  __shared__ double sh[UC_THREADS];
+  __shared__ int flag;
+  peer_block_wait(ps);
+  __syncthreads();
+  double a = 0.0, z = 0.0;
+  for (int i = blockIdx.x * UC_THREADS + threadIdx.x; i < len; i += gridDim.x * UC_THREADS) {
+    double v = 0.0;
+    for (int r = 0; r < ps.nranks; ++r) v += __ldcg(parts + (size_t)r * len + i);
+    sb_out[i] = v;
+    if (i < ep.n) {
+      if (ep.side[i] == 1) a += v;
+      z = fma(ep.setz[i], v, z);
+    }
+  }
+  charge_epilogue(ep, a, z, threadIdx.x, UC_THREADS, 0, sh, &flag);
+}
+
 // q_i = (S.b)_i + potdiff * setq_i (+ qinit_i): fix_conp.cpp:1153-1158
 __global__ void __launch_bounds__(256)
 finalize_q_kernel(int n, const double *__restrict__ sb, const double *__restrict__ setq,
@@ -379,7 +403,7 @@ __device__ __forceinline__ bool sy_in_band(int rg, int nr, const SyChunk &ch, in
 __global__ void __launch_bounds__(THREADS, 1)
 symv_tma_kernel(const double *__restrict__ S, size_t pitch, int N, int row0, const int2 *__restrict__ strips,
                 int nstrips, int L, const double *__restrict__ b, double *__restrict__ rowpart,
-                double *__restrict__ colpart) {
+                double *__restrict__ colpart, PeerSync ps_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SySmem &sm = *reinterpret_cast<SySmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -429,6 +453,12 @@ symv_tma_kernel(const double *__restrict__ S, size_t pitch, int N, int row0, con
   }
 
   // ===== consumers =====
+  // several GPUs: b is being written by the peers' gather kernels.  The producer warp is already
+  // streaming S (which is local); the consumers poll the flags before their first read of b.
+  if (ps_b.arena) {
+    peer_block_wait(ps_b);
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+  }
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
     const int a = strips[s].x, bnd = strips[s].y;
     if (a >= bnd) continue;
@@ -438,11 +468,16 @@ symv_tma_kernel(const double *__restrict__ S, size_t pitch, int N, int row0, con
     for (int t = tid; t < h; t += CONSUMERS) sm.bstrip[t] = b[a + t];
     asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     double *cp = colpart + (size_t)s * L;
-    SyChunk ch;
-    for (int k = 0; sy_chunk(k, a, bnd, N, H, ch); ++k) {
+    SyChunk ch, nxt;
+    bool have = sy_chunk(0, a, bnd, N, H, ch);
+    double2 bv = make_double2(0.0, 0.0);
+    if (have && 2 * tid < ch.w) bv = *reinterpret_cast<const double2 *>(b + ch.cact + 2 * tid);
+    for (int k = 0; have; ++k) {
       const bool active = 2 * tid < ch.w;
-      double2 bv = make_double2(0.0, 0.0);
-      if (active) bv = *reinterpret_cast<const double2 *>(b + ch.cact + 2 * tid);
+      // b of the next chunk is fetched now so that its L2 latency hides behind this chunk's stages
+      const bool have_next = sy_chunk(k + 1, a, bnd, N, H, nxt);
+      double2 bv_next = make_double2(0.0, 0.0);
+      if (have_next && 2 * tid < nxt.w) bv_next = *reinterpret_cast<const double2 *>(b + nxt.cact + 2 * tid);
       const int cu0 = ch.cb + 2 * tid;  // unwrapped column of this thread's first element
       double col0 = 0.0, col1 = 0.0;
       for (int g = 0; g < ngroups; ++g) {
@@ -528,6 +563,9 @@ symv_tma_kernel(const double *__restrict__ S, size_t pitch, int N, int row0, con
         if (++stage == SY_STAGES) { stage = 0; phase ^= 1; }
       }
       if (active) *reinterpret_cast<double2 *>(cp + ch.joff + 2 * tid) = make_double2(col0, col1);
+      ch = nxt;
+      bv = bv_next;
+      have = have_next;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
     for (int t = tid; t < h; t += CONSUMERS) {
@@ -549,7 +587,7 @@ constexpr int SR_THREADS = 256;
 __global__ void __launch_bounds__(SR_THREADS)
 symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restrict__ strips, int nstrips, int L,
                    const double *__restrict__ rowpart, const double *__restrict__ colpart,
-                   double *__restrict__ out, ChargeEpilogue ep) {
+                   double *__restrict__ out, ChargeEpilogue ep, PeerSync ps, size_t off_parts) {
   __shared__ double sh[SR_THREADS];
   __shared__ double part[SR_THREADS / 32][32];
   __shared__ int flag;
@@ -585,11 +623,16 @@ symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restri
           pz = fma(ep.setz[c], t, pz);
         }
       }
-      out[c] = t;
+      if (ps.arena) {  // this rank's partial sum goes into slot `rank` of every rank's staging area
+        for (int r = 0; r < ps.nranks; ++r) peer_ptr<double>(ps, r, off_parts)[(size_t)ps.rank * out_len + c] = t;
+      } else {
+        out[c] = t;
+      }
     }
     __syncthreads();
   }
   if (ep.enabled) charge_epilogue(ep, pa, pz, threadIdx.x, SR_THREADS, 0, sh, &flag);
+  peer_block_signal(ps);
 }
 
 }  // namespace
@@ -615,7 +658,12 @@ int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int nc
 SymvPlan plan_symv(int N, int row0, int nrows, int num_sms, std::vector<int2> &strips) {
   SymvPlan p;
   strips.clear();
-  if (N < 64 || nrows <= 0) return p;
+  if (N < 64) return p;
+  if (nrows <= 0) {  // a rank without rows still takes part in the exchanges: no strips, zero partial sum
+    p.usable = true;
+    p.L = 2;
+    return p;
+  }
   const int grid = std::min(num_sms, nrows);
   const int nstrips = std::max(grid, (nrows + SY_HMAX - 1) / SY_HMAX);
   const int hmax = (nrows + nstrips - 1) / nstrips;
@@ -633,7 +681,7 @@ SymvPlan plan_symv(int N, int row0, int nrows, int num_sms, std::vector<int2> &s
 
 int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, int nrows, const double *b,
                 const SymvPlan &plan, double *rowpart, double *colpart, double *out, int out_len,
-                const ChargeEpilogue *ep) {
+                const ChargeEpilogue *ep, const PeerSync &wait_b, const PeerSync &push_parts, size_t off_parts) {
   if (!plan.usable || !plan.strips) CONP_THROW(CONP_ERR_STATE, "launch_symv: no plan");
   static bool attr_set = false;
   const size_t smem = sizeof(SySmem);
@@ -641,24 +689,39 @@ int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, 
     CUDA_CHECK(cudaFuncSetAttribute(symv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  symv_tma_kernel<<<plan.grid, THREADS, smem, s>>>(S, pitch, N, row0, plan.strips, plan.nstrips, plan.L, b, rowpart,
-                                                  colpart);
-  CUDA_CHECK(cudaGetLastError());
+  int launched = 1;
+  if (plan.grid > 0) {
+    symv_tma_kernel<<<plan.grid, THREADS, smem, s>>>(S, pitch, N, row0, plan.strips, plan.nstrips, plan.L, b,
+                                                    rowpart, colpart, wait_b);
+    CUDA_CHECK(cudaGetLastError());
+    ++launched;
+  } else if (wait_b.arena) {
+    launched += p2p_wait_sync(wait_b, s);  // nobody here reads b, but the exchange must be consumed
+  }
   ChargeEpilogue e;
   if (ep) e = *ep;
   else memset(&e, 0, sizeof(e));
   int grid = (out_len + 31) / 32;
   grid = grid < 1 ? 1 : (grid > 1024 ? 1024 : grid);  // epilogue partials: 2 per block, 1024 blocks max
   symv_reduce_kernel<<<grid, SR_THREADS, 0, s>>>(N, out_len, row0, nrows, plan.strips, plan.nstrips, plan.L, rowpart,
-                                                 colpart, out, e);
+                                                 colpart, out, e, push_parts, off_parts);
   CUDA_CHECK(cudaGetLastError());
-  return 2;
+  return launched;
 }
 
 int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep) {
   int grid = (ep.n + UC_THREADS * 4 - 1) / (UC_THREADS * 4);
   grid = grid < 1 ? 1 : (grid > 128 ? 128 : grid);
   update_charge_kernel<<<grid, UC_THREADS, 0, s>>>(ep);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_update_charge_sum(cudaStream_t s, const ChargeEpilogue &ep, const PeerSync &ps, const double *parts,
+                             int len, double *sb_out) {
+  int grid = (len + UC_THREADS * 4 - 1) / (UC_THREADS * 4);
+  grid = grid < 1 ? 1 : (grid > 128 ? 128 : grid);
+  update_charge_sum_kernel<<<grid, UC_THREADS, 0, s>>>(ep, ps, parts, len, sb_out);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -92,12 +92,17 @@ __device__ __forceinline__ double wrap_coord(const CellGrid &g, int a, double x)
 // ---------------------------------------------------------------------------
 // per-step counting sort of the point charges
 // ---------------------------------------------------------------------------
-// pack: raw LAMMPS positions -> wrapped PosQ + type, sum(q z), cell histogram
+// pack: raw LAMMPS positions -> wrapped PosQ + type, sum(q z), cell histogram.
+// Several GPUs, peer-to-peer path (ps.arena != nullptr): `packed` is this rank's block of the gathered
+// array; every charge is also stored into the same slot of every peer's array, the last block adds this
+// rank's sum(q z) in the block's last (padding) slot and raises the flags -- the position all-gather
+// happens inside the kernel that produces the positions.
 __global__ void __launch_bounds__(256)
 pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int *__restrict__ idx,
                   const double *__restrict__ q, const int *__restrict__ type, PosQ *__restrict__ packed,
                   int *__restrict__ packed_type, int *__restrict__ cell_of, int *__restrict__ slot,
-                  int *__restrict__ cell_count, double *__restrict__ qz_sum) {
+                  int *__restrict__ cell_count, double *__restrict__ qz_sum, PeerSync ps, size_t off_block,
+                  int mpad) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   double qz = 0.0;
   if (j < m) {
@@ -117,6 +122,9 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
       cell_of[j] = cell;
       slot[j] = atomicAdd(&cell_count[cell], 1);
     }
+    if (ps.arena)
+      for (int r = 0; r < ps.nranks; ++r)
+        if (r != ps.rank) peer_ptr<PosQ>(ps, r, off_block)[j] = p;
   }
   __shared__ double sh[8];
 #pragma unroll
@@ -129,14 +137,25 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
     for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
     if (threadIdx.x == 0 && v != 0.0) atomicAdd(qz_sum, v);
   }
+  peer_block_signal(ps, [&] {
+    if ((int)threadIdx.x < ps.nranks) {
+      const double tot = __ldcg(qz_sum);  // complete: every block added its share before taking its ticket
+      peer_ptr<PosQ>(ps, threadIdx.x, off_block)[mpad - 1].x = tot;
+    }
+  });
 }
 
 // multi-GPU: the gathered charges sit in `nranks` blocks of `mpad` slots; block r holds
-// counts[r] charges, the rest is padding (the last slot carries that rank's sum(q z))
+// counts[r] charges, the rest is padding (the last slot carries that rank's sum(q z)).  With the fused
+// exchange (ps.arena != nullptr) the kernel first waits for every rank's block to have landed.
 __global__ void __launch_bounds__(256)
 bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts,
                      const PosQ *__restrict__ packed, int *__restrict__ cell_of, int *__restrict__ slot,
-                     int *__restrict__ cell_count) {
+                     int *__restrict__ cell_count, PeerSync ps) {
+  if (ps.arena) {
+    peer_block_wait(ps);
+    __syncthreads();
+  }
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   if (j % mpad >= counts[j / mpad]) {
@@ -149,13 +168,17 @@ bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts
   slot[j] = atomicAdd(&cell_count[cell], 1);
 }
 
-// exclusive scan of cell_count -> cell_start[ncells+1] by one block: every thread sums a
-// contiguous chunk of the histogram (int4 loads, all in flight at once), one block-wide scan of the
-// 1024 chunk totals, then the chunk is walked again to write the prefixes (cell_count is padded
-// with zeros to a multiple of 4 and both arrays are 16-byte aligned)
+// exclusive scan of cell_count -> cell_start[ncells+1] by one block (cell_count is padded with zeros
+// to a multiple of 4 and both arrays are 16-byte aligned).  SMEM: the whole histogram is first staged
+// in shared memory with coalesced int4 loads that are all in flight at once, each thread then scans
+// a contiguous chunk out of shared memory (odd chunk length in words: conflict-free), and the
+// result leaves with coalesced stores -- a few microseconds for ~50k cells.  Histograms that do not
+// fit take the same steps straight from global memory.
+template <bool SMEM>
 __global__ void __launch_bounds__(1024, 1)
 cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict__ cell_start,
                  const PosQ *__restrict__ packed, int mpad, int nranks, double *__restrict__ qz_sum) {
+  extern __shared__ __align__(16) int hist[];
   __shared__ int wsum[32];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (qz_sum && t == 0) {  // multi-GPU: sum(q z) partials ride in the last slot of every rank's block
@@ -163,14 +186,28 @@ cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict
     for (int r = 0; r < nranks; ++r) v += packed[(size_t)r * mpad + mpad - 1].x;
     *qz_sum = v;
   }
-  const int nvec = (ncells + 3) >> 2;            // int4 groups in the histogram
-  const int per = (nvec + 1023) >> 10;           // groups per thread
-  const int v0 = t * per, v1 = min(v0 + per, nvec);
-  const int4 *cnt4 = reinterpret_cast<const int4 *>(cell_count);
+  const int nvec = (ncells + 3) >> 2;  // int4 groups in the histogram
+  int per, i0, i1;
   int tsum = 0;
-  for (int v = v0; v < v1; ++v) {
-    const int4 c = cnt4[v];
-    tsum += (c.x + c.y) + (c.z + c.w);
+  if (SMEM) {
+    const int4 *cnt4 = reinterpret_cast<const int4 *>(cell_count);
+    int4 *h4 = reinterpret_cast<int4 *>(hist);
+#pragma unroll 4
+    for (int v = t; v < nvec; v += 1024) h4[v] = cnt4[v];
+    __syncthreads();
+    per = ((4 * nvec + 1023) >> 10) | 1;  // words per thread, odd
+    i0 = min(t * per, 4 * nvec);
+    i1 = min(i0 + per, 4 * nvec);
+    for (int i = i0; i < i1; ++i) tsum += hist[i];
+  } else {
+    per = (nvec + 1023) >> 10;  // int4 groups per thread
+    i0 = min(t * per, nvec);
+    i1 = min(i0 + per, nvec);
+    const int4 *cnt4 = reinterpret_cast<const int4 *>(cell_count);
+    for (int v = i0; v < i1; ++v) {
+      const int4 c = cnt4[v];
+      tsum += (c.x + c.y) + (c.z + c.w);
+    }
   }
   int incl = tsum;
 #pragma unroll
@@ -193,19 +230,30 @@ cell_scan_kernel(int ncells, const int *__restrict__ cell_count, int *__restrict
   }
   __syncthreads();
   int run = wsum[warp] + incl - tsum;
-  int4 *out4 = reinterpret_cast<int4 *>(cell_start);
-  for (int v = v0; v < v1; ++v) {
-    const int4 c = cnt4[v];
-    const int idx = 4 * v;
-    const int4 o = make_int4(run, run + c.x, run + c.x + c.y, run + c.x + c.y + c.z);
-    if (idx + 3 < ncells) {
-      out4[v] = o;
-    } else {  // tail group: cell_start[ncells] belongs to the grand total
-      cell_start[idx] = o.x;
-      if (idx + 1 < ncells) cell_start[idx + 1] = o.y;
-      if (idx + 2 < ncells) cell_start[idx + 2] = o.z;
+  if (SMEM) {
+    for (int i = i0; i < i1; ++i) {  // in place: count -> exclusive prefix
+      const int c = hist[i];
+      hist[i] = run;
+      run += c;
     }
-    run = o.w + c.w;
+    __syncthreads();
+    for (int i = t; i < ncells; i += 1024) cell_start[i] = hist[i];
+  } else {
+    const int4 *cnt4 = reinterpret_cast<const int4 *>(cell_count);
+    int4 *out4 = reinterpret_cast<int4 *>(cell_start);
+    for (int v = i0; v < i1; ++v) {
+      const int4 c = cnt4[v];
+      const int idx = 4 * v;
+      const int4 o = make_int4(run, run + c.x, run + c.x + c.y, run + c.x + c.y + c.z);
+      if (idx + 3 < ncells) {
+        out4[v] = o;
+      } else {  // tail group: cell_start[ncells] belongs to the grand total
+        cell_start[idx] = o.x;
+        if (idx + 1 < ncells) cell_start[idx + 1] = o.y;
+        if (idx + 2 < ncells) cell_start[idx + 2] = o.z;
+      }
+      run = o.w + c.w;
+    }
   }
 }
 
@@ -646,25 +694,38 @@ void build_near_mask(const CellGrid &g, int begin, int end, const double *xyz, s
 
 int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx,
                       const double *q, const int *type, PosQ *packed, int *packed_type, int *cell_of, int *slot,
-                      int *cell_count, double *qz_sum) {
-  if (m <= 0) return 0;
-  pack_count_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, x_raw, idx, q, type, packed, packed_type, cell_of, slot,
-                                                    cell_count, qz_sum);
+                      int *cell_count, double *qz_sum, const PeerSync &ps, size_t off_block, int mpad) {
+  if (m <= 0 && !ps.arena) return 0;
+  // with the fused exchange a rank without charges still signals: one (idle) block
+  pack_count_kernel<<<std::max((m + 255) / 256, 1), 256, 0, s>>>(g, m, x_raw, idx, q, type, packed, packed_type,
+                                                                 cell_of, slot, cell_count, qz_sum, ps, off_block, mpad);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
 int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, int mpad, const int *counts,
-                         const PosQ *packed, int *cell_of, int *slot, int *cell_count) {
-  if (m <= 0) return 0;
-  bin_positions_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, mpad, counts, packed, cell_of, slot, cell_count);
+                         const PosQ *packed, int *cell_of, int *slot, int *cell_count, const PeerSync &ps) {
+  if (m <= 0 && !ps.arena) return 0;
+  bin_positions_kernel<<<std::max((m + 255) / 256, 1), 256, 0, s>>>(g, m, mpad, counts, packed, cell_of, slot,
+                                                                    cell_count, ps);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
 int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start, const PosQ *packed,
                      int mpad, int nranks, double *qz_sum) {
-  cell_scan_kernel<<<1, 1024, 0, s>>>(ncells, cell_count, cell_start, packed, mpad, nranks, qz_sum);
+  const size_t smem = sizeof(int) * 4 * (size_t)((ncells + 3) / 4);
+  if (smem <= 200 * 1024) {
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(cell_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+      smem_set = 200 * 1024;
+    }
+    cell_scan_kernel<true><<<1, 1024, smem, s>>>(ncells, cell_count, cell_start, packed, mpad, nranks, qz_sum);
+  } else {
+    cell_scan_kernel<false><<<1, 1024, 0, s>>>(ncells, cell_count, cell_start, packed, mpad, nranks, qz_sum);
+  }
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -25,11 +25,15 @@
 // The 2-D FFTs are cuFFT (library); everything else is hand-written.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstring>
+
 namespace conp {
 
 namespace {
 
 constexpr int OFFSET = 16384;  // pppm_conp.cpp:32
+constexpr int SPREAD_BLOCKS_PER_SM = 0;  // 0: no cap (see launch_pppm_spread)
 constexpr int MAXORDER = 7;    // LAMMPS PPPM MAXORDER
 
 __device__ __forceinline__ int wrapi(int m, int n) {
@@ -102,17 +106,26 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
   }
 }
 
-// z-convolution with the tabulated kernel.  A block owns `cols` consecutive
-// (kx,ky) columns (cols*16 B of every plane of the plane-major spectra).  It
-// stages rho^ of those columns (all input planes) and their kernel rows K[d]
-// in shared memory with coalesced loads, then each thread owns one (column,
-// output plane) pair and runs its window out of shared memory.
-// For k_xy != 0 the kernel decays like the Ewald Gaussian / exp(-|k_xy| |dz|):
-// krad[col] bounds the circular |d| beyond which |K| is below ~1e-18 of the
-// column maximum (measured on the table at setup, see ctx.cu), and only input
-// planes inside that window are visited; the dropped tail is below the
-// rounding level of the reference's own FFTs.
+// z-convolution with the tabulated kernel, one launch for all (kx,ky) columns.
+//
+// For k_xy != 0 the kernel decays like the Ewald Gaussian / exp(-|k_xy| |dz|): krad[col] bounds the
+// circular |d| beyond which |K| is below ~1e-18 of the column maximum (measured on the table at
+// setup, see ctx.cu); the dropped tail is below the rounding level of the reference's own FFTs.
+// The output planes sit in thin groups at the electrodes, so a column only needs the input planes
+// within its radius of an output plane.
+//
+//  * "Narrow" blocks own ZC_COLS = 8 consecutive columns (128 B of every plane of the plane-major
+//    spectra).  The host has worked out which planes of this rank's slab the group's window touches
+//    (ZconvGroup: a few intervals, compacted row numbers); the block stages those planes of rho^ and
+//    the 2 rblock + 1 table entries K[-rblock .. rblock] with cp.async (everything in flight at
+//    once), then each thread owns one (column, output plane) pair and runs its window out of
+//    shared memory, ascending input plane.  ~15 KB per block: several blocks per SM, so the loads of
+//    one hide behind the sums of another.
+//  * "Wide" blocks take one of the few small-|k_xy| columns whose kernel reaches across the whole
+//    mesh: each warp owns output planes, its lanes stride over all slab planes straight from L2 and
+//    the partial sums are combined with a fixed shuffle tree.
 constexpr int ZC_THREADS = 256;
+constexpr int ZC_COLS = 8;
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
@@ -122,150 +135,72 @@ __device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
 
 template <bool REALK>
 __global__ void __launch_bounds__(ZC_THREADS)
-zconv_kernel(int ncol, int cols, int nz, int nzl, int zs_lo, int zin_lo, int nzo, const int *__restrict__ zout_list,
-             const int *__restrict__ krad, const int *__restrict__ blocks, const double2 *__restrict__ rhat,
+zconv_kernel(int ncol, int nz, int nzl, int zs_lo, int nzo, const int *__restrict__ aout,
+             const int *__restrict__ krad, const ZconvGroup *__restrict__ groups, int n_narrow,
+             const int *__restrict__ wide_cols, int rcap, int npcap, const double2 *__restrict__ rhat,
              const double *__restrict__ Kr, const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
   // rhat: spectra of this rank's nzl input planes (compact planes zs_lo .. zs_lo+nzl-1); on several
-  // GPUs uhat is this rank's partial sum and is all-reduced afterwards
-  extern __shared__ __align__(16) unsigned char zc_smem[];
-  double2 *rh = reinterpret_cast<double2 *>(zc_smem);  // [nzl][cols]
-  const int kstride = REALK ? (nz | 1) : nz;            // odd row pitch: conflict-free across columns
-  double *ksr = reinterpret_cast<double *>(rh + (size_t)nzl * cols);  // REALK: [cols][kstride]
-  double2 *ksc = reinterpret_cast<double2 *>(ksr);                     // else:  [cols][nz]
-  __shared__ int s_rblock;
-  const int c0 = blocks[blockIdx.x] * cols;
-  if (threadIdx.x == 0) {
-    int r = 0;
-    for (int cc = 0; cc < cols; ++cc) r = max(r, krad[min(c0 + cc, ncol - 1)]);
-    s_rblock = r;
-  }
-  __syncthreads();
-  const int rblock = s_rblock;
-  const bool all = 2 * rblock + 1 >= nz;
-  // staging with cp.async: every load of the block is in flight at once (the kernel is latency-bound
-  // otherwise).  Only the table entries inside the block's largest window are fetched.
-  for (int idx = threadIdx.x; idx < nzl * cols; idx += blockDim.x) {
-    const int t = idx / cols, cc = idx - t * cols;
-    cp_async<16>(&rh[idx], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
-  }
-  for (int cc = 0; cc < cols; ++cc) {
-    const int c = min(c0 + cc, ncol - 1);
-    if (REALK) {
-      const double *src = Kr + (size_t)c * nz;
-      for (int d = threadIdx.x; d < nz; d += blockDim.x)
-        if (all || min(d, nz - d) <= rblock) cp_async<8>(&ksr[cc * kstride + d], src + d);
-    } else {
-      const double2 *src = Kc + (size_t)c * nz;
-      for (int d = threadIdx.x; d < nz; d += blockDim.x)
-        if (all || min(d, nz - d) <= rblock) cp_async<16>(&ksc[cc * kstride + d], src + d);
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-  for (int item = threadIdx.x; item < cols * nzo; item += blockDim.x) {
-    const int zo = item / cols, cc = item - zo * cols;
-    const int c = c0 + cc;
-    if (c >= ncol) continue;
+  // GPUs uhat is this rank's partial sum and is all-reduced afterwards.  aout[zo] = position of output
+  // plane zo on the ring in compact input-plane coordinates.
+  if ((int)blockIdx.x >= n_narrow) {
+    // ---------------- wide column ----------------
+    const int c = wide_cols[blockIdx.x - n_narrow];
     const int R = krad[c];
-    // a = position of the output plane on the ring, in compact input-plane coordinates
-    int a = (zout_list[zo] - zin_lo) % nz;
-    if (a < 0) a += nz;
-    double ar = 0.0, ai = 0.0;
-    // compact input planes z0..z1 (inclusive), clipped to this rank's slab; table index d = (a - zi) mod nz
-    auto run = [&](int z0, int z1) {
-      z0 = max(z0, zs_lo);
-      z1 = min(z1, zs_lo + nzl - 1);
-      int d = a - z0;
-      d += (d < 0) ? nz : 0;
-      d -= (d >= nz) ? nz : 0;
-      for (int zi = z0; zi <= z1; ++zi) {
-        const double2 r = rh[(zi - zs_lo) * cols + cc];
-        if (REALK) {
-          const double k = ksr[cc * kstride + d];
-          ar = fma(k, r.x, ar);
-          ai = fma(k, r.y, ai);
-        } else {
-          const double2 k = ksc[cc * kstride + d];
-          ar = fma(k.x, r.x, ar); ar = fma(-k.y, r.y, ar);
-          ai = fma(k.x, r.y, ai); ai = fma(k.y, r.x, ai);
+    const bool all = 2 * R + 1 >= nz;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int zo = warp; zo < nzo; zo += ZC_THREADS / 32) {
+      const int a = aout[zo];
+      double ar = 0.0, ai = 0.0;
+      for (int t = lane; t < nzl; t += 32) {
+        int d = a - (zs_lo + t);
+        d += (d < 0) ? nz : 0;  // table index (a - zi) mod nz
+        if (all || min(d, nz - d) <= R) {
+          const double2 r = rhat[(size_t)t * ncol + c];
+          if (REALK) {
+            const double k = Kr[(size_t)c * nz + d];
+            ar = fma(k, r.x, ar);
+            ai = fma(k, r.y, ai);
+          } else {
+            const double2 k = Kc[(size_t)c * nz + d];
+            ar = fma(k.x, r.x, ar); ar = fma(-k.y, r.y, ar);
+            ai = fma(k.x, r.y, ai); ai = fma(k.y, r.x, ai);
+          }
         }
-        d = d ? d - 1 : nz - 1;
       }
-    };
-    if (2 * R + 1 >= nz) {
-      run(0, nz - 1);
-    } else {
-      run(a - R, a + R);                        // main window
-      if (a - R < 0) run(a - R + nz, nz - 1);   // wrapped from below
-      if (a + R >= nz) run(0, a + R - nz);      // wrapped from above
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ar += __shfl_xor_sync(0xffffffffu, ar, o);
+        ai += __shfl_xor_sync(0xffffffffu, ai, o);
+      }
+      if (lane == 0) uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
     }
-    uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
+    return;
   }
-}
-
-// Narrow variant: for most (kx,ky) the kernel K(d) is negligible beyond a few tens of planes, and
-// the output planes sit in two thin groups at the electrodes, so only the input planes within the
-// block's window of an output plane are staged -- compacted in shared memory through `rowof` --
-// together with the 2 rblock + 1 table entries K[-rblock .. rblock].  The block needs ~15 KB instead
-// of the whole column, several blocks share an SM and the loads of one hide behind the sums of
-// another.  Summation order per output is the same as in zconv_kernel (ascending input plane).
-constexpr int ZC_COLS = 8;
-
-template <bool REALK>
-__global__ void __launch_bounds__(ZC_THREADS)
-zconv_narrow_kernel(int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo, const int *__restrict__ zout_list,
-                    const int *__restrict__ krad, const int *__restrict__ groups, int rcap, int npcap,
-                    const double2 *__restrict__ rhat, const double *__restrict__ Kr,
-                    const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
+  // ---------------- narrow group ----------------
   extern __shared__ __align__(16) unsigned char zc_smem[];
-  double2 *rh = reinterpret_cast<double2 *>(zc_smem);                   // [npcap][ZC_COLS]
+  double2 *rh = reinterpret_cast<double2 *>(zc_smem);                      // [npcap][ZC_COLS]
   const int kst = 2 * rcap + 1;
   double *ksr = reinterpret_cast<double *>(rh + (size_t)npcap * ZC_COLS);  // REALK: [ZC_COLS][kst]
   double2 *ksc = reinterpret_cast<double2 *>(ksr);                          // else:  [ZC_COLS][kst]
-  int *rowof = reinterpret_cast<int *>(zc_smem + sizeof(double2) * (size_t)npcap * ZC_COLS +
-                                       (REALK ? sizeof(double) : sizeof(double2)) * (size_t)ZC_COLS * kst);
-  __shared__ int s_rblock, s_wcount[ZC_THREADS / 32], s_base;
-  const int c0 = groups[blockIdx.x] * ZC_COLS;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    int r = 0;
-    for (int cc = 0; cc < ZC_COLS; ++cc) r = max(r, krad[min(c0 + cc, ncol - 1)]);
-    s_rblock = r;
-    s_base = 0;
-  }
+  __shared__ ZconvGroup gd;
+  if (threadIdx.x < sizeof(ZconvGroup) / sizeof(int))
+    reinterpret_cast<int *>(&gd)[threadIdx.x] = reinterpret_cast<const int *>(groups + blockIdx.x)[threadIdx.x];
   __syncthreads();
-  const int rblock = s_rblock;
-  // which planes of the slab lie within rblock (on the ring) of an output plane; rowof = compact row
-  for (int t0 = 0; t0 < nzl; t0 += ZC_THREADS) {
-    const int t = t0 + threadIdx.x;
-    bool needed = false;
-    if (t < nzl) {
-      const int zi = zs_lo + t;
-      for (int zo = 0; zo < nzo && !needed; ++zo) {
-        int a = (zout_list[zo] - zin_lo) % nz;
-        if (a < 0) a += nz;
-        const int d = abs(a - zi);
-        needed = min(d, nz - d) <= rblock;
-      }
+  const int c0 = gd.c0, rblock = gd.rblock;
+  // compact row of slab plane t (t must lie in one of the group's intervals)
+  auto rowof = [&](int t) {
+    int row = 0;
+#pragma unroll
+    for (int i = 0; i < ZconvGroup::MAXI; ++i)
+      if (i < gd.nint && t >= gd.lo[i] && t < gd.hi[i]) row = gd.base[i] + t - gd.lo[i];
+    return row;
+  };
+  for (int i = 0; i < gd.nint; ++i) {
+    const int n = (gd.hi[i] - gd.lo[i]) * ZC_COLS;
+    for (int idx = threadIdx.x; idx < n; idx += ZC_THREADS) {
+      const int t = gd.lo[i] + idx / ZC_COLS, cc = idx % ZC_COLS;
+      cp_async<16>(&rh[(gd.base[i] + t - gd.lo[i]) * ZC_COLS + cc], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, needed);
-    if (lane == 0) s_wcount[warp] = __popc(m);
-    __syncthreads();
-    int before = s_base;
-    for (int w = 0; w < warp; ++w) before += s_wcount[w];
-    if (t < nzl) rowof[t] = needed ? before + __popc(m & ((1u << lane) - 1u)) : -1;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w = 0; w < ZC_THREADS / 32; ++w) tot += s_wcount[w];
-      s_base += tot;
-    }
-    __syncthreads();
-  }
-  for (int idx = threadIdx.x; idx < nzl * ZC_COLS; idx += ZC_THREADS) {
-    const int t = idx / ZC_COLS, cc = idx - t * ZC_COLS;
-    const int row = rowof[t];
-    if (row >= 0) cp_async<16>(&rh[row * ZC_COLS + cc], &rhat[(size_t)t * ncol + min(c0 + cc, ncol - 1)]);
   }
   for (int idx = threadIdx.x; idx < ZC_COLS * (2 * rblock + 1); idx += ZC_THREADS) {
     const int cc = idx / (2 * rblock + 1), j = idx - cc * (2 * rblock + 1);
@@ -284,15 +219,14 @@ zconv_narrow_kernel(int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo, c
     const int c = c0 + cc;
     if (c >= ncol) continue;
     const int R = krad[c];
-    int a = (zout_list[zo] - zin_lo) % nz;
-    if (a < 0) a += nz;
+    const int a = aout[zo];
     double ar = 0.0, ai = 0.0;
     // input planes z0..z1 clipped to the slab; signed distance of plane zi is a - zi + shift
     auto run = [&](int z0, int z1, int shift) {
       z0 = max(z0, zs_lo);
       z1 = min(z1, zs_lo + nzl - 1);
       if (z0 > z1) return;
-      int row = rowof[z0 - zs_lo];           // the planes of one run are consecutive compact rows
+      int row = rowof(z0 - zs_lo);  // the planes of one run are consecutive compact rows
       int j = a - z0 + shift + rblock;
       for (int zi = z0; zi <= z1; ++zi, ++row, --j) {
         const double2 r = rh[row * ZC_COLS + cc];
@@ -389,28 +323,35 @@ ele_point_table_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, cons
 }
 
 // one warp per electrode row: b_k = -sum w u (pppm_conp.cpp:285-298), slab
-// term (:301-313), then b = b_k + b_real
+// term (:301-313), then b = b_k + b_real.  On several GPUs (peer-to-peer path) the kernel is its own
+// b_comm (fix_conp.cpp:641-648): the row's b goes straight into every peer's copy of the vector and
+// the last block raises the flags the matvec kernel polls.
 __global__ void __launch_bounds__(256)
 gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ poff,
                 const double *__restrict__ pw, const double *__restrict__ u_brick,
                 const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
-                const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b) {
+                const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b,
+                PeerSync ps, size_t off_b) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i >= row_end) return;
-  const int npts = g.order * g.order * g.order;
-  const int *po = poff + (size_t)i * npts;
-  const double *w = pw + (size_t)i * npts;
-  double acc = 0.0;
-  for (int t = lane; t < npts; t += 32) acc = fma(w[t], u_brick[po[t]], acc);
+  if (i < row_end) {
+    const int npts = g.order * g.order * g.order;
+    const int *po = poff + (size_t)i * npts;
+    const double *w = pw + (size_t)i * npts;
+    double acc = 0.0;
+    for (int t = lane; t < npts; t += 32) acc = fma(w[t], u_brick[po[t]], acc);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     double bk = -acc;
     if (slab_pref != 0.0) bk -= ez[i] * (slab_pref * qz_sum[0]);
-    b_kspace[i] = bk;
-    b[i] = bk + b_real[i];
+    const double bi = bk + b_real[i];
+    if (lane == 0) {
+      b_kspace[i] = bk;
+      b[i] = bi;
+    }
+    if (ps.arena && lane < ps.nranks && lane != ps.rank) peer_ptr<double>(ps, lane, off_b)[i] = bi;
   }
+  peer_block_signal(ps);
 }
 
 // electrode re-spread with the cached weights; one thread per (atom, n, m) row.
@@ -456,7 +397,20 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
   if (m_bound <= 0 || g.zs_n <= 0) return 0;
   const long long threads = (long long)m_bound * g.order * g.order;
   const unsigned grid = (unsigned)((threads + 255) / 256);
-  spread_kernel<<<grid, 256, 0, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, brick, range_flag);
+  // The kernel is bound by the SM's red.global issue rate, not by occupancy.  Asking for a slice of
+  // (unused) dynamic shared memory caps it at SPREAD_BLOCKS_PER_SM blocks per SM, which leaves
+  // registers and warp slots for the real-space pair kernel that runs beside it on the side stream.
+  static int per_sm = -1;
+  static size_t smem = 0;
+  if (per_sm < 0) {
+    const char *e = getenv("CONP_SPREAD_BLOCKS_PER_SM");
+    per_sm = e ? atoi(e) : SPREAD_BLOCKS_PER_SM;
+    if (per_sm > 0 && per_sm < 8) {
+      smem = ((size_t)(227 * 1024) / per_sm - 1024) & ~(size_t)127;
+      CUDA_CHECK(cudaFuncSetAttribute(spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+  }
+  spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, brick, range_flag);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -468,40 +422,30 @@ int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, co
 }
 
 namespace {
-size_t zc_narrow_smem(int npcap, int rcap, int nzl, bool real_k) {
+size_t zc_narrow_smem(int npcap, int rcap, bool real_k) {
   return sizeof(double2) * (size_t)npcap * ZC_COLS +
-         (real_k ? sizeof(double) : sizeof(double2)) * (size_t)ZC_COLS * (2 * rcap + 1) + sizeof(int) * (size_t)nzl;
-}
-int zc_wide_cols(int nz, int nzl, bool real_k, size_t *smem_out) {
-  // widest column group whose rho^ + K rows fit in shared memory
-  const size_t kbytes = real_k ? sizeof(double) * (size_t)(nz | 1) : sizeof(double2) * (size_t)nz;
-  for (int cols = 8; cols >= 1; cols >>= 1) {
-    const size_t smem = (sizeof(double2) * (size_t)nzl + kbytes) * cols;
-    if (smem <= 200 * 1024) {
-      if (smem_out) *smem_out = smem;
-      return cols;
-    }
-  }
-  return 0;
+         (real_k ? sizeof(double) : sizeof(double2)) * (size_t)ZC_COLS * (2 * rcap + 1);
 }
 }  // namespace
 
-// Split the column groups between the two kernels.  The narrow kernel is sized for the largest window
-// radius whose staging still fits ZC_NARROW_SMEM; np(R) = planes of [0, nzi) within R of an output plane.
-void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, int nzl, int zin_lo,
-                     const std::vector<int> &zout, bool real_k, std::vector<int> &narrow, std::vector<int> &wide,
-                     ZconvPlan &plan) {
+// Split the column groups between the narrow and the wide path and describe, for every narrow
+// group, which planes of this rank's slab [zs_lo, zs_lo + nzl) it stages.  The narrow path is sized for
+// the largest window radius whose staging still fits ZC_NARROW_SMEM; np(R) = planes of [0, nzi)
+// within R (on the ring) of an output plane.
+void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, int zs_lo, int nzl, int zin_lo,
+                     const std::vector<int> &zout, bool real_k, std::vector<ZconvGroup> &narrow,
+                     std::vector<int> &wide, std::vector<int> &aout, ZconvPlan &plan) {
   constexpr size_t ZC_NARROW_SMEM = 44 * 1024;
   narrow.clear();
   wide.clear();
+  aout.clear();
   plan = ZconvPlan();
-  plan.cols_w = zc_wide_cols(nz, std::max(nzl, 1), real_k, nullptr);
-  if (plan.cols_w < 1) CONP_THROW(CONP_ERR_ARG, "PPPM mesh too deep in z for the z-convolution kernel (nz = %d)", nz);
   // distance of every input plane to the nearest output plane (on the ring)
   std::vector<int> dist(std::max(nzi, 1), nz);
   for (int zo : zout) {
     int a = (zo - zin_lo) % nz;
     if (a < 0) a += nz;
+    aout.push_back(a);
     for (int zi = 0; zi < nzi; ++zi) {
       const int d = std::abs(a - zi);
       dist[zi] = std::min(dist[zi], std::min(d, nz - d));
@@ -512,79 +456,74 @@ void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, in
   for (int r = 1; r <= nz; ++r) npof[r] += npof[r - 1];
   int rcap = -1;
   for (int r = 0; 2 * r + 1 < nz; ++r) {
-    if (zc_narrow_smem(npof[r], r, std::max(nzl, 1), real_k) > ZC_NARROW_SMEM) break;
+    if (zc_narrow_smem(npof[r], r, real_k) > ZC_NARROW_SMEM) break;
     rcap = r;
   }
   const int ngroups = (ncol + ZC_COLS - 1) / ZC_COLS;
+  int npmax = 1;
   for (int gi = 0; gi < ngroups; ++gi) {
     int rb = 0;
     for (int cc = 0; cc < ZC_COLS; ++cc) rb = std::max(rb, krad[std::min(gi * ZC_COLS + cc, ncol - 1)]);
-    if (rb <= rcap) {
-      narrow.push_back(gi);
+    ZconvGroup g;
+    std::memset(&g, 0, sizeof(g));
+    g.c0 = gi * ZC_COLS;
+    g.rblock = rb;
+    bool ok = rb <= rcap;
+    if (ok) {  // intervals of slab planes within rb of an output plane
+      int t = 0;
+      while (t < nzl && ok) {
+        if (dist[zs_lo + t] > rb) { ++t; continue; }
+        int e = t;
+        while (e < nzl && dist[zs_lo + e] <= rb) ++e;
+        if (g.nint == ZconvGroup::MAXI) { ok = false; break; }
+        g.lo[g.nint] = t;
+        g.hi[g.nint] = e;
+        g.base[g.nint] = g.np;
+        g.np += e - t;
+        ++g.nint;
+        t = e;
+      }
+    }
+    if (ok) {
+      narrow.push_back(g);
+      npmax = std::max(npmax, g.np);
     } else {
-      const int per = ZC_COLS / plan.cols_w;
-      for (int i = 0; i < per; ++i)
-        if ((gi * per + i) * plan.cols_w < ncol) wide.push_back(gi * per + i);
+      for (int cc = 0; cc < ZC_COLS && gi * ZC_COLS + cc < ncol; ++cc) wide.push_back(gi * ZC_COLS + cc);
     }
   }
   plan.n_narrow = (int)narrow.size();
   plan.n_wide = (int)wide.size();
   plan.rcap = std::max(rcap, 0);
-  plan.npcap = rcap >= 0 ? std::max(npof[rcap], 1) : 1;
+  plan.npcap = npmax;
 }
 
-int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int zin_lo, int nzo,
-                      const int *zout_list, const int *krad, const ZconvPlan &plan, const cufftDoubleComplex *rhat,
-                      const double *Kr, const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
-  int launched = 0;
-  static size_t smem_set_r = 0, smem_set_c = 0, nsmem_set_r = 0, nsmem_set_c = 0;
-  if (plan.n_wide > 0) {
-    size_t smem = 0;
-    const int cols = zc_wide_cols(nz, std::max(nzl, 1), Kr != nullptr, &smem);
-    if (cols != plan.cols_w) CONP_THROW(CONP_ERR_STATE, "z-convolution plan is stale (cols %d vs %d)", cols, plan.cols_w);
-    if (Kr) {
-      if (smem > smem_set_r) {
-        CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set_r = smem;
-      }
-      zconv_kernel<true><<<plan.n_wide, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad,
-                                                               plan.wide, (const double2 *)rhat, Kr, nullptr,
-                                                               (double2 *)uhat);
-    } else {
-      if (smem > smem_set_c) {
-        CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set_c = smem;
-      }
-      zconv_kernel<false><<<plan.n_wide, ZC_THREADS, smem, s>>>(ncol, cols, nz, nzl, zs_lo, zin_lo, nzo, zout_list,
-                                                                krad, plan.wide, (const double2 *)rhat, nullptr,
-                                                                (const double2 *)Kc, (double2 *)uhat);
+int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int nzo, const int *krad,
+                      const ZconvPlan &plan, const cufftDoubleComplex *rhat, const double *Kr,
+                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
+  const int grid = plan.n_narrow + plan.n_wide;
+  if (grid <= 0) return 0;
+  static size_t smem_set_r = 0, smem_set_c = 0;
+  const size_t smem = zc_narrow_smem(plan.npcap, plan.rcap, Kr != nullptr);
+  if (Kr) {
+    if (smem > smem_set_r) {
+      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set_r = smem;
     }
-    CUDA_CHECK(cudaGetLastError());
-    ++launched;
-  }
-  if (plan.n_narrow > 0) {
-    const size_t smem = zc_narrow_smem(plan.npcap, plan.rcap, std::max(nzl, 1), Kr != nullptr);
-    if (Kr) {
-      if (smem > nsmem_set_r) {
-        CUDA_CHECK(cudaFuncSetAttribute(zconv_narrow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nsmem_set_r = smem;
-      }
-      zconv_narrow_kernel<true><<<plan.n_narrow, ZC_THREADS, smem, s>>>(
-          ncol, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad, plan.narrow, plan.rcap, plan.npcap,
-          (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
-    } else {
-      if (smem > nsmem_set_c) {
-        CUDA_CHECK(cudaFuncSetAttribute(zconv_narrow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nsmem_set_c = smem;
-      }
-      zconv_narrow_kernel<false><<<plan.n_narrow, ZC_THREADS, smem, s>>>(
-          ncol, nz, nzl, zs_lo, zin_lo, nzo, zout_list, krad, plan.narrow, plan.rcap, plan.npcap,
-          (const double2 *)rhat, nullptr, (const double2 *)Kc, (double2 *)uhat);
+    zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, nz, nzl, zs_lo, nzo, plan.aout, krad, plan.narrow,
+                                                      plan.n_narrow, plan.wide, plan.rcap, plan.npcap,
+                                                      (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
+  } else {
+    if (smem > smem_set_c) {
+      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set_c = smem;
     }
-    CUDA_CHECK(cudaGetLastError());
-    ++launched;
+    zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, nz, nzl, zs_lo, nzo, plan.aout, krad, plan.narrow,
+                                                       plan.n_narrow, plan.wide, plan.rcap, plan.npcap,
+                                                       (const double2 *)rhat, nullptr, (const double2 *)Kc,
+                                                       (double2 *)uhat);
   }
-  return launched;
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
 }
 
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
@@ -621,11 +560,13 @@ int launch_pppm_point_table(cudaStream_t s, const PPPMGeom &g, int n, const int 
 
 int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int row_end, const int *poff,
                          const double *pw, const double *u_brick, const double *ez, const double *qz_sum,
-                         double slab_pref, const double *b_real, double *b_kspace, double *b) {
+                         double slab_pref, const double *b_real, double *b_kspace, double *b, const PeerSync &ps,
+                         size_t off_b) {
   const int n = row_end - row_begin;
-  if (n <= 0) return 0;
-  gather_b_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez, qz_sum,
-                                              slab_pref, b_real, b_kspace, b);
+  if (n <= 0 && !ps.arena) return 0;
+  // a rank without rows still takes part in the exchange: one block that only signals
+  gather_b_kernel<<<std::max((n + 7) / 8, 1), 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez, qz_sum,
+                                                           slab_pref, b_real, b_kspace, b, ps, off_b);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
