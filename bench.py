@@ -66,7 +66,8 @@ def make_case(name, kspace):
 
 
 # measured DRAM bytes per launch (ncu --set full, profiles/): (workload, kernel) -> read + written
-TRAFFIC = {("cfg5", "gemv"): 12.801121e9 + 6.872832e6, ("cfg4", "gemv"): 800.11392e6 + 3.297536e6}
+TRAFFIC = {("cfg5", "gemv"): 12.801121e9 + 6.872832e6, ("cfg4", "gemv"): 800.11392e6 + 3.297536e6,
+           ("cfg5", "symv"): 6.615392e9 + 13.343488e6, ("cfg4", "symv"): 406.715392e6 + 5.890816e6}
 
 DEFAULT_WORKLOAD = "cfg5"  # BASELINE configs[4]: the configuration the 1/2/4/8-GPU metric is quoted on; fits one GPU
 

@@ -238,6 +238,34 @@ p2p_reduce_bcast_kernel(char *const *__restrict__ arena, int rank, int nranks, s
   }
 }
 
+// Pull variant of the all-reduce for a vector whose producer kernel has already raised the flags of
+// `ps_ready` on every peer (peer_block_signal in its tail): I own slice `rank`; wait for everybody's
+// partial, read the slice from every rank's copy of the vector (mine locally, the others over NVLink,
+// in rank order so that the sum is deterministic), and store the total into every rank's vector.  One
+// kernel and one flag round instead of scatter + wait + reduce.
+__global__ void __launch_bounds__(256)
+p2p_pull_reduce_bcast_kernel(PeerSync ps_ready, PeerSync ps_done, size_t off, size_t n, size_t slice) {
+  peer_block_wait(ps_ready);
+  __syncthreads();
+  const int rank = ps_ready.rank, nranks = ps_ready.nranks;
+  const size_t lo = (size_t)rank * slice;
+  const size_t cnt = lo < n ? (n - lo < slice ? n - lo : slice) : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x) {
+    double part[P2P_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+      if (r < nranks) part[r] = __ldcg(reinterpret_cast<const double *>(ps_ready.arena[r] + off) + lo + i);
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+      if (r < nranks) v += part[r];
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+      if (r < nranks) reinterpret_cast<double *>(ps_ready.arena[r] + off)[lo + i] = v;
+  }
+  peer_block_signal(ps_done);
+}
+
 // reduce-scatter stage 1: send slice o of my partial vector to owner o's staging row `rank`
 __global__ void __launch_bounds__(256)
 p2p_scatter_kernel(char *const *__restrict__ arena, int rank, int nranks, size_t off, size_t n, size_t slice,
@@ -391,6 +419,15 @@ PeerSync p2p_sync(PeerArena *a, int chan) {
   ps.nranks = a->nranks;
   ps.chan = chan;
   return ps;
+}
+
+int p2p_allreduce_pull_f64(PeerArena *a, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t s) {
+  const size_t slice = (n + a->nranks - 1) / a->nranks;
+  const unsigned grid = (unsigned)std::min<size_t>(296, std::max<size_t>(1, (slice + 255) / 256));
+  p2p_pull_reduce_bcast_kernel<<<grid, 256, 0, s>>>(p2p_sync(a, chan_ready), p2p_sync(a, chan_done), arena_off(off), n,
+                                                    slice);
+  CUDA_CHECK(cudaGetLastError());
+  return 1 + p2p_wait(a, chan_done, s);
 }
 
 int p2p_error(PeerArena *a) {

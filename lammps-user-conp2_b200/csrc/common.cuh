@@ -217,6 +217,9 @@ int p2p_wait(PeerArena *, int chan, cudaStream_t);
 // deterministic sum over ranks of n doubles at `off` (result in place on every rank); `stage_off` is
 // scratch of nranks * ceil(n/nranks) doubles; uses channels chan and chan+1
 int p2p_allreduce_f64(PeerArena *, size_t off, size_t n, size_t stage_off, int chan, cudaStream_t);
+// same sum for a vector whose producer kernel raised `chan_ready` itself (peer_block_signal): pull the
+// partial slices over NVLink, store the total everywhere, wait on `chan_done`
+int p2p_allreduce_pull_f64(PeerArena *, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t);
 int p2p_error(PeerArena *);  // non-zero after a wait timed out
 // argument for kernels that do their own exchange (peer.cuh); a null arena gives the no-op value
 PeerSync p2p_sync(PeerArena *, int chan);
@@ -333,7 +336,8 @@ void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, in
                      std::vector<int> &wide, std::vector<int> &aout, ZconvPlan &plan);
 int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int nzo, const int *krad,
                       const ZconvPlan &plan, const cufftDoubleComplex *rhat, const double *Kr,
-                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat);
+                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat,
+                      const PeerSync &ps /* several GPUs: announce the partial spectra */);
 int launch_expand_planes(cudaStream_t s, size_t plane, int nplanes, int nz, int lo, const int *list,
                          const double *compact, double *full);
 int launch_pppm_ele_stencil(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *ex,

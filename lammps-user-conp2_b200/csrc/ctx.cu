@@ -417,11 +417,13 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     }
     if (pg.zs_n > 0) CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
     c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.nzo, c->d_krad.p, c->zplan,
-                                     c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p);
-    // every rank holds the partial sum over its slab: one small all-reduce completes the spectra
+                                     c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p,
+                                     fused ? p2p_sync(c->p2p, 1) : PeerSync());
+    // every rank holds the partial sum over its slab: one small all-reduce completes the spectra (zconv has
+    // announced its partial; the owner of a slice pulls it from every rank, sums, and stores it everywhere)
     if (multi) {
-      if (c->p2p)
-        c->launches += p2p_allreduce_f64(c->p2p, c->off_uhat, 2 * (size_t)pg.nzo * c->ncol, c->off_stage, 1, s);
+      if (fused)
+        c->launches += p2p_allreduce_pull_f64(c->p2p, c->off_uhat, 2 * (size_t)pg.nzo * c->ncol, 1, 2, s);
       else
         comm_allreduce_sum_f64(c->comm, (double *)c->d_uhat.p, 2 * (size_t)pg.nzo * c->ncol, s);
     }

@@ -103,6 +103,7 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
                   int *__restrict__ packed_type, int *__restrict__ cell_of, int *__restrict__ slot,
                   int *__restrict__ cell_count, double *__restrict__ qz_sum, PeerSync ps, size_t off_block,
                   int mpad) {
+  __shared__ __align__(16) PosQ tile[256];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   double qz = 0.0;
   if (j < m) {
@@ -122,11 +123,22 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
       cell_of[j] = cell;
       slot[j] = atomicAdd(&cell_count[cell], 1);
     }
-    if (ps.arena)
-      for (int r = 0; r < ps.nranks; ++r)
-        if (r != ps.rank) peer_ptr<PosQ>(ps, r, off_block)[j] = p;
+    if (ps.arena) tile[threadIdx.x] = p;
   }
   __shared__ double sh[8];
+  if (ps.arena) {
+    // the block's 256 records leave as whole 512-byte warp stores (16 B per lane), one pass per peer:
+    // NVLink moves full lines instead of the 8-byte fragments a per-thread struct store would produce
+    __syncthreads();
+    const int base = blockIdx.x * blockDim.x;
+    const int nrec = min((int)blockDim.x, m - base);
+    const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+    for (int r = 0; r < ps.nranks; ++r) {
+      if (r == ps.rank) continue;
+      uint4 *dst = reinterpret_cast<uint4 *>(peer_ptr<PosQ>(ps, r, off_block) + base);
+      for (int t = threadIdx.x; t < 2 * nrec; t += blockDim.x) dst[t] = src[t];
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) qz += __shfl_xor_sync(0xffffffffu, qz, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = qz;

@@ -56,23 +56,27 @@ template <class F>
 __device__ __forceinline__ void peer_block_signal(const PeerSync &ps, F &&before_flags) {
   if (!ps.arena) return;
   __shared__ int s_last;
-  __threadfence_system();
-  __syncthreads();
   ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(ps.arena[ps.rank]);
+  // The barrier orders the block's stores before thread 0's fence, and fences are cumulative: one
+  // system-scope fence per block (not per thread) publishes them before the ticket is taken.
+  __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int t = atomicAdd(&mine->prod_ticket[ps.chan], 1u);
     s_last = (t == gridDim.x * gridDim.y - 1);
-    if (s_last) mine->prod_ticket[ps.chan] = 0u;
+    if (s_last) {
+      mine->prod_ticket[ps.chan] = 0u;
+      __threadfence();  // acquire side: see what the other blocks stored / accumulated
+    }
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();  // see what the other blocks stored / accumulated
   before_flags();
-  __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < ps.nranks && (int)threadIdx.x != ps.rank) {
     const unsigned long long e = mine->epoch[ps.chan] + 1ull;
     ArenaCtl *theirs = reinterpret_cast<ArenaCtl *>(ps.arena[threadIdx.x]);
+    __threadfence_system();
     peer_st_release(&theirs->flags[ps.chan][ps.rank], e);
   }
 }

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(ZC_THREADS)
 zconv_kernel(int ncol, int nz, int nzl, int zs_lo, int nzo, const int *__restrict__ aout,
              const int *__restrict__ krad, const ZconvGroup *__restrict__ groups, int n_narrow,
              const int *__restrict__ wide_cols, int rcap, int npcap, const double2 *__restrict__ rhat,
-             const double *__restrict__ Kr, const double2 *__restrict__ Kc, double2 *__restrict__ uhat) {
+             const double *__restrict__ Kr, const double2 *__restrict__ Kc, double2 *__restrict__ uhat,
+             PeerSync ps) {
   // rhat: spectra of this rank's nzl input planes (compact planes zs_lo .. zs_lo+nzl-1); on several
   // GPUs uhat is this rank's partial sum and is all-reduced afterwards.  aout[zo] = position of output
   // plane zo on the ring in compact input-plane coordinates.
@@ -174,6 +175,7 @@ zconv_kernel(int ncol, int nz, int nzl, int zs_lo, int nzo, const int *__restric
       }
       if (lane == 0) uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
     }
+    peer_block_signal(ps);  // several GPUs: this rank's partial spectra are complete when every block is through
     return;
   }
   // ---------------- narrow group ----------------
@@ -246,6 +248,7 @@ zconv_kernel(int ncol, int nz, int nzl, int zs_lo, int nzo, const int *__restric
     if (a + R >= nz) run(0, a + R - nz, -nz);     // wrapped from above
     uhat[(size_t)zo * ncol + c] = make_double2(ar, ai);
   }
+  peer_block_signal(ps);
 }
 
 // compact <-> full brick copies for the on-demand outputs
@@ -326,30 +329,40 @@ ele_point_table_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, cons
 // term (:301-313), then b = b_k + b_real.  On several GPUs (peer-to-peer path) the kernel is its own
 // b_comm (fix_conp.cpp:641-648): the row's b goes straight into every peer's copy of the vector and
 // the last block raises the flags the matvec kernel polls.
+constexpr int GB_ROWS = 32;  // rows per block: one 256-byte line of b per peer
+
 __global__ void __launch_bounds__(256)
 gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ poff,
                 const double *__restrict__ pw, const double *__restrict__ u_brick,
                 const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
                 const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b,
                 PeerSync ps, size_t off_b) {
+  __shared__ double sb[GB_ROWS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i < row_end) {
-    const int npts = g.order * g.order * g.order;
+  const int base = row_begin + blockIdx.x * GB_ROWS;
+  const int npts = g.order * g.order * g.order;
+  for (int k = warp; k < GB_ROWS; k += 8) {
+    const int i = base + k;
+    if (i >= row_end) break;
     const int *po = poff + (size_t)i * npts;
     const double *w = pw + (size_t)i * npts;
     double acc = 0.0;
     for (int t = lane; t < npts; t += 32) acc = fma(w[t], u_brick[po[t]], acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    double bk = -acc;
-    if (slab_pref != 0.0) bk -= ez[i] * (slab_pref * qz_sum[0]);
-    const double bi = bk + b_real[i];
     if (lane == 0) {
+      double bk = -acc;
+      if (slab_pref != 0.0) bk -= ez[i] * (slab_pref * qz_sum[0]);
+      const double bi = bk + b_real[i];
       b_kspace[i] = bk;
       b[i] = bi;
+      sb[k] = bi;
     }
-    if (ps.arena && lane < ps.nranks && lane != ps.rank) peer_ptr<double>(ps, lane, off_b)[i] = bi;
+  }
+  if (ps.arena) {  // warp r sends the block's rows to rank r: one contiguous line per peer
+    __syncthreads();
+    for (int r = warp; r < ps.nranks; r += 8)
+      if (r != ps.rank && base + lane < row_end) peer_ptr<double>(ps, r, off_b)[base + lane] = sb[lane];
   }
   peer_block_signal(ps);
 }
@@ -499,7 +512,7 @@ void plan_pppm_zconv(const std::vector<int> &krad, int ncol, int nz, int nzi, in
 
 int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int nzo, const int *krad,
                       const ZconvPlan &plan, const cufftDoubleComplex *rhat, const double *Kr,
-                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat) {
+                      const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat, const PeerSync &ps) {
   const int grid = plan.n_narrow + plan.n_wide;
   if (grid <= 0) return 0;
   static size_t smem_set_r = 0, smem_set_c = 0;
@@ -511,7 +524,7 @@ int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int 
     }
     zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, nz, nzl, zs_lo, nzo, plan.aout, krad, plan.narrow,
                                                       plan.n_narrow, plan.wide, plan.rcap, plan.npcap,
-                                                      (const double2 *)rhat, Kr, nullptr, (double2 *)uhat);
+                                                      (const double2 *)rhat, Kr, nullptr, (double2 *)uhat, ps);
   } else {
     if (smem > smem_set_c) {
       CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -520,7 +533,7 @@ int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int 
     zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, nz, nzl, zs_lo, nzo, plan.aout, krad, plan.narrow,
                                                        plan.n_narrow, plan.wide, plan.rcap, plan.npcap,
                                                        (const double2 *)rhat, nullptr, (const double2 *)Kc,
-                                                       (double2 *)uhat);
+                                                       (double2 *)uhat, ps);
   }
   CUDA_CHECK(cudaGetLastError());
   return 1;
@@ -565,8 +578,9 @@ int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int r
   const int n = row_end - row_begin;
   if (n <= 0 && !ps.arena) return 0;
   // a rank without rows still takes part in the exchange: one block that only signals
-  gather_b_kernel<<<std::max((n + 7) / 8, 1), 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez, qz_sum,
-                                                           slab_pref, b_real, b_kspace, b, ps, off_b);
+  gather_b_kernel<<<std::max((n + GB_ROWS - 1) / GB_ROWS, 1), 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez,
+                                                                           qz_sum, slab_pref, b_real, b_kspace, b, ps,
+                                                                           off_b);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -1,0 +1,68 @@
+"""BASELINE configs[3] at full size (synthetic 10 000 electrode atoms / 100 000 charges, conp, PPPM,
+slab) through the C ABI.  The oracle cannot finish the O(N^2 K) setup at this size in test time, so
+the checks are the size-independent properties of SURVEY 8(c): electroneutrality, S.e = 0, linearity
+of the charges in the applied voltage, conq inverting conp, bit-reproducibility of the matvec, and the
+symmetric half-band product against a dense product with the same S."""
+import numpy as np
+import pytest
+
+from cases import synthetic
+from conp_b200.fix_conp import make_fix
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg4():
+    lmp, arg = synthetic("cfg4", mode="pppm", accuracy=1e-4)
+    fix = make_fix(lmp, arg)
+    fix.setup()
+    yield fix
+    fix.close()
+
+
+def test_uses_the_symmetric_kernel_and_is_neutral(cfg4):
+    info = cfg4.ctx.info()
+    assert info.n_ele == 10000 and info.n_elyte == 100000
+    assert info.symmetric_matvec == 1 and 0.0 <= info.asymmetry < 1e-9
+    q = cfg4.pre_force()
+    assert abs(q.sum()) < 1e-12                       # total electroneutrality, north_star
+    assert np.abs(q).max() > 1e-4                     # a real solve, not zeros
+    # projected matrix annihilates the constant vector: S.e = 0 (fix_conp.cpp:1011-1020)
+    Se = cfg4.ctx.matvec(np.ones(info.n_ele))
+    S_scale = np.abs(cfg4.ctx.matvec(np.where(np.arange(info.n_ele) % 2 == 0, 1.0, -1.0))).max()
+    assert np.abs(Se).max() < 1e-9 * max(S_scale, 1.0)
+
+
+def test_charges_are_affine_in_the_voltage(cfg4):
+    ctx, s = cfg4.ctx, cfg4.lmp.system
+    x = s.x[cfg4.owned]
+    q0, _ = ctx.pre_force(x, cfg4.kspace_mode, 0, 0.0)
+    q1, _ = ctx.pre_force(x, cfg4.kspace_mode, 0, 1.0)
+    q2, sc2 = ctx.pre_force(x, cfg4.kspace_mode, 0, 2.0)
+    q0, q1, q2 = q0.copy(), q1.copy(), q2.copy()
+    d = np.abs((q2 - q0) - 2.0 * (q1 - q0)).max()
+    assert d <= 1e-9 * np.abs(q2).max() + 1e-12
+    # conq fed with the right-electrode charge of the dV = 2 run returns dV = 2 (tests/cond/input:56-66)
+    side = np.asarray(cfg4.side)
+    qr = q2[side == -1].sum()
+    _, dv = ctx.pre_force(x, cfg4.kspace_mode, 1, qr)
+    assert abs(dv - 2.0) < 1e-8
+
+
+def test_step_is_bit_reproducible_in_the_matvec(cfg4):
+    n = cfg4.ctx.info().n_ele
+    v = np.random.default_rng(5).standard_normal(n)
+    a = cfg4.ctx.matvec(v)
+    b = cfg4.ctx.matvec(v)
+    assert np.array_equal(a, b)
+
+
+def test_symmetric_product_equals_dense_product_of_the_same_matrix(cfg4):
+    S = cfg4.ctx.get_matrix()
+    n = S.shape[0]
+    assert np.array_equal(S, S.T)                     # symmetrised at setup
+    v = np.random.default_rng(6).standard_normal(n)
+    ref = S @ v
+    got = cfg4.ctx.matvec(v)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(S).sum(axis=1).max() * np.abs(v).max()
