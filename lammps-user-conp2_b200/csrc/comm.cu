@@ -238,6 +238,22 @@ p2p_reduce_bcast_kernel(char *const *__restrict__ arena, int rank, int nranks, s
   }
 }
 
+// Raise this rank's flag of `chan` on every peer: launched right after a producer kernel that stored
+// into the peers' arenas without signalling (PeerSync::signal_in_kernel == 0).  The kernel boundary has
+// completed those stores; optionally one double (*value) is first copied to byte offset value_off of
+// every rank's arena (the rank's sum(q z), which only exists once the whole producer grid is done).
+__global__ void __launch_bounds__(32)
+p2p_signal_kernel(PeerSync ps, size_t value_off, const double *__restrict__ value) {
+  const int r = threadIdx.x;
+  if (r >= ps.nranks) return;
+  ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(ps.arena[ps.rank]);
+  if (value) *reinterpret_cast<double *>(ps.arena[r] + value_off) = __ldcg(value);
+  if (r == ps.rank) return;
+  const unsigned long long e = mine->epoch[ps.chan] + 1ull;
+  __threadfence_system();
+  peer_st_release(&reinterpret_cast<ArenaCtl *>(ps.arena[r])->flags[ps.chan][ps.rank], e);
+}
+
 // Pull variant of the all-reduce for a vector whose producer kernel has already raised the flags of
 // `ps_ready` on every peer (peer_block_signal in its tail): I own slice `rank`; wait for everybody's
 // partial, read the slice from every rank's copy of the vector (mine locally, the others over NVLink,
@@ -419,6 +435,12 @@ PeerSync p2p_sync(PeerArena *a, int chan) {
   ps.nranks = a->nranks;
   ps.chan = chan;
   return ps;
+}
+
+int p2p_signal(PeerArena *a, int chan, cudaStream_t s, size_t value_off, const double *value) {
+  p2p_signal_kernel<<<1, 32, 0, s>>>(p2p_sync(a, chan), value ? arena_off(value_off) : 0, value);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
 }
 
 int p2p_allreduce_pull_f64(PeerArena *a, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t s) {

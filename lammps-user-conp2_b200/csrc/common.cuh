@@ -223,6 +223,9 @@ int p2p_allreduce_pull_f64(PeerArena *, size_t off, size_t n, int chan_ready, in
 int p2p_error(PeerArena *);  // non-zero after a wait timed out
 // argument for kernels that do their own exchange (peer.cuh); a null arena gives the no-op value
 PeerSync p2p_sync(PeerArena *, int chan);
+// flags of `chan` for a producer kernel that did not signal itself; value != nullptr: *value is first
+// stored at payload offset value_off of every rank's arena
+int p2p_signal(PeerArena *, int chan, cudaStream_t, size_t value_off = 0, const double *value = nullptr);
 int p2p_wait_sync(const PeerSync &, cudaStream_t);  // stand-alone wait on a PeerSync
 
 // ---------------------------------------------------------------------------
@@ -283,6 +286,7 @@ int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_
 // multi-GPU layout: nranks blocks of mpad slots, counts[r] valid charges each; m = nranks*mpad
 int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, int mpad, const int *counts,
                          const PosQ *packed, int *cell_of, int *slot, int *cell_count,
+                         const unsigned char *relevant /* per-cell filter or nullptr */,
                          const PeerSync &ps /* wait for the fused all-gather */);
 // qz_sum != nullptr: also sum the per-rank sum(q z) partials stored in the last slot of every block
 int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cell_start, const PosQ *packed,

@@ -99,6 +99,10 @@ struct conp_ctx {
   DevBuf<int> d_ecellstart, d_runstart;
   DevBuf<PairRun> d_runs;
   DevBuf<unsigned char> d_nearmask;
+  // several GPUs, PPPM, non-periodic z: cells whose charges this rank needs at all (reachable from its
+  // rows, or in the z-range of its slab of input planes); the others are not sorted
+  DevBuf<unsigned char> d_relevant;
+  bool have_relevant = false;
 
   // pppm ---------------------------------------------------------------------------
   PPPMGeom pg;
@@ -130,6 +134,10 @@ struct conp_ctx {
   // timing ----------------------------------------------------------------------------
   cudaEvent_t ev[16];
   cudaEvent_t sev[NSTAGE + 1];
+  cudaEvent_t kev[6];           // CONP_DEBUG: spread | fft | zconv | all-reduce | ifft inside the k-space stage
+  double kev_ms[5] = {0, 0, 0, 0, 0};
+  bool signal_in_kernel = false;  // CONP_SIGNAL_IN_KERNEL=1: producers raise the flags themselves (per-block fences)
+  bool uhat_nccl = false;       // CONP_UHAT_NCCL=1: NCCL all-reduce for the spectra even on the peer-to-peer path
   bool stage_timing = false;
   double stage_ms[NSTAGE] = {0, 0, 0, 0, 0, 0, 0, 0};
   int stage_n = 0;
@@ -180,6 +188,18 @@ double slab_pref(const conp_ctx *c) {
   return 4.0 * MY_PI / volume;  // km_ewald.cpp:839, pppm_conp.cpp:307
 }
 
+// z-layers of cells (z-major order => one contiguous range of sorted charges) whose stencils can reach
+// this rank's slab of input planes
+void slab_cell_layers(const conp_ctx *c, int *cz_lo_out, int *cz_hi_out) {
+  const PPPMGeom &pg = c->pg;
+  const CellGrid &g = c->grid_b;
+  const double zlo = c->boxlo[2] + (pg.zin_lo + pg.zs_lo - pg.order - 1) / pg.delinv[2];
+  const double zhi = c->boxlo[2] + (pg.zin_lo + pg.zs_lo + pg.zs_n + pg.order + 1) / pg.delinv[2];
+  int cz_lo = (int)std::floor((zlo - g.lo[2]) * g.cinv[2]) - 1, cz_hi = (int)std::floor((zhi - g.lo[2]) * g.cinv[2]) + 1;
+  *cz_lo_out = std::max(0, std::min(cz_lo, g.nc[2] - 1));
+  *cz_hi_out = std::max(0, std::min(cz_hi, g.nc[2] - 1));
+}
+
 // electrodes never move: sort this rank's rows into the cell grid once and mark
 // the cells from which a point charge can reach them
 void ensure_static_cells(conp_ctx *c) {
@@ -200,6 +220,18 @@ void ensure_static_cells(conp_ctx *c) {
   c->d_ecellstart.upload(cs, c->stream);
   c->d_nearmask.upload(mask, c->stream);
   c->d_nearcount.zero(1, c->stream);
+  c->have_relevant = false;
+  if (c->nranks > 1 && c->have_pppm && !c->periodic[2] && getenv("CONP_SORT_ALL") == nullptr) {
+    std::vector<unsigned char> rel((size_t)c->grid_b.ncells, 0);
+    for (const PairRun &r : runs)
+      for (int cell = r.c0; cell < r.c1; ++cell) rel[cell] = 1;
+    int cz_lo = 0, cz_hi = 0;
+    slab_cell_layers(c, &cz_lo, &cz_hi);
+    const size_t layer = (size_t)c->grid_b.nc[1] * c->grid_b.nc[0];
+    if (c->pg.zs_n > 0) std::fill(rel.begin() + cz_lo * layer, rel.begin() + (cz_hi + 1) * layer, (unsigned char)1);
+    c->d_relevant.upload(rel, c->stream);
+    c->have_relevant = true;
+  }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->static_cells = true;
 }
@@ -348,6 +380,14 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   int *ptype_local = c->d_ptype.p + c->m_offsets[c->rank];
   // several GPUs, peer-to-peer path: the exchanges are done by the producing / consuming kernels
   const bool fused = multi && c->p2p != nullptr;
+  // producer side of a fused exchange: store into the peers; the flags go up in the kernel's last block
+  // or, by default, from a one-block p2p_signal kernel behind it (see PeerSync::signal_in_kernel)
+  auto producer = [&](int chan) {
+    PeerSync ps = p2p_sync(c->p2p, chan);
+    ps.signal_in_kernel = c->signal_in_kernel ? 1 : 0;
+    return ps;
+  };
+  const bool late_signal = fused && !c->signal_in_kernel;
   const PeerSync ps_pos = fused ? p2p_sync(c->p2p, 0) : PeerSync();
   if (!multi) {
     c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
@@ -357,8 +397,13 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     // every rank's positions go to every rank; the sum(q z) partial rides in the block's last (padding)
     // slot.  Types and charges are static between reneighbourings and were gathered in conp_post_neighbor.
     c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
-                                     ptype_local, nullptr, nullptr, nullptr, c->scal(2), ps_pos,
+                                     ptype_local, nullptr, nullptr, nullptr, c->scal(2),
+                                     fused ? producer(0) : PeerSync(),
                                      c->off_packed + sizeof(PosQ) * (size_t)c->m_offsets[c->rank], c->mpad);
+    if (late_signal)  // + this rank's sum(q z) into the block's padding slot on every rank
+      c->launches += p2p_signal(c->p2p, 0, s,
+                                c->off_packed + sizeof(PosQ) * (size_t)(c->m_offsets[c->rank] + c->mpad - 1),
+                                c->scal(2));
   }
   stage_mark(c, 1);
   if (multi) {
@@ -367,8 +412,11 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                  cudaMemcpyDeviceToDevice, s));
       comm_allgather(c->comm, packed_local, c->d_packed.p, sizeof(PosQ) * (size_t)c->mpad, s);
     }
+    // PPPM mode: only the charges this rank can use (near its rows, or in its slab) are sorted
+    const unsigned char *relevant =
+        (kspace_mode == CONP_KSPACE_PPPM && c->have_relevant) ? c->d_relevant.p : nullptr;
     c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, c->d_mcounts.p, c->d_packed.p, c->d_cellof.p,
-                                        c->d_slot.p, c->d_cellcount.p, ps_pos);
+                                        c->d_slot.p, c->d_cellcount.p, relevant, ps_pos);
   }
   c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p, c->d_packed.p, c->mpad,
                                   c->nranks, multi ? c->scal(2) : nullptr);
@@ -398,16 +446,14 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   if (kspace_mode == CONP_KSPACE_PPPM) {
     const PPPMGeom &pg = c->pg;
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
+    auto kmark = [&](int i) { if (c->stage_timing) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
+    kmark(0);
     if (!multi || c->periodic[2]) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
                                         c->d_flag.p);
     } else {
-      // cells (z-major order => one contiguous range of sorted charges) whose stencils can reach the slab
-      const double zlo = c->boxlo[2] + (pg.zin_lo + pg.zs_lo - pg.order - 1) / pg.delinv[2];
-      const double zhi = c->boxlo[2] + (pg.zin_lo + pg.zs_lo + pg.zs_n + pg.order + 1) / pg.delinv[2];
-      int cz_lo = (int)std::floor((zlo - g.lo[2]) * g.cinv[2]) - 1, cz_hi = (int)std::floor((zhi - g.lo[2]) * g.cinv[2]) + 1;
-      cz_lo = std::max(0, std::min(cz_lo, g.nc[2] - 1));
-      cz_hi = std::max(0, std::min(cz_hi, g.nc[2] - 1));
+      int cz_lo = 0, cz_hi = 0;
+      slab_cell_layers(c, &cz_lo, &cz_hi);
       const int cell_lo = cz_lo * g.nc[1] * g.nc[0], cell_hi = (cz_hi + 1) * g.nc[1] * g.nc[0];
       // upper bound of the charges in the range: uniform share + 50 %, the kernel grid-strides beyond it
       const long long bound = (long long)c->m_total * (cz_hi - cz_lo + 1) / g.nc[2] * 3 / 2 + 1024;
@@ -415,25 +461,33 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                         c->d_sorted.p, c->d_cellstart.p, cell_lo, cell_hi, c->d_brick.p,
                                         c->d_flag.p);
     }
+    kmark(1);
     if (pg.zs_n > 0) CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
+    kmark(2);
+    const bool uhat_p2p = fused && !c->uhat_nccl;
     c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.nzo, c->d_krad.p, c->zplan,
                                      c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p,
-                                     fused ? p2p_sync(c->p2p, 1) : PeerSync());
+                                     uhat_p2p ? producer(1) : PeerSync());
+    if (uhat_p2p && late_signal) c->launches += p2p_signal(c->p2p, 1, s);
+    kmark(3);
     // every rank holds the partial sum over its slab: one small all-reduce completes the spectra (zconv has
     // announced its partial; the owner of a slice pulls it from every rank, sums, and stores it everywhere)
     if (multi) {
-      if (fused)
+      if (uhat_p2p)
         c->launches += p2p_allreduce_pull_f64(c->p2p, c->off_uhat, 2 * (size_t)pg.nzo * c->ncol, 1, 2, s);
       else
         comm_allreduce_sum_f64(c->comm, (double *)c->d_uhat.p, 2 * (size_t)pg.nzo * c->ncol, s);
     }
+    kmark(4);
     CUFFT_CHECK(cufftExecZ2D(c->plan_b, c->d_uhat.p, c->d_ubrick.p));
+    kmark(5);
     c->launches += 2;  // at least one kernel per cuFFT exec (library)
     stage_mark(c, 4);
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
     c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_poff.p, c->d_pw.p, c->d_ubrick.p,
                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p,
-                                        fused_b ? p2p_sync(c->p2p, 3) : PeerSync(), c->off_b);
+                                        fused_b ? producer(3) : PeerSync(), c->off_b);
+    if (fused_b && late_signal) c->launches += p2p_signal(c->p2p, 3, s);
   } else {
     const EwaldHost &e = c->ew;
     c->launches += launch_axis_tables(s, c->m_total, nullptr, nullptr, nullptr, c->d_sorted.p, e.unitk, e.kxmax,
@@ -472,8 +526,9 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     stage_mark(c, 7);
   } else if (fused_mv) {
     c->launches += launch_symv(s, c->d_mat.p, c->pitch, c->N, c->r0, nr, c->d_b.p, c->sy, c->d_rowpart.p,
-                               c->d_colpart.p, c->d_sb.p, (int)c->vlen, nullptr, p2p_sync(c->p2p, 3),
-                               p2p_sync(c->p2p, 4), c->off_parts);
+                               c->d_colpart.p, c->d_sb.p, (int)c->vlen, nullptr, p2p_sync(c->p2p, 3), producer(4),
+                               c->off_parts);
+    if (late_signal) c->launches += p2p_signal(c->p2p, 4, s);
     stage_mark(c, 7);
     c->launches += launch_update_charge_sum(s, make_epilogue(c, variant, false), p2p_sync(c->p2p, 4),
                                             (const double *)(p2p_local(c->p2p) + c->off_parts), (int)c->vlen,
@@ -556,6 +611,12 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
       CUDA_CHECK(cudaEventElapsedTime(&ms, c->sev[i], c->sev[i + 1]));
       c->stage_ms[i] += ms;
     }
+    if (kspace_mode == CONP_KSPACE_PPPM)
+      for (int i = 0; i < 5; ++i) {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]));
+        c->kev_ms[i] += ms;
+      }
     c->stage_n++;
   }
 }
@@ -654,6 +715,9 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     c->overlap = getenv("CONP_NO_OVERLAP") == nullptr;
     for (auto &ev : c->ev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
+    for (auto &ev : c->kev) CUDA_CHECK(cudaEventCreate(&ev));
+    c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
+    c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
     c->d_scal.zero(16, c->stream);
     c->d_partials.zero(2 * 1024, c->stream);
     c->d_counter.zero(1, c->stream);
@@ -693,6 +757,7 @@ void conp_destroy(conp_ctx *c) {
   comm_destroy(c->comm);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->sev) cudaEventDestroy(ev);
+  for (auto &ev : c->kev) cudaEventDestroy(ev);
   for (cudaEvent_t e : {c->ev_begin, c->ev_cleared, c->ev_sorted, c->ev_pair})
     if (e) cudaEventDestroy(e);
   if (c->side) cudaStreamDestroy(c->side);
@@ -871,6 +936,7 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
                     double shift, double shiftone) {
   return guard(c, [&] {
     need(c->have_ele, "conp_pppm_setup: call conp_set_electrodes first");
+    c->static_cells = false;  // the per-rank cell relevance mask depends on the slab of planes
     if (order < 1 || order > 7) CONP_THROW(CONP_ERR_ARG, "conp_pppm_setup: PPPM order must be 1..7");
     for (int a = 0; a < 3; ++a)
       if (mesh[a] < order) CONP_THROW(CONP_ERR_ARG, "conp_pppm_setup: mesh smaller than the stencil");
@@ -1542,7 +1608,11 @@ int conp_stage_times(conp_ctx *c, int enable, double *out8) {
   const int n = c->stage_n;
   if (out8)
     for (int i = 0; i < NSTAGE; ++i) out8[i] = n ? c->stage_ms[i] / n : 0.0;
+  if (n && getenv("CONP_DEBUG"))
+    fprintf(stderr, "[conp] rank %d k-space stage (ms): spread %.4f fft %.4f zconv %.4f all-reduce %.4f ifft %.4f\n",
+            c->rank, c->kev_ms[0] / n, c->kev_ms[1] / n, c->kev_ms[2] / n, c->kev_ms[3] / n, c->kev_ms[4] / n);
   c->stage_timing = enable != 0;
+  for (auto &v : c->kev_ms) v = 0;
   for (auto &v : c->stage_ms) v = 0;
   c->stage_n = 0;
   return n;

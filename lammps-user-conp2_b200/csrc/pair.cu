@@ -163,7 +163,7 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
 __global__ void __launch_bounds__(256)
 bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts,
                      const PosQ *__restrict__ packed, int *__restrict__ cell_of, int *__restrict__ slot,
-                     int *__restrict__ cell_count, PeerSync ps) {
+                     int *__restrict__ cell_count, const unsigned char *__restrict__ relevant, PeerSync ps) {
   if (ps.arena) {
     peer_block_wait(ps);
     __syncthreads();
@@ -176,6 +176,10 @@ bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts
   }
   const PosQ p = packed[j];
   const int cell = (cell_coord(g, 2, p.z) * g.nc[1] + cell_coord(g, 1, p.y)) * g.nc[0] + cell_coord(g, 0, p.x);
+  if (relevant && !relevant[cell]) {  // nothing on this rank reads charges of that cell
+    cell_of[j] = -1;
+    return;
+  }
   cell_of[j] = cell;
   slot[j] = atomicAdd(&cell_count[cell], 1);
 }
@@ -716,10 +720,11 @@ int launch_pack_count(cudaStream_t s, const CellGrid &g, int m, const double *x_
 }
 
 int launch_bin_positions(cudaStream_t s, const CellGrid &g, int m, int mpad, const int *counts,
-                         const PosQ *packed, int *cell_of, int *slot, int *cell_count, const PeerSync &ps) {
+                         const PosQ *packed, int *cell_of, int *slot, int *cell_count,
+                         const unsigned char *relevant, const PeerSync &ps) {
   if (m <= 0 && !ps.arena) return 0;
   bin_positions_kernel<<<std::max((m + 255) / 256, 1), 256, 0, s>>>(g, m, mpad, counts, packed, cell_of, slot,
-                                                                    cell_count, ps);
+                                                                    cell_count, relevant, ps);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -31,6 +31,10 @@ struct ArenaCtl {
 struct PeerSync {
   char *const *arena = nullptr;  // device array: mapped base of every rank's arena
   int rank = 0, nranks = 1, chan = 0;
+  // 1: the producer kernel raises the flags itself (one system fence per block); 0: it only stores, and
+  // a one-block p2p_signal kernel raises them after the kernel boundary (cheaper for grids of many
+  // small blocks: measured ~20 us of fences per kernel at ~1000 blocks)
+  int signal_in_kernel = 1;
 };
 
 __device__ __forceinline__ unsigned long long peer_ld_acquire(const unsigned long long *p) {
@@ -54,7 +58,7 @@ __device__ __forceinline__ T *peer_ptr(const PeerSync &ps, int r, size_t off) {
 // payload that needs the whole grid's result.
 template <class F>
 __device__ __forceinline__ void peer_block_signal(const PeerSync &ps, F &&before_flags) {
-  if (!ps.arena) return;
+  if (!ps.arena || !ps.signal_in_kernel) return;
   __shared__ int s_last;
   ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(ps.arena[ps.rank]);
   // The barrier orders the block's stores before thread 0's fence, and fences are cumulative: one
