@@ -136,6 +136,7 @@ struct conp_ctx {
   cudaEvent_t sev[NSTAGE + 1];
   cudaEvent_t kev[6];           // CONP_DEBUG: spread | fft | zconv | all-reduce | ifft inside the k-space stage
   double kev_ms[5] = {0, 0, 0, 0, 0};
+  bool debug = false;             // CONP_DEBUG: extra timers and plan printouts on stderr
   bool signal_in_kernel = false;  // CONP_SIGNAL_IN_KERNEL=1: producers raise the flags themselves (per-block fences)
   bool uhat_nccl = false;       // CONP_UHAT_NCCL=1: NCCL all-reduce for the spectra even on the peer-to-peer path
   bool stage_timing = false;
@@ -446,7 +447,7 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   if (kspace_mode == CONP_KSPACE_PPPM) {
     const PPPMGeom &pg = c->pg;
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
-    auto kmark = [&](int i) { if (c->stage_timing) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
+    auto kmark = [&](int i) { if (c->stage_timing && c->debug) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
     kmark(0);
     if (!multi || c->periodic[2]) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
@@ -611,7 +612,7 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
       CUDA_CHECK(cudaEventElapsedTime(&ms, c->sev[i], c->sev[i + 1]));
       c->stage_ms[i] += ms;
     }
-    if (kspace_mode == CONP_KSPACE_PPPM)
+    if (kspace_mode == CONP_KSPACE_PPPM && c->debug)
       for (int i = 0; i < 5; ++i) {
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]));
@@ -716,6 +717,7 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     for (auto &ev : c->ev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->kev) CUDA_CHECK(cudaEventCreate(&ev));
+    c->debug = getenv("CONP_DEBUG") != nullptr;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
     c->d_scal.zero(16, c->stream);
@@ -1608,7 +1610,7 @@ int conp_stage_times(conp_ctx *c, int enable, double *out8) {
   const int n = c->stage_n;
   if (out8)
     for (int i = 0; i < NSTAGE; ++i) out8[i] = n ? c->stage_ms[i] / n : 0.0;
-  if (n && getenv("CONP_DEBUG"))
+  if (n && c->debug)
     fprintf(stderr, "[conp] rank %d k-space stage (ms): spread %.4f fft %.4f zconv %.4f all-reduce %.4f ifft %.4f\n",
             c->rank, c->kev_ms[0] / n, c->kev_ms[1] / n, c->kev_ms[2] / n, c->kev_ms[3] / n, c->kev_ms[4] / n);
   c->stage_timing = enable != 0;

@@ -329,19 +329,19 @@ ele_point_table_kernel(PPPMGeom g, int n_ele, const int *__restrict__ widx, cons
 // term (:301-313), then b = b_k + b_real.  On several GPUs (peer-to-peer path) the kernel is its own
 // b_comm (fix_conp.cpp:641-648): the row's b goes straight into every peer's copy of the vector and
 // the last block raises the flags the matvec kernel polls.
-constexpr int GB_ROWS = 32;  // rows per block: one 256-byte line of b per peer
+constexpr int GB_ROWS = 32;  // rows per block on several GPUs: one 256-byte line of b per peer
 
 __global__ void __launch_bounds__(256)
 gather_b_kernel(PPPMGeom g, int row_begin, int row_end, const int *__restrict__ poff,
                 const double *__restrict__ pw, const double *__restrict__ u_brick,
                 const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
                 const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b,
-                PeerSync ps, size_t off_b) {
+                PeerSync ps, size_t off_b, int rows_per_block) {
   __shared__ double sb[GB_ROWS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int base = row_begin + blockIdx.x * GB_ROWS;
+  const int base = row_begin + blockIdx.x * rows_per_block;
   const int npts = g.order * g.order * g.order;
-  for (int k = warp; k < GB_ROWS; k += 8) {
+  for (int k = warp; k < rows_per_block; k += 8) {
     const int i = base + k;
     if (i >= row_end) break;
     const int *po = poff + (size_t)i * npts;
@@ -578,9 +578,9 @@ int launch_pppm_gather_b(cudaStream_t s, const PPPMGeom &g, int row_begin, int r
   const int n = row_end - row_begin;
   if (n <= 0 && !ps.arena) return 0;
   // a rank without rows still takes part in the exchange: one block that only signals
-  gather_b_kernel<<<std::max((n + GB_ROWS - 1) / GB_ROWS, 1), 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez,
-                                                                           qz_sum, slab_pref, b_real, b_kspace, b, ps,
-                                                                           off_b);
+  const int rpb = ps.arena ? GB_ROWS : 8;  // one GPU: a row per warp, as many blocks as possible
+  gather_b_kernel<<<std::max((n + rpb - 1) / rpb, 1), 256, 0, s>>>(g, row_begin, row_end, poff, pw, u_brick, ez, qz_sum,
+                                                                   slab_pref, b_real, b_kspace, b, ps, off_b, rpb);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
