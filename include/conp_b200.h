@@ -217,6 +217,12 @@ int conp_bench_gemv(conp_ctx *ctx, int reps, float *ms_per_rep_out);
  * ddot_ loop of get_setq, fix_conp.cpp:1090-1096, applied to any vector): lets a
  * host check the resident matrix, e.g. S.e = 0 after the projection. [collective] */
 int conp_matvec(conp_ctx *ctx, const double *v, double *out);
+/* Host-only (no GPU needed): the strip decomposition the symmetric matvec uses for the row block
+ * [row0, row0+nrows) of an n x n matrix on a device with num_sms SMs.  strips_out receives
+ * min(*nstrips_out, max_strips) pairs [begin, end); *slice_len_out is the length of a strip's column
+ * slice.  Returns 0 and *nstrips_out = -1 when the symmetric kernel does not apply (n < 64). */
+int conp_plan_symv(int n, int row0, int nrows, int num_sms, int max_strips, int *strips_out, int *nstrips_out,
+                   int *slice_len_out);
 int conp_bench_dgemm_tflops(conp_ctx *ctx, int n, double *tflops_out);
 
 #ifdef __cplusplus

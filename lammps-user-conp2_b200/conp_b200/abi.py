@@ -28,7 +28,7 @@ SYMBOLS = [
     "conp_pre_force", "conp_solve_device", "conp_get_charges", "conp_get_b", "conp_get_density",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
-    "conp_matvec",
+    "conp_matvec", "conp_plan_symv",
 ]
 
 
@@ -44,6 +44,21 @@ class ConpInfo(C.Structure):
         ("ee", C.c_double), ("dd", C.c_double), ("totsetq", C.c_double),
         ("symmetric_matvec", C.c_int), ("reserved0", C.c_int), ("asymmetry", C.c_double),
     ]
+
+
+def plan_symv(n, row0, nrows, num_sms=148):
+    """Strip decomposition of the symmetric matvec (host-only entry point): (strips[nstrips][2], L) or None."""
+    L = load_library()
+    ns, sl = C.c_int(0), C.c_int(0)
+    cap = max(num_sms, nrows // 256 + 2, 1)
+    out = np.zeros((cap, 2), dtype=np.int32)
+    rc = L.conp_plan_symv(int(n), int(row0), int(nrows), int(num_sms), cap, out.ctypes.data_as(c_ip), C.byref(ns),
+                          C.byref(sl))
+    if rc != 0:
+        raise RuntimeError(f"conp_plan_symv: status {rc}")
+    if ns.value < 0:
+        return None
+    return out[:ns.value].copy(), sl.value
 
 
 class ConpError(RuntimeError):
@@ -104,6 +119,8 @@ def load_library(path: str | None = None):
     L.conp_bench_gemv.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.conp_bench_dgemm_tflops.argtypes = [vp, C.c_int, c_dp]
     L.conp_matvec.argtypes = [vp, c_dp, c_dp]
+    L.conp_plan_symv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int)]
     if path is None:
         _lib = L
     return L

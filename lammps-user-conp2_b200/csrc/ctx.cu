@@ -1657,6 +1657,21 @@ int conp_matvec(conp_ctx *c, const double *v, double *out) {
   });
 }
 
+int conp_plan_symv(int n, int row0, int nrows, int num_sms, int max_strips, int *strips_out, int *nstrips_out,
+                   int *slice_len_out) {
+  if (!nstrips_out || !slice_len_out || num_sms < 1) return CONP_ERR_ARG;
+  std::vector<int2> strips;
+  const SymvPlan p = plan_symv(n, row0, nrows, num_sms, strips);
+  *nstrips_out = p.usable ? p.nstrips : -1;
+  *slice_len_out = p.usable ? p.L : 0;
+  if (strips_out)
+    for (int s = 0; s < (int)strips.size() && s < max_strips; ++s) {
+      strips_out[2 * s] = strips[s].x;
+      strips_out[2 * s + 1] = strips[s].y;
+    }
+  return CONP_OK;
+}
+
 int conp_bench_dgemm_tflops(conp_ctx *c, int n, double *tflops_out) {
   return guard(c, [&] {
     DevBuf<double> A, B, C;
