@@ -206,3 +206,28 @@ def test_symmetric_and_general_paths_agree(monkeypatch):
         assert fix.ctx.info().symmetric_matvec == (1 if flag == "0" else 0)
         fix.close()
     assert np.abs(q["0"] - q["1"]).max() <= 1e-9 * np.abs(q["1"]).max() + 1e-12
+
+
+def test_unsymmetric_influence_function_takes_the_complex_kernel():
+    """greensfn is an input at the ABI.  LAMMPS' table is even in every k component, which makes the
+    z-convolution kernel K(kx,ky;d) real; a table that is not even in kz (here: scaled by
+    1 + 0.25 sin(2 pi kz/nz)) gives a complex K and exercises zconv_kernel<false>.  The oracle
+    consumes the same table with full complex 3-D FFTs (pppm_conp.cpp:235-266)."""
+    def factory():
+        lmp, arg = synthetic("tiny", h=1.5)
+        orig = lmp.pppm_tables
+
+        def skewed():
+            t = orig()
+            nx, ny, nz = t.mesh
+            kz = np.arange(nz)
+            f = 1.0 + 0.25 * np.sin(2.0 * np.pi * kz / nz)
+            t.greensfn = (t.greensfn.reshape(nz, ny, nx) * f[:, None, None]).reshape(-1).copy()
+            return t
+        lmp.pppm_tables = skewed
+        return lmp, arg
+    fix, ref, q, qr = both(factory)
+    b, bk = fix.ctx.get_b()
+    assert np.abs(bk - ref.b_kspace).max() <= 5e-12 * max(1.0, np.abs(ref.b_kspace).max())
+    close(q, qr)
+    fix.close()
