@@ -378,6 +378,24 @@ int launch_ewald_bextract(cudaStream_t s, int row_begin, int row_end, const doub
                           double slab_pref, const double *b_real, double *b_kspace, double *b);
 // k-major panel Pt[2*kc][ld]: rows kk / kc+kk = sqrt(2 u_k) {cos, sin}(k.r_i), k = k0+kk; segs = runs of
 // consecutive k with equal (kx,ky) inside the chunk
+// GEMM form of the structure-factor sum and of the b extraction (large systems), see ewald.cu
+struct EwaldGemm {
+  int nkxy = 0, nkz1 = 0, chunk = 0;
+  size_t np = 0;                           // nkxy * nkz1
+  DevBuf<short> d_xk, d_yk;                // (kx, ky) of every distinct pair
+  DevBuf<int> d_kxyof;                     // pair index of every listed k-vector
+  DevBuf<double> d_fr, d_fi, d_cz, d_sz;   // operands of one chunk of point charges
+  DevBuf<double> d_p, d_a, d_t;            // products P1..P4, combinations A1..A4, Tr/Ti
+  DevBuf<double> d_fxre, d_fxie, d_cze, d_sze;  // static electrode-side operands (own rows)
+};
+void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, cudaStream_t s);
+int ewald_gemm_electrodes(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin, int row_end,
+                          const double2 *etab);
+int ewald_gemm_sfac(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int m, const PosQ *atoms,
+                    const double2 *tab, const short *kz, double *sfac);
+int ewald_gemm_bextract(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin,
+                        int row_end, const short *kz, const double *ug, const double *sfac, const double *ez,
+                        const double *qz_sum, double slab_pref, const double *b_real, double *b_kspace, double *b);
 int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, int kymax, int kzmax, int k0,
                        int kc, int nseg, const int2 *segs, const short *kx, const short *ky, const short *kz,
                        const double *ug, double *panel, size_t ld);

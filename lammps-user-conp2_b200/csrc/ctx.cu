@@ -51,6 +51,11 @@ struct conp_ctx {
   DevBuf<short> d_kx, d_ky, d_kz;
   DevBuf<double> d_ug, d_sfac;
   DevBuf<double2> d_etab, d_jtab;
+  // GEMM form of the Ewald sums: -1 automatic (large M*K), 0 never, 1 always (CONP_EWALD_GEMM)
+  EwaldGemm eg;
+  int eg_mode = -1;
+  bool eg_valid = false;
+  DevBuf<unsigned char> d_blas_ws;
 
   // pair -----------------------------------------------------------------
   int pairmode = 0, ntypes = 0, smartlist = 0;
@@ -348,6 +353,21 @@ void decide_symmetry(conp_ctx *c, double *full, bool own_inverse) {
   c->sym = true;
 }
 
+// Ewald mode: the GEMM form pays off once the direct O(M K) sum is more than a few launches' worth
+bool use_ewald_gemm(const conp_ctx *c) {
+  if (c->eg_mode >= 0) return c->eg_mode == 1;
+  return (long long)c->m_total * c->ew.kcount >= 20000000LL;
+}
+
+// operands and workspaces of the GEMM form (outside graph capture: allocates)
+void ensure_ewald_gemm(conp_ctx *c) {
+  if (c->eg_valid) return;
+  ewald_gemm_plan(c->eg, c->ew, c->m_total, c->r1 - c->r0, c->stream);
+  c->launches += ewald_gemm_electrodes(c->stream, c->eg, c->ew, c->r0, c->r1, c->d_etab.p);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->eg_valid = true;
+}
+
 // --------------------------------------------------------------------------
 // the per-step pipeline (device side, asynchronous on c->stream).  Inputs:
 // positions in c->d_xraw, the variant's value in scal(12).  Everything here is
@@ -491,15 +511,24 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     if (fused_b && late_signal) c->launches += p2p_signal(c->p2p, 3, s);
   } else {
     const EwaldHost &e = c->ew;
+    const bool gemm = use_ewald_gemm(c);
     c->launches += launch_axis_tables(s, c->m_total, nullptr, nullptr, nullptr, c->d_sorted.p, e.unitk, e.kxmax,
                                       e.kymax, e.kzmax, c->d_jtab.p);
-    c->launches += launch_ewald_sfac(s, c->m_total, c->d_sorted.p, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
-                                     c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
+    if (gemm)
+      c->launches += ewald_gemm_sfac(c->blas, s, c->eg, e, c->m_total, c->d_sorted.p, c->d_jtab.p, c->d_kz.p,
+                                     c->d_sfac.p);
+    else
+      c->launches += launch_ewald_sfac(s, c->m_total, c->d_sorted.p, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax,
+                                       e.kcount, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
     stage_mark(c, 4);
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
-    c->launches += launch_ewald_bextract(s, c->r0, c->r1, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
-                                         c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, c->d_sfac.p, c->d_ez.p,
-                                         c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
+    if (gemm)
+      c->launches += ewald_gemm_bextract(c->blas, s, c->eg, e, c->r0, c->r1, c->d_kz.p, c->d_ug.p, c->d_sfac.p,
+                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
+    else
+      c->launches += launch_ewald_bextract(s, c->r0, c->r1, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
+                                           c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, c->d_sfac.p, c->d_ez.p,
+                                           c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
   }
   stage_mark(c, 5);
 
@@ -573,6 +602,7 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
   if (kspace_mode == CONP_KSPACE_EWALD) {
     const EwaldHost &e = c->ew;
     c->d_jtab.reserve(((size_t)e.kxmax + e.kymax + e.kzmax + 3) * (size_t)std::max(c->m_total, 1));
+    if (use_ewald_gemm(c)) ensure_ewald_gemm(c);
   }
 
   cudaGraphExec_t &exec = c->graph_exec[kspace_mode][variant];
@@ -718,6 +748,7 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->kev) CUDA_CHECK(cudaEventCreate(&ev));
     c->debug = getenv("CONP_DEBUG") != nullptr;
+    if (getenv("CONP_EWALD_GEMM")) c->eg_mode = atoi(getenv("CONP_EWALD_GEMM")) != 0 ? 1 : 0;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
     c->d_scal.zero(16, c->stream);
@@ -731,6 +762,9 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     CUSOLVER_CHECK(cusolverDnSetStream(c->solver, c->stream));
     CUBLAS_CHECK(cublasCreate(&c->blas));
     CUBLAS_CHECK(cublasSetStream(c->blas, c->stream));
+    // user-owned workspace: cuBLAS must not allocate while the step is being captured into a graph
+    c->d_blas_ws.reserve((size_t)64 << 20);
+    CUBLAS_CHECK(cublasSetWorkspace(c->blas, c->d_blas_ws.p, (size_t)64 << 20));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = c;
     return CONP_OK;
@@ -818,6 +852,7 @@ int conp_set_ewald(conp_ctx *c, double g_ewald, double accuracy_abs, double q2, 
     c->d_sfac.zero(2 * (size_t)std::max(c->ew.kcount, 1), c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->have_ewald = true;
+    c->eg_valid = false;
   });
 }
 
@@ -929,6 +964,7 @@ int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type,
                                       e.kzmax, c->d_etab.p);
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->have_ele = true;
+    c->eg_valid = false;
     c->static_cells = false;
     c->have_A = c->inverted = c->have_setq = false;
   });
@@ -1409,6 +1445,7 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     drop_graphs(c);
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->have_atoms = true;
+    c->eg_valid = false;
   });
 }
 

@@ -224,6 +224,127 @@ bextract_kernel(int row_begin, int row_end, const double2 *__restrict__ etab, in
   }
 }
 
+// ---------------------------------------------------------------------------
+// GEMM form of the two O(M K) / O(N K) sums (large systems).  A k-vector's phase factorises,
+// exp(i k.r) = [E_x[kx] E_y[ky]] E_z[kz], and the k list is every (kx,ky) pair times a range of kz, so
+//     S(kxy, +-m) = sum_j f_j(kxy) E_z,j[m]^(+-1),   f_j(kxy) = q_j E_x,j[kx] E_y,j[ky]
+// is a (pairs x atoms) by (atoms x harmonics) matrix product.  With f = fr + i fi, E_z[m] = c + i s the
+// four real products P1 = Fr C^T, P2 = Fi S^T, P3 = Fr S^T, P4 = Fi C^T give both signs of kz:
+//     S(+m) = (P1 - P2) + i (P3 + P4),   S(-m) = (P1 + P2) + i (P4 - P3).
+// The products run as cuBLAS DGEMMs (plain library GEMMs on the FP64 tensor cores); the kernels below
+// build the operands from the per-atom axis tables and pick the listed k-vectors out of the result.
+// The dense product also covers the (kxy, m) combinations outside the cut-off sphere (about half);
+// they are never read.  b extraction is the transposed problem with W_k = 2 u_k S_k:
+//     T_i(kxy) = sum_m [W(kxy,+m) conj(E_z,i[m]) + W(kxy,-m) E_z,i[m]],  b_i = -sum_kxy Re(conj(e_xy,i) T_i)
+// ---------------------------------------------------------------------------
+// operands of one chunk of point charges: Fr/Fi[j][nkxy], Cz/Sz[j][nkz1] (atom-major = column-major
+// (nkxy x chunk) and (nkz1 x chunk)); one block per atom
+__global__ void __launch_bounds__(128)
+eg_fill_atoms_kernel(int j0, int jn, const PosQ *__restrict__ atoms, const double2 *__restrict__ tab, int T, int kxmax,
+                     int kymax, int nkxy, const short *__restrict__ xk, const short *__restrict__ yk, int nkz1,
+                     double *__restrict__ Fr, double *__restrict__ Fi, double *__restrict__ Cz,
+                     double *__restrict__ Sz) {
+  const int jl = blockIdx.x;
+  if (jl >= jn) return;
+  const int j = j0 + jl;
+  const double2 *row = tab + (size_t)j * T;
+  const double q = atoms[j].q;  // q == 0 (km_ewald.cpp:686) gives exact zeros
+  for (int t = threadIdx.x; t < nkxy; t += blockDim.x) {
+    const int ky = yk[t];
+    const double2 ex = row[xk[t]];
+    double2 ey = row[kxmax + 1 + (ky < 0 ? -ky : ky)];
+    if (ky < 0) ey.y = -ey.y;
+    Fr[(size_t)jl * nkxy + t] = q * (ex.x * ey.x - ex.y * ey.y);
+    Fi[(size_t)jl * nkxy + t] = q * (ex.x * ey.y + ex.y * ey.x);
+  }
+  for (int m = threadIdx.x; m < nkz1; m += blockDim.x) {
+    const double2 ez = row[kxmax + kymax + 2 + m];
+    Cz[(size_t)jl * nkz1 + m] = ez.x;
+    Sz[(size_t)jl * nkz1 + m] = ez.y;
+  }
+}
+
+// static electrode-side operands for the rows [row_begin, row_end): unit-charge e_xy and E_z tables
+__global__ void __launch_bounds__(128)
+eg_fill_electrodes_kernel(int row_begin, int nrows, const double2 *__restrict__ etab, int T, int kxmax, int kymax,
+                          int nkxy, const short *__restrict__ xk, const short *__restrict__ yk, int nkz1,
+                          double *__restrict__ Fxr, double *__restrict__ Fxi, double *__restrict__ Cz,
+                          double *__restrict__ Sz) {
+  const int il = blockIdx.x;
+  if (il >= nrows) return;
+  const double2 *row = etab + (size_t)(row_begin + il) * T;
+  for (int t = threadIdx.x; t < nkxy; t += blockDim.x) {
+    const int ky = yk[t];
+    const double2 ex = row[xk[t]];
+    double2 ey = row[kxmax + 1 + (ky < 0 ? -ky : ky)];
+    if (ky < 0) ey.y = -ey.y;
+    Fxr[(size_t)il * nkxy + t] = ex.x * ey.x - ex.y * ey.y;
+    Fxi[(size_t)il * nkxy + t] = ex.x * ey.y + ex.y * ey.x;
+  }
+  for (int m = threadIdx.x; m < nkz1; m += blockDim.x) {
+    const double2 ez = row[kxmax + kymax + 2 + m];
+    Cz[(size_t)il * nkz1 + m] = ez.x;
+    Sz[(size_t)il * nkz1 + m] = ez.y;
+  }
+}
+
+// S(k) of the listed k-vectors out of the four products (column-major nkxy x nkz1, stride np apart)
+__global__ void __launch_bounds__(256)
+eg_sfac_gather_kernel(int kcount, const int *__restrict__ kxyof, const short *__restrict__ kzs, int nkxy, size_t np,
+                      const double *__restrict__ P, double *__restrict__ sfac) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kcount) return;
+  const int kz = kzs[k];
+  const size_t at = (size_t)kxyof[k] + (size_t)nkxy * (kz < 0 ? -kz : kz);
+  const double p1 = P[at], p2 = P[np + at], p3 = P[2 * np + at], p4 = P[3 * np + at];
+  sfac[2 * (size_t)k] = kz >= 0 ? p1 - p2 : p1 + p2;
+  sfac[2 * (size_t)k + 1] = kz >= 0 ? p3 + p4 : p4 - p3;
+}
+
+// W_k = 2 u_k S_k scattered into the four combinations the transposed products need (A zeroed
+// before): A1 = Wr+ + Wr-, A2 = Wi+ - Wi-, A3 = Wi+ + Wi-, A4 = Wr- - Wr+.  An entry receives at most
+// two addends (kz = +-m), so the atomic sum does not depend on their order.
+__global__ void __launch_bounds__(256)
+eg_scatter_w_kernel(int kcount, const int *__restrict__ kxyof, const short *__restrict__ kzs, int nkxy, size_t np,
+                    const double *__restrict__ ug, const double *__restrict__ sfac, double *__restrict__ A) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kcount) return;
+  const int kz = kzs[k];
+  const size_t at = (size_t)kxyof[k] + (size_t)nkxy * (kz < 0 ? -kz : kz);
+  const double u2 = 2.0 * ug[k];
+  const double wr = u2 * sfac[2 * (size_t)k], wi = u2 * sfac[2 * (size_t)k + 1];
+  atomicAdd(A + at, wr);
+  atomicAdd(A + np + at, kz >= 0 ? wi : -wi);
+  atomicAdd(A + 2 * np + at, wi);
+  atomicAdd(A + 3 * np + at, kz >= 0 ? -wr : wr);
+}
+
+// b_i = -sum_kxy (e_xy,r Tr + e_xy,i Ti) - z_i * slabcorr ; b = b_k + b_real.  One warp per row.
+__global__ void __launch_bounds__(256)
+eg_b_reduce_kernel(int row_begin, int nrows, int nkxy, const double *__restrict__ Fxr, const double *__restrict__ Fxi,
+                   const double *__restrict__ Tr, const double *__restrict__ Ti, const double *__restrict__ ez,
+                   const double *__restrict__ qz_sum, double slab_pref, const double *__restrict__ b_real,
+                   double *__restrict__ b_kspace, double *__restrict__ b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int il = blockIdx.x * 8 + warp;
+  if (il >= nrows) return;
+  const size_t o = (size_t)il * nkxy;
+  double acc = 0.0;
+  for (int t = lane; t < nkxy; t += 32) {
+    acc = fma(Fxr[o + t], Tr[o + t], acc);
+    acc = fma(Fxi[o + t], Ti[o + t], acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    const int i = row_begin + il;
+    double bk = -acc;
+    if (slab_pref != 0.0) bk -= ez[i] * (slab_pref * qz_sum[0]);  // slabcorr km_ewald.cpp:839-846
+    b_kspace[i] = bk;
+    b[i] = bk + b_real[i];
+  }
+}
+
 // Gram operand, k-major: Pt[kk][i] = sqrt(2 u_k) cos(k.r_i), Pt[kc+kk][i] = sqrt(2 u_k) sin(k.r_i)
 // for k = k0+kk.  One thread per (atom i, segment): a segment is a run of
 // consecutive k with equal (kx, ky) and consecutive kz, walked by rotating
@@ -294,5 +415,118 @@ int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, in
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
+
+// ---- GEMM form: host side ---------------------------------------------------------------------------
+void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, cudaStream_t s) {
+  // distinct (kx, ky) pairs in list order (the list is (kx, ky) major, kz minor)
+  std::vector<short> xk, yk;
+  std::vector<int> kxyof(e.kcount);
+  for (int k = 0; k < e.kcount; ++k) {
+    if (xk.empty() || xk.back() != e.kx[k] || yk.back() != e.ky[k]) {
+      xk.push_back(e.kx[k]);
+      yk.push_back(e.ky[k]);
+    }
+    kxyof[k] = (int)xk.size() - 1;
+  }
+  g.nkxy = (int)xk.size();
+  g.nkz1 = e.kzmax + 1;
+  g.np = (size_t)g.nkxy * g.nkz1;
+  if (xk.empty()) { xk.push_back(0); yk.push_back(0); }
+  if (kxyof.empty()) kxyof.push_back(0);
+  g.d_xk.upload(xk, s);
+  g.d_yk.upload(yk, s);
+  g.d_kxyof.upload(kxyof, s);
+  // chunk of point charges whose operands fit ~1 GB
+  const size_t per_atom = sizeof(double) * 2 * ((size_t)g.nkxy + g.nkz1);
+  size_t chunk = ((size_t)1 << 30) / std::max<size_t>(per_atom, 1);
+  chunk = std::max<size_t>(1024, chunk / 256 * 256);
+  g.chunk = (int)std::min<size_t>(chunk, (size_t)std::max(m_total, 1));
+  g.d_fr.reserve((size_t)g.chunk * g.nkxy);
+  g.d_fi.reserve((size_t)g.chunk * g.nkxy);
+  g.d_cz.reserve((size_t)g.chunk * g.nkz1);
+  g.d_sz.reserve((size_t)g.chunk * g.nkz1);
+  g.d_p.reserve(4 * std::max<size_t>(g.np, 1));
+  g.d_a.reserve(4 * std::max<size_t>(g.np, 1));
+  const size_t nr = (size_t)std::max(nrows, 1);
+  g.d_t.reserve(2 * nr * g.nkxy);
+  g.d_fxre.reserve(nr * g.nkxy);
+  g.d_fxie.reserve(nr * g.nkxy);
+  g.d_cze.reserve(nr * g.nkz1);
+  g.d_sze.reserve(nr * g.nkz1);
+}
+
+int ewald_gemm_electrodes(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin, int row_end,
+                          const double2 *etab) {
+  const int n = row_end - row_begin;
+  if (n <= 0 || g.nkxy <= 0) return 0;
+  const int T = e.kxmax + e.kymax + e.kzmax + 3;
+  eg_fill_electrodes_kernel<<<n, 128, 0, s>>>(row_begin, n, etab, T, e.kxmax, e.kymax, g.nkxy, g.d_xk.p, g.d_yk.p,
+                                              g.nkz1, g.d_fxre.p, g.d_fxie.p, g.d_cze.p, g.d_sze.p);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int ewald_gemm_sfac(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int m, const PosQ *atoms,
+                    const double2 *tab, const short *kz, double *sfac) {
+  if (e.kcount <= 0) return 0;
+  if (m <= 0) {
+    CUDA_CHECK(cudaMemsetAsync(sfac, 0, sizeof(double) * 2 * (size_t)e.kcount, s));  // km_ewald.cpp:160-161
+    return 0;
+  }
+  const int T = e.kxmax + e.kymax + e.kzmax + 3;
+  const double one = 1.0, zero = 0.0;
+  int launched = 0;
+  double *P1 = g.d_p.p, *P2 = P1 + g.np, *P3 = P2 + g.np, *P4 = P3 + g.np;
+  for (int j0 = 0; j0 < m; j0 += g.chunk) {
+    const int jn = std::min(g.chunk, m - j0);
+    eg_fill_atoms_kernel<<<jn, 128, 0, s>>>(j0, jn, atoms, tab, T, e.kxmax, e.kymax, g.nkxy, g.d_xk.p, g.d_yk.p,
+                                            g.nkz1, g.d_fr.p, g.d_fi.p, g.d_cz.p, g.d_sz.p);
+    CUDA_CHECK(cudaGetLastError());
+    const double *beta = j0 == 0 ? &zero : &one;
+    // P (nkxy x nkz1, column-major) (+)= F (nkxy x jn) * Z^T, Z stored as (nkz1 x jn) column-major
+    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fr.p, g.nkxy, g.d_cz.p,
+                             g.nkz1, beta, P1, g.nkxy));
+    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fi.p, g.nkxy, g.d_sz.p,
+                             g.nkz1, beta, P2, g.nkxy));
+    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fr.p, g.nkxy, g.d_sz.p,
+                             g.nkz1, beta, P3, g.nkxy));
+    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fi.p, g.nkxy, g.d_cz.p,
+                             g.nkz1, beta, P4, g.nkxy));
+    launched += 5;
+  }
+  eg_sfac_gather_kernel<<<(e.kcount + 255) / 256, 256, 0, s>>>(e.kcount, g.d_kxyof.p, kz, g.nkxy, g.np, g.d_p.p, sfac);
+  CUDA_CHECK(cudaGetLastError());
+  return launched + 1;
+}
+
+int ewald_gemm_bextract(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin,
+                        int row_end, const short *kz, const double *ug, const double *sfac, const double *ez,
+                        const double *qz_sum, double slab_pref, const double *b_real, double *b_kspace, double *b) {
+  const int n = row_end - row_begin;
+  if (n <= 0) return 0;
+  const double one = 1.0, zero = 0.0;
+  CUDA_CHECK(cudaMemsetAsync(g.d_a.p, 0, sizeof(double) * 4 * g.np, s));
+  if (e.kcount > 0) {
+    eg_scatter_w_kernel<<<(e.kcount + 255) / 256, 256, 0, s>>>(e.kcount, g.d_kxyof.p, kz, g.nkxy, g.np, ug, sfac,
+                                                               g.d_a.p);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  double *A1 = g.d_a.p, *A2 = A1 + g.np, *A3 = A2 + g.np, *A4 = A3 + g.np;
+  double *Tr = g.d_t.p, *Ti = Tr + (size_t)n * g.nkxy;
+  // T (nkxy x n, column-major) = A (nkxy x nkz1) * Z_e (nkz1 x n)
+  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A1, g.nkxy, g.d_cze.p, g.nkz1,
+                           &zero, Tr, g.nkxy));
+  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A2, g.nkxy, g.d_sze.p, g.nkz1,
+                           &one, Tr, g.nkxy));
+  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A3, g.nkxy, g.d_cze.p, g.nkz1,
+                           &zero, Ti, g.nkxy));
+  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A4, g.nkxy, g.d_sze.p, g.nkz1,
+                           &one, Ti, g.nkxy));
+  eg_b_reduce_kernel<<<(n + 7) / 8, 256, 0, s>>>(row_begin, n, g.nkxy, g.d_fxre.p, g.d_fxie.p, Tr, Ti, ez, qz_sum,
+                                                 slab_pref, b_real, b_kspace, b);
+  CUDA_CHECK(cudaGetLastError());
+  return 6;
+}
+
 
 }  // namespace conp

@@ -256,3 +256,22 @@ def test_error_paths():
         fix.ctx.invert_project()
     assert "Inversion failed" in str(e.value)
     fix.close()
+
+
+@pytest.mark.parametrize("case", ["dilute0", "dilute2", "dilute4", "il1", "small"])
+def test_ewald_gemm_form(case, monkeypatch):
+    """Ewald mode with the structure factors and the b extraction computed as matrix products
+    (ewald_gemm_sfac / ewald_gemm_bextract; automatic only for large M*K, forced here) against the
+    oracle's loops (km_ewald.cpp:668-825): slab, ffield, noslab zneutr, il_onelayer, synthetic."""
+    monkeypatch.setenv("CONP_EWALD_GEMM", "1")
+    if case.startswith("dilute"):
+        fix, ref, q, qr = run_pair(dilute, int(case[-1]))
+    elif case == "il1":
+        fix, ref, q, qr = run_pair(il, 1, twolayer=False)
+    else:
+        fix, ref, q, qr = run_pair(synthetic, "small", mode="ewald", ff="slab", h=1.25, accuracy=1e-4)
+    check_all(fix, ref, q, qr)
+    # second call runs eagerly again or is captured, third replays the CUDA graph (cuBLAS nodes inside)
+    fix.pre_force()
+    q_close(fix.pre_force(), qr)
+    fix.close()
