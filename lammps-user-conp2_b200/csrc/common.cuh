@@ -12,6 +12,9 @@
 #include <string>
 #include <vector>
 
+#include <map>
+#include <utility>
+
 #include "../../include/conp_b200.h"
 #include "peer.cuh"
 
@@ -227,6 +230,20 @@ PeerSync p2p_sync(PeerArena *, int chan);
 // stored at payload offset value_off of every rank's arena
 int p2p_signal(PeerArena *, int chan, cudaStream_t, size_t value_off = 0, const double *value = nullptr);
 int p2p_wait_sync(const PeerSync &, cudaStream_t);  // stand-alone wait on a PeerSync
+
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per device (one process may hold
+// contexts on several GPUs), so the largest size requested so far is remembered per (kernel, device).
+template <class Kernel>
+inline void ensure_dynamic_smem(Kernel kernel, size_t bytes) {
+  static std::map<std::pair<const void *, int>, size_t> granted;
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  size_t &have = granted[{reinterpret_cast<const void *>(kernel), dev}];
+  if (bytes > have) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // kernel launchers (one .cu per group); all take the context's stream and

@@ -640,12 +640,8 @@ symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restri
 int launch_gemv(cudaStream_t s, const double *S, size_t pitch, int nrows, int ncols_pad, const double *b,
                 double *out, int num_sms, const ChargeEpilogue *ep) {
   if (nrows <= 0) return 0;
-  static bool attr_set = false;
   const size_t smem = sizeof(Smem);
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(gemv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_dynamic_smem(gemv_tma_kernel, smem);
   int grid = num_sms < nrows ? num_sms : nrows;
   ChargeEpilogue e;
   if (ep) e = *ep;
@@ -683,12 +679,8 @@ int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, 
                 const SymvPlan &plan, double *rowpart, double *colpart, double *out, int out_len,
                 const ChargeEpilogue *ep, const PeerSync &wait_b, const PeerSync &push_parts, size_t off_parts) {
   if (!plan.usable || !plan.strips) CONP_THROW(CONP_ERR_STATE, "launch_symv: no plan");
-  static bool attr_set = false;
   const size_t smem = sizeof(SySmem);
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(symv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_dynamic_smem(symv_tma_kernel, smem);
   int launched = 1;
   if (plan.grid > 0) {
     symv_tma_kernel<<<plan.grid, THREADS, smem, s>>>(S, pitch, N, row0, plan.strips, plan.nstrips, plan.L, b,

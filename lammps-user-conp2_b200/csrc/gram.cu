@@ -154,11 +154,7 @@ int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const dou
                            const double *panel_all, size_t ld, double *C, size_t pitch, int lower_only) {
   if (nrows <= 0 || n <= 0 || kdim <= 0) return 0;
   if (kdim % BK) CONP_THROW(CONP_ERR_ARG, "gram: kdim must be a multiple of %d", BK);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem)));
-    attr_set = true;
-  }
+  ensure_dynamic_smem(gram_kernel, sizeof(GramSmem));
   dim3 grid((n + BN - 1) / BN, (nrows + BM - 1) / BM);
   gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, C, pitch,
                                                       lower_only);

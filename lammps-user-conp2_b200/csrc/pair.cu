@@ -733,12 +733,7 @@ int launch_cell_scan(cudaStream_t s, int ncells, const int *cell_count, int *cel
                      int mpad, int nranks, double *qz_sum) {
   const size_t smem = sizeof(int) * 4 * (size_t)((ncells + 3) / 4);
   if (smem <= 200 * 1024) {
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      CUDA_CHECK(cudaFuncSetAttribute(cell_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-      smem_set = 200 * 1024;
-    }
+    ensure_dynamic_smem(cell_scan_kernel<true>, 200 * 1024);
     cell_scan_kernel<true><<<1, 1024, smem, s>>>(ncells, cell_count, cell_start, packed, mpad, nranks, qz_sum);
   } else {
     cell_scan_kernel<false><<<1, 1024, 0, s>>>(ncells, cell_count, cell_start, packed, mpad, nranks, qz_sum);

@@ -418,11 +418,9 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
   if (per_sm < 0) {
     const char *e = getenv("CONP_SPREAD_BLOCKS_PER_SM");
     per_sm = e ? atoi(e) : SPREAD_BLOCKS_PER_SM;
-    if (per_sm > 0 && per_sm < 8) {
-      smem = ((size_t)(227 * 1024) / per_sm - 1024) & ~(size_t)127;
-      CUDA_CHECK(cudaFuncSetAttribute(spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (per_sm > 0 && per_sm < 8) smem = ((size_t)(227 * 1024) / per_sm - 1024) & ~(size_t)127;
   }
+  if (smem > 0) ensure_dynamic_smem(spread_kernel, smem);
   spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, brick, range_flag);
   CUDA_CHECK(cudaGetLastError());
   return 1;
@@ -515,21 +513,14 @@ int launch_pppm_zconv(cudaStream_t s, int ncol, int nz, int nzl, int zs_lo, int 
                       const cufftDoubleComplex *Kc, cufftDoubleComplex *uhat, const PeerSync &ps) {
   const int grid = plan.n_narrow + plan.n_wide;
   if (grid <= 0) return 0;
-  static size_t smem_set_r = 0, smem_set_c = 0;
   const size_t smem = zc_narrow_smem(plan.npcap, plan.rcap, Kr != nullptr);
   if (Kr) {
-    if (smem > smem_set_r) {
-      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set_r = smem;
-    }
+    ensure_dynamic_smem(zconv_kernel<true>, smem);
     zconv_kernel<true><<<grid, ZC_THREADS, smem, s>>>(ncol, nz, nzl, zs_lo, nzo, plan.aout, krad, plan.narrow,
                                                       plan.n_narrow, plan.wide, plan.rcap, plan.npcap,
                                                       (const double2 *)rhat, Kr, nullptr, (double2 *)uhat, ps);
   } else {
-    if (smem > smem_set_c) {
-      CUDA_CHECK(cudaFuncSetAttribute(zconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set_c = smem;
-    }
+    ensure_dynamic_smem(zconv_kernel<false>, smem);
     zconv_kernel<false><<<grid, ZC_THREADS, smem, s>>>(ncol, nz, nzl, zs_lo, nzo, plan.aout, krad, plan.narrow,
                                                        plan.n_narrow, plan.wide, plan.rcap, plan.npcap,
                                                        (const double2 *)rhat, nullptr, (const double2 *)Kc,
