@@ -346,7 +346,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": describe(name), "kspace": args.kspace, "mesh": list(lmp.mesh) if lmp.mesh else None,
                    "kcount_A": info.kcount, "parallelism": f"S rows sharded x{world}, electrolyte chunks x{world}",
-                   "l2_policy": f"inputs larger than L2 (S row block {8.0*nrows*N/1e6:.0f} MB streamed every step; "
+                   "l2_policy": f"inputs larger than L2 ({gemv_bytes/1e6:.0f} MB of the S row block streamed every step"
+                                f"{' (half band of the symmetric matrix)' if sym else ''}; "
                                 f"{NSETS} jittered position sets, sigma {JITTER} A)"},
         "electrode_atom_updates_per_s": value * N,
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms,
