@@ -14,6 +14,14 @@ from conp_b200 import abi
 R, C = 8, 512  # rows per stage, columns per chunk (gemv.cu)
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _library():
+    import os
+    if not os.path.exists(abi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def chunks(a, bnd, N, H):
     CS, CE = a & ~1, bnd + H
     end1 = min(CE, N)
