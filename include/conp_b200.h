@@ -169,7 +169,11 @@ int conp_post_neighbor(conp_ctx *ctx, int nlocal, const double *q, const int *ty
  * (fix_conp.cpp:1120-1161, fix_conq.cpp:41-90, fix_cond.cpp:70-126).
  * x = atom->x[0] (nlocal x 3).  value = dV [V] for conp, right-electrode
  * charge for conq, D for cond.  q_ele_out[n_ele] = new electrode charges in
- * eleall order; scalar_out = the fix's compute_scalar(). [collective] */
+ * eleall order; scalar_out = the fix's compute_scalar(). [collective]
+ * On several GPUs the ranks' steps write into each other's device buffers: a
+ * rank must not enter conp_pre_force while another is still inside
+ * conp_post_force / conp_get_* of the previous solve (the shim puts an
+ * MPI_Barrier in front; inside one solve the library orders itself). */
 int conp_pre_force(conp_ctx *ctx, const double *x, int kspace_mode, int variant, double value,
                    double *q_ele_out, double *scalar_out);
 

@@ -284,6 +284,11 @@ void FixConpB200::pre_force(int)
   if (update->ntimestep % everynum) return;
   if (potdiffstr) potdiff = input->variable->compute_equal(potdiffvar);          // reference :1143
   const int mode = pppmflag ? CONP_KSPACE_PPPM : CONP_KSPACE_EWALD;
+  /* On several GPUs a rank's step writes straight into its peers' device buffers (positions, b, S.b).
+     No rank may start the next solve while another is still in conp_post_force / conp_get_density of
+     the previous one; LAMMPS' own per-step collectives normally guarantee that, the barrier makes it
+     unconditional (a few microseconds against a step of hundreds). */
+  if (comm->nprocs > 1) MPI_Barrier(world);
   check(conp_pre_force(ctx, &atom->x[0][0], mode, variant(), potdiff, eleallq.data(), &scalar_output));
   scatter_charges();
 }
