@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CONP_ABI_VERSION 1
+#define CONP_ABI_VERSION 2
 #define CONP_UNIQUE_ID_BYTES 128
 
 typedef struct conp_ctx conp_ctx;
@@ -73,6 +73,9 @@ typedef struct conp_info {
 /* ---- lifetime ---------------------------------------------------------- */
 
 int conp_abi_version(void);
+/* Number of usable (sm_100) CUDA devices of this node, so that a host without the CUDA runtime
+ * headers can map its node-local MPI rank to a device (shim/fix_conp.cpp). */
+int conp_device_count(int *count_out);
 
 /* Rank 0 creates the NCCL unique id; the host broadcasts the 128 bytes to
  * the other ranks (MPI_Bcast on LAMMPS' `world`) before conp_create(). */
@@ -124,7 +127,7 @@ int conp_set_electrodes(conp_ctx *ctx, int n_ele, const int *tag, const int *typ
  * greensfn on the full mesh [nz][ny][nx] x-fastest, shift/shiftone;
  * pppm_conp.cpp:146-148, 199-203, 245-249).  Also caches the electrode
  * stencils (aaa_map_rho, pppm_conp.cpp:318-344) and allocates the bricks
- * (setup_allocate :346-356). */
+ * (setup_allocate :346-356). [collective]; conp_post_neighbor must follow. */
 int conp_pppm_setup(conp_ctx *ctx, const int mesh[3], int order, const double *rho_coeff,
                     const double *greensfn, double shift, double shiftone);
 
@@ -158,10 +161,15 @@ int conp_set_unit_voltage(conp_ctx *ctx, double evscale, const double *q_init, i
  * owns: static per-atom data until the next reneighbouring.  mask/groupbits
  * as in LAMMPS (atom->mask, groupbit | jgroupbit): atoms with
  * (mask & ele_bits) != 0 are electrode atoms and are skipped; mask may be
- * NULL when only non-electrode atoms are passed.  counts[nranks] = nlocal of
- * every rank (NULL when nranks == 1). */
+ * NULL when only non-electrode atoms are passed.  [collective] (the ranks
+ * exchange their counts of charged atoms and size the exchange buffers).
+ * Call order: after conp_set_electrodes / conp_pppm_setup -- both invalidate
+ * the per-rank atom data (the exchange buffers depend on N and on the mesh),
+ * so a host that runs its kspace->setup() after setup_post_neighbor, as the
+ * reference's hook order does (fix_conp.cpp:382-391), calls this again before
+ * the first solve. */
 int conp_post_neighbor(conp_ctx *ctx, int nlocal, const double *q, const int *type, const int *mask,
-                       int ele_bits, const int *counts);
+                       int ele_bits);
 
 /* FixConp::pre_force (fix_conp.cpp:543-573) = b_cal (:677-695: k-space part
  * km_ewald.cpp:153-167 or pppm_conp.cpp:269-316, real-space part

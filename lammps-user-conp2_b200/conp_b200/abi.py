@@ -22,7 +22,7 @@ KSPACE_EWALD, KSPACE_PPPM = 0, 1
 
 # every symbol include/conp_b200.h declares (checked by tests/test_abi_symbols.py)
 SYMBOLS = [
-    "conp_abi_version", "conp_get_unique_id", "conp_create", "conp_destroy", "conp_last_error", "conp_get_info",
+    "conp_abi_version", "conp_device_count", "conp_get_unique_id", "conp_create", "conp_destroy", "conp_last_error", "conp_get_info",
     "conp_set_cell", "conp_set_ewald", "conp_set_pair", "conp_set_electrodes", "conp_pppm_setup", "conp_build_A",
     "conp_load_matrix", "conp_get_matrix", "conp_invert_project", "conp_set_unit_voltage", "conp_post_neighbor",
     "conp_pre_force", "conp_solve_device", "conp_get_charges", "conp_get_b", "conp_get_density",
@@ -102,7 +102,8 @@ def load_library(path: str | None = None):
     L.conp_get_matrix.argtypes = [vp, c_dp]
     L.conp_invert_project.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_dp]
     L.conp_set_unit_voltage.argtypes = [vp, C.c_double, c_dp, C.c_int, C.c_int, C.c_int, c_dp]
-    L.conp_post_neighbor.argtypes = [vp, C.c_int, c_dp, c_ip, c_ip, C.c_int, c_ip]
+    L.conp_post_neighbor.argtypes = [vp, C.c_int, c_dp, c_ip, c_ip, C.c_int]
+    L.conp_device_count.argtypes = [c_ip]
     L.conp_pre_force.argtypes = [vp, c_dp, C.c_int, C.c_int, C.c_double, c_dp, c_dp]
     L.conp_solve_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double]
     L.conp_get_charges.argtypes = [vp, c_dp, c_dp]
@@ -241,10 +242,10 @@ class Context:
         return t.value
 
     # per step ------------------------------------------------------------------
-    def post_neighbor(self, q, typ, mask=None, ele_bits=0, counts=None):
-        qq, tt, mm, cc = f64(q), i32(typ), i32(mask), i32(counts)
+    def post_neighbor(self, q, typ, mask=None, ele_bits=0):
+        qq, tt, mm = f64(q), i32(typ), i32(mask)
         self._nlocal = int(qq.shape[0])
-        self._ck(self.L.conp_post_neighbor(self.h, self._nlocal, _dp(qq), _ip(tt), _ip(mm), int(ele_bits), _ip(cc)))
+        self._ck(self.L.conp_post_neighbor(self.h, self._nlocal, _dp(qq), _ip(tt), _ip(mm), int(ele_bits)))
 
     def pre_force(self, x, kspace_mode, variant, value):
         xx = f64(x)

@@ -92,8 +92,18 @@ struct DevBuf {
     cap = n;
     owned = false;
   }
+  // take over another buffer's allocation
+  void adopt(DevBuf &o) {
+    release();
+    p = o.p; cap = o.cap; owned = o.owned;
+    o.p = nullptr; o.cap = 0; o.owned = true;
+  }
   void reserve(size_t n) {
     if (n <= cap) return;
+    // a view into the peer-to-peer arena must never be silently replaced by a private allocation: the
+    // peers keep writing into the arena.  The owner (ctx.cu: drop_p2p / ensure_p2p) re-sizes the arena.
+    if (p && !owned)
+      CONP_THROW(CONP_ERR_STATE, "internal: buffer attached to the exchange arena asked to grow (%zu > %zu)", n, cap);
     release();
     void *q = nullptr;
     cudaError_t e = cudaMalloc(&q, n * sizeof(T));
@@ -254,12 +264,14 @@ inline void ensure_dynamic_smem(Kernel kernel, size_t bytes) {
 // update_charge epilogue parameters (device pointers); see charge_epilogue() in gemv.cu
 struct ChargeEpilogue {
   int enabled, variant, n, row_offset, one_electrode;
+  int neutral, n_left;   // neutral: remove the rounding residual sum(S.b)/n from every charge (projection on)
+  double sum_setz;
   double totsetq, lz, vmult;
   const double *value;   // dV | QR | D in device memory
   const double *dipole;  // sum q z of the non-electrode atoms
   const int *side;
   const double *setz, *setq, *qinit, *sb;
-  double *q_out, *scalar_out /* [0]=scalar, [1]=potdiff */, *partials /* 2 per block */;
+  double *q_out, *scalar_out /* [0]=scalar, [1]=potdiff, [13]=mean residual */, *partials /* 3 per block */;
   unsigned int *counter;
 };
 // out[r] = sum_c S[r*pitch + c] * b[c], r < nrows, c < ncols_pad (pad columns of S and b are zero).
@@ -285,7 +297,7 @@ int launch_update_charge_sum(cudaStream_t s, const ChargeEpilogue &ep, const Pee
                              int len, double *sb_out);
 int launch_update_charge(cudaStream_t s, const ChargeEpilogue &ep);
 int launch_finalize_q(cudaStream_t s, int n, const double *sb, const double *setq, const double *qinit,
-                      const double *scal /* [1] = potdiff */, double *q_out);
+                      const double *scal /* [1] = potdiff, [13] = mean residual of S.b */, double *q_out);
 
 // pair.cu ------------------------------------------------------------------
 CellGrid make_cell_grid(const double lo[3], const double prd[3], const int periodic[3], double rc);

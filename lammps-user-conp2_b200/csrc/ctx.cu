@@ -84,6 +84,10 @@ struct conp_ctx {
   bool have_qinit = false;
   double totsetq = 0, vmult = 0, evscale = 0, ee = 0, dd = 0;
   int one_electrode = 0;
+  // electroneutrality polish of the epilogue (see charge_epilogue): on when the projection is
+  bool neutral_polish = false, projected_here = false;
+  int n_left = 0;
+  double sum_setz = 0;
   double build_ms = 0, invert_ms = 0;
 
   // atoms ------------------------------------------------------------------------
@@ -149,7 +153,7 @@ struct conp_ctx {
   int stage_n = 0;
 
   // scalars in d_scal: [0] scalar_output [1] potdiff [2] qz_sum [3] projection total [4..11] energies
-  // [12] value (dV | QR | D) of the current solve
+  // [12] value (dV | QR | D) of the current solve [13] mean residual of S.b taken off every charge
   double *scal(int i) { return d_scal.p + i; }
 };
 
@@ -258,6 +262,9 @@ ChargeEpilogue make_epilogue(conp_ctx *c, int variant, bool fused) {
   ep.n = c->N;
   ep.row_offset = (fused && !c->sym) ? c->r0 : 0;
   ep.one_electrode = c->one_electrode;
+  ep.neutral = c->neutral_polish ? 1 : 0;
+  ep.n_left = c->n_left;
+  ep.sum_setz = c->sum_setz;
   ep.totsetq = c->totsetq;
   ep.lz = c->prd[2];
   ep.vmult = c->vmult;
@@ -275,6 +282,17 @@ ChargeEpilogue make_epilogue(conp_ctx *c, int variant, bool fused) {
   return ep;
 }
 
+// Detach every view and free the arena.  Collective (p2p_destroy closes the peers' mappings): used by the
+// setup entry points that change the size of an exchanged buffer; conp_post_neighbor builds the next one.
+void drop_p2p(conp_ctx *c) {
+  if (!c->p2p) return;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->d_b.release(); c->d_sb.release(); c->d_uhat.release(); c->d_packed.release();
+  p2p_destroy(c->p2p);
+  c->p2p = nullptr;
+  c->p2p_bytes = 0;
+}
+
 // (Re)build the peer-to-peer arena when the exchanged buffers changed size.  Collective: every rank
 // sees the same sizes, so every rank takes the same branch.
 void ensure_p2p(conp_ctx *c) {
@@ -289,12 +307,8 @@ void ensure_p2p(conp_ctx *c) {
   const size_t pt_bytes = up(sizeof(double) * c->vlen * c->nranks);  // one partial S.b per rank
   const size_t need = 2 * b_bytes + u_bytes + st_bytes + pk_bytes + pt_bytes;
   if (c->p2p && need == c->p2p_bytes) return;
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  if (c->p2p) {
-    c->d_b.release(); c->d_sb.release(); c->d_uhat.release(); c->d_packed.release();
-    p2p_destroy(c->p2p);
-    c->p2p = nullptr;
-  }
+  drop_p2p(c);
+  // the views about to be attached may still own private memory from a single-context phase
   c->p2p = p2p_create(c->comm, need, c->stream);
   c->p2p_bytes = need;
   if (!c->p2p) return;  // IPC not available: stay on NCCL
@@ -667,6 +681,7 @@ void project_full(conp_ctx *c, double *S, int nullneutral, int zneutr) {
   w.reserve(N);
   // first pass always evaluates e^T S e (reported even without neutralisation, fix_conp.cpp:986-1009)
   c->launches += launch_project(c->stream, N, S, N, nullptr, w.p, c->scal(3), nullneutral);
+  if (nullneutral) c->projected_here = true;
   double tot = 0;
   CUDA_CHECK(cudaMemcpyAsync(&tot, c->scal(3), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -700,6 +715,18 @@ void store_rows_from_full(conp_ctx *c, double *full) {
 extern "C" {
 
 int conp_abi_version(void) { return CONP_ABI_VERSION; }
+
+int conp_device_count(int *count_out) {
+  if (!count_out) return CONP_ERR_ARG;
+  int ndev = 0, ok = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) ndev = 0;
+  for (int d = 0; d < ndev; ++d) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major >= 10) ++ok;
+  }
+  *count_out = ok;
+  return ok > 0 ? CONP_OK : CONP_ERR_CUDA;
+}
 
 int conp_get_unique_id(void *id_out) {
   try {
@@ -752,7 +779,7 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
     c->d_scal.zero(16, c->stream);
-    c->d_partials.zero(2 * 1024, c->stream);
+    c->d_partials.zero(3 * 1024, c->stream);
     c->d_counter.zero(1, c->stream);
     c->h_value.reserve(64);
     c->use_graph = getenv("CONP_NO_GRAPH") == nullptr;
@@ -786,10 +813,7 @@ void conp_destroy(conp_ctx *c) {
   }
   if (c->solver) cusolverDnDestroy(c->solver);
   if (c->blas) cublasDestroy(c->blas);
-  if (c->p2p) {
-    c->d_b.release(); c->d_sb.release(); c->d_uhat.release(); c->d_packed.release();
-    p2p_destroy(c->p2p);
-  }
+  try { drop_p2p(c); } catch (...) {}
   comm_destroy(c->comm);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->sev) cudaEventDestroy(ev);
@@ -912,6 +936,10 @@ int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type,
     if (n_ele < 1 || !type || !side || !xyz) CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: empty electrode");
     if (n_ele > 65535) CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: n_ele > 65535 not supported");
     const int N = n_ele;
+    // b and S.b may be views into the exchange arena sized for the previous electrode: rebuild it
+    // (conp_post_neighbor must follow, it sizes the arena for the new vectors)
+    drop_p2p(c);
+    c->have_atoms = false;
     c->N = N;
     c->h_tag.assign(N, 0);
     if (tag) c->h_tag.assign(tag, tag + N);
@@ -975,6 +1003,11 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
   return guard(c, [&] {
     need(c->have_ele, "conp_pppm_setup: call conp_set_electrodes first");
     c->static_cells = false;  // the per-rank cell relevance mask depends on the slab of planes
+    // the output-plane spectra live in the exchange arena, whose size depends on the mesh: an arena built by
+    // an earlier conp_post_neighbor (the shim's hook order: setup_post_neighbor, then kspace->setup()) is
+    // dropped here and conp_post_neighbor must be called again before the next solve
+    drop_p2p(c);
+    c->have_atoms = false;
     if (order < 1 || order > 7) CONP_THROW(CONP_ERR_ARG, "conp_pppm_setup: PPPM order must be 1..7");
     for (int a = 0; a < 3; ++a)
       if (mesh[a] < order) CONP_THROW(CONP_ERR_ARG, "conp_pppm_setup: mesh smaller than the stencil");
@@ -1208,6 +1241,7 @@ int conp_build_A(conp_ctx *c) {
     c->build_ms = ms;
     c->have_A = true;
     c->inverted = false;
+    c->projected_here = false;
   });
 }
 
@@ -1219,8 +1253,13 @@ int conp_load_matrix(conp_ctx *c, const double *full, int is_inverse) {
     c->d_mat.zero((size_t)std::max(nr, 1) * c->pitch, c->stream);
     c->sym = false;
     c->asym_rel = -1.0;
-    if (is_inverse && c->sym_allowed && c->sym_plan_ok) {
-      // a ready-made inverse: look at the whole matrix once to see whether the symmetric product applies
+    c->projected_here = false;
+    c->d_fullS.release();
+    if (is_inverse) {
+      // a ready-made inverse: look at the whole matrix once to see whether the symmetric product applies.
+      // The full copy is kept until conp_invert_project / conp_set_unit_voltage know whether this is a
+      // one-electrode run, whose inv file holds the UNprojected inverse (fix_conp.cpp:958-977) and is
+      // projected after get_setq (:1115).
       DevBuf<double> F;
       F.upload(full, (size_t)N * N, c->stream);
       decide_symmetry(c, F.p, false);
@@ -1229,6 +1268,7 @@ int conp_load_matrix(conp_ctx *c, const double *full, int is_inverse) {
                                      (size_t)N * sizeof(double), (size_t)N * sizeof(double), nr,
                                      cudaMemcpyDeviceToDevice, c->stream));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      c->d_fullS.adopt(F);
     } else if (nr > 0) {
       CUDA_CHECK(cudaMemcpy2DAsync(c->d_mat.p, c->pitch * sizeof(double), full + (size_t)c->r0 * N,
                                    (size_t)N * sizeof(double), (size_t)N * sizeof(double), nr,
@@ -1311,9 +1351,10 @@ int conp_invert_project(conp_ctx *c, int nullneutral, int zneutr, int one_electr
       if (!c->one_electrode) project_full(c, c->d_fullS.p, nullneutral, zneutr);  // fix_conp.cpp:958
       store_rows_from_full(c, c->d_fullS.p);
       CUDA_CHECK(cudaStreamSynchronize(s));
-      if (!c->one_electrode) c->d_fullS.release();
       c->inverted = true;
     }
+    // the full copy is only needed for the deferred projection of a one-electrode run
+    if (!c->one_electrode) c->d_fullS.release();
     CUDA_CHECK(cudaEventRecord(c->ev[15], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     float ms = 0;
@@ -1342,10 +1383,24 @@ int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int
     CUDA_CHECK(cudaMemcpyAsync(setq.data(), c->d_setq.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(setz.data(), c->d_setz.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
+    // with the projection on, e^T S = 0 up to rounding: take that residual off S.d (see charge_epilogue)
+    // (only for a matrix projected here: an `inv` file is used exactly as given)
+    c->neutral_polish = nullneutral != 0 && (c->projected_here || (one_electrode && c->d_fullS.p));
+    c->n_left = 0;
+    c->sum_setz = 0;
     double tot = 0, zOAz = 0;
     for (int i = 0; i < N; ++i) {
-      if (c->h_side[i] == 1) tot += setq[i];  // :1098-1104
-      zOAz += setq[i] * setz[i];              // fix_cond.cpp:62
+      if (c->h_side[i] == 1) { tot += setq[i]; c->n_left++; }  // :1098-1104
+      zOAz += setq[i] * setz[i];                                  // fix_cond.cpp:62
+      c->sum_setz += setz[i];
+    }
+    if (c->neutral_polish) {
+      double mean = 0;
+      for (int i = 0; i < N; ++i) mean += setq[i];
+      mean /= N;
+      for (int i = 0; i < N; ++i) setq[i] -= mean;
+      CUDA_CHECK(cudaMemcpyAsync(c->d_setq.p, setq.data(), sizeof(double) * N, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
     }
     c->totsetq = tot;
     c->dd = -tot;
@@ -1374,12 +1429,10 @@ int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int
 
 // ---- per step --------------------------------------------------------------------
 
-int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type, const int *mask, int ele_bits,
-                       const int *counts) {
+int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type, const int *mask, int ele_bits) {
   return guard(c, [&] {
     need(c->have_ele && c->have_pair, "conp_post_neighbor: setup incomplete");
     if (nlocal < 0 || (nlocal > 0 && (!q || !type))) CONP_THROW(CONP_ERR_ARG, "conp_post_neighbor: bad arrays");
-    (void)counts;
     cudaStream_t s = c->stream;
     c->nlocal = nlocal;
     // charged non-electrode atoms; uncharged ones contribute exact zeros to every
@@ -1409,7 +1462,9 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     for (int r = 0; r < c->nranks; ++r) { tot += c->m_counts[r]; cmax = std::max(cmax, c->m_counts[r]); }
     c->m_total = tot;
     if (c->nranks > 1) {
-      c->mpad = cmax + 1;  // + the slot that carries sum(q z)
+      // + the slot that carries sum(q z); ~6 % head-room rounded to 1024 slots so that the arena (whose size
+      // depends on mpad) survives the small count changes of an ordinary reneighbouring
+      c->mpad = (int)round_up((size_t)cmax + 1 + (size_t)cmax / 16, 1024);
       c->m_slots = c->nranks * c->mpad;
       for (int r = 0; r < c->nranks; ++r) c->m_offsets[r] = r * c->mpad;
     } else {

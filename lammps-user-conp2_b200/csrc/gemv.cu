@@ -111,13 +111,15 @@ __device__ __forceinline__ double block_reduce_ordered(double v, double *sh, int
 
 // called by `nthreads` threads (tid 0..nthreads-1) of every block; a, z are the
 // thread's partial sums over rows of this block
-__device__ void charge_epilogue(const ChargeEpilogue &ep, double a, double z, int tid, int nthreads, int bar_id,
-                                double *sh /* >= nthreads doubles */, int *sh_flag) {
+__device__ void charge_epilogue(const ChargeEpilogue &ep, double a, double z, double e, int tid, int nthreads,
+                                int bar_id, double *sh /* >= nthreads doubles */, int *sh_flag) {
   const double pl = block_reduce_ordered(a, sh, tid, nthreads, bar_id);
   const double pz = block_reduce_ordered(z, sh, tid, nthreads, bar_id);
+  const double pe = block_reduce_ordered(e, sh, tid, nthreads, bar_id);
   if (tid == 0) {
-    ep.partials[2 * blockIdx.x] = pl;
-    ep.partials[2 * blockIdx.x + 1] = pz;
+    ep.partials[3 * blockIdx.x] = pl;
+    ep.partials[3 * blockIdx.x + 1] = pz;
+    ep.partials[3 * blockIdx.x + 2] = pe;
     __threadfence();
     const unsigned ticket = atomicAdd(ep.counter, 1u);
     *sh_flag = (ticket == gridDim.x - 1);
@@ -125,14 +127,23 @@ __device__ void charge_epilogue(const ChargeEpilogue &ep, double a, double z, in
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   if (!*sh_flag) return;
   __threadfence();
-  double ta = 0.0, tz = 0.0;
+  double ta = 0.0, tz = 0.0, te = 0.0;
   for (unsigned k = tid; k < gridDim.x; k += nthreads) {
-    ta += __ldcg(ep.partials + 2 * k);
-    tz += __ldcg(ep.partials + 2 * k + 1);
+    ta += __ldcg(ep.partials + 3 * k);
+    tz += __ldcg(ep.partials + 3 * k + 1);
+    te += __ldcg(ep.partials + 3 * k + 2);
   }
-  const double tot_left = block_reduce_ordered(ta, sh, tid, nthreads, bar_id);
-  const double tot_z = block_reduce_ordered(tz, sh, tid, nthreads, bar_id);
+  double tot_left = block_reduce_ordered(ta, sh, tid, nthreads, bar_id);
+  double tot_z = block_reduce_ordered(tz, sh, tid, nthreads, bar_id);
+  const double tot_all = block_reduce_ordered(te, sh, tid, nthreads, bar_id);
   if (tid == 0) {
+    // e^T S = 0 holds only to the rounding of the projection (fix_conp.cpp:1011-1020) and of the N-term
+    // sums: at N = 40 000 the charges add up to a few 1e-12 e.  With the projection on, that residual
+    // is taken off every charge evenly (~1e-16 e per atom), which keeps the total at the 1e-14 level.
+    const double mean = ep.neutral ? tot_all / ep.n : 0.0;
+    tot_left -= mean * ep.n_left;
+    tot_z -= mean * ep.sum_setz;
+    ep.scalar_out[13] = mean;
     const double value = __ldcg(ep.value);
     double potdiff, scalar;
     if (ep.variant == CONP_VARIANT_CONP) {  // fix_conp.cpp:1149-1159
@@ -267,14 +278,15 @@ gemv_tma_kernel(const double *__restrict__ S, size_t pitch, int nrows, int ncols
     double *scratch = &sm.st[0].tile[0][0];
     int *flag = reinterpret_cast<int *>(&sm.red[0][0][0]);
     asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
-    double a = 0.0, z = 0.0;
+    double a = 0.0, z = 0.0, e = 0.0;
     for (int r = row_a + tid; r < row_b; r += CONSUMERS) {
       const double v = out[r];
       const int gi = ep.row_offset + r;
       if (ep.side[gi] == 1) a += v;
       z = fma(ep.setz[gi], v, z);
+      e += v;
     }
-    charge_epilogue(ep, a, z, tid, CONSUMERS, 1, scratch, flag);
+    charge_epilogue(ep, a, z, e, tid, CONSUMERS, 1, scratch, flag);
   }
 }
 
@@ -285,13 +297,14 @@ __global__ void __launch_bounds__(UC_THREADS)
 update_charge_kernel(ChargeEpilogue ep) {
   __shared__ double sh[UC_THREADS];
   __shared__ int flag;
-  double a = 0.0, z = 0.0;
+  double a = 0.0, z = 0.0, e = 0.0;
   for (int i = blockIdx.x * UC_THREADS + threadIdx.x; i < ep.n; i += gridDim.x * UC_THREADS) {
     const double v = ep.sb[i];
     if (ep.side[i] == 1) a += v;
     z = fma(ep.setz[i], v, z);
+    e += v;
   }
-  charge_epilogue(ep, a, z, threadIdx.x, UC_THREADS, 0, sh, &flag);
+  charge_epilogue(ep, a, z, e, threadIdx.x, UC_THREADS, 0, sh, &flag);
 }
 
 // Several GPUs, symmetric matvec, peer-to-peer path: every rank's partial S.b sits in slot r of the
@@ -305,7 +318,7 @@ update_charge_sum_kernel(ChargeEpilogue ep, PeerSync ps, const double *__restric
   __shared__ int flag;
   peer_block_wait(ps);
   __syncthreads();
-  double a = 0.0, z = 0.0;
+  double a = 0.0, z = 0.0, e = 0.0;
   for (int i = blockIdx.x * UC_THREADS + threadIdx.x; i < len; i += gridDim.x * UC_THREADS) {
     double v = 0.0;
     for (int r = 0; r < ps.nranks; ++r) v += __ldcg(parts + (size_t)r * len + i);
@@ -313,9 +326,10 @@ update_charge_sum_kernel(ChargeEpilogue ep, PeerSync ps, const double *__restric
     if (i < ep.n) {
       if (ep.side[i] == 1) a += v;
       z = fma(ep.setz[i], v, z);
+      e += v;
     }
   }
-  charge_epilogue(ep, a, z, threadIdx.x, UC_THREADS, 0, sh, &flag);
+  charge_epilogue(ep, a, z, e, threadIdx.x, UC_THREADS, 0, sh, &flag);
 }
 
 // q_i = (S.b)_i + potdiff * setq_i (+ qinit_i): fix_conp.cpp:1153-1158
@@ -324,7 +338,7 @@ finalize_q_kernel(int n, const double *__restrict__ sb, const double *__restrict
                   const double *__restrict__ qinit, const double *__restrict__ scal, double *__restrict__ q_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double q = sb[i] + scal[1] * setq[i];
+  double q = (sb[i] - scal[13]) + scal[1] * setq[i];
   if (qinit) q += qinit[i];
   q_out[i] = q;
 }
@@ -594,7 +608,7 @@ symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restri
   const int H = N / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (out_len + 31) / 32;
-  double pa = 0.0, pz = 0.0;
+  double pa = 0.0, pz = 0.0, pe = 0.0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int c = tile * 32 + lane;
     double v = 0.0;
@@ -621,6 +635,7 @@ symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restri
         if (ep.enabled) {
           if (ep.side[c] == 1) pa += t;
           pz = fma(ep.setz[c], t, pz);
+          pe += t;
         }
       }
       if (ps.arena) {  // this rank's partial sum goes into slot `rank` of every rank's staging area
@@ -631,7 +646,7 @@ symv_reduce_kernel(int N, int out_len, int row0, int nrows, const int2 *__restri
     }
     __syncthreads();
   }
-  if (ep.enabled) charge_epilogue(ep, pa, pz, threadIdx.x, SR_THREADS, 0, sh, &flag);
+  if (ep.enabled) charge_epilogue(ep, pa, pz, pe, threadIdx.x, SR_THREADS, 0, sh, &flag);
   peer_block_signal(ps);
 }
 
@@ -694,7 +709,7 @@ int launch_symv(cudaStream_t s, const double *S, size_t pitch, int N, int row0, 
   if (ep) e = *ep;
   else memset(&e, 0, sizeof(e));
   int grid = (out_len + 31) / 32;
-  grid = grid < 1 ? 1 : (grid > 1024 ? 1024 : grid);  // epilogue partials: 2 per block, 1024 blocks max
+  grid = grid < 1 ? 1 : (grid > 1024 ? 1024 : grid);  // epilogue partials: 3 per block, 1024 blocks max
   symv_reduce_kernel<<<grid, SR_THREADS, 0, s>>>(N, out_len, row0, nrows, plan.strips, plan.nstrips, plan.L, rowpart,
                                                  colpart, out, e, push_parts, off_parts);
   CUDA_CHECK(cudaGetLastError());

@@ -387,7 +387,7 @@ ele_spread_kernel(PPPMGeom g, int n_ele, int row_begin, int row_end, const int *
   const int n = nm / order, m = nm - n * order;
   const double *w = weights + (size_t)i * 3 * order;
   const int *wi = widx + (size_t)i * 3 * order;
-  double qi = sb[i] + scal[1] * setq[i];
+  double qi = (sb[i] - scal[13]) + scal[1] * setq[i];
   if (qinit) qi += qinit[i];
   if (nm == 0) q_out[i] = qi;
   if (!mine) return;

@@ -275,7 +275,7 @@ void FixConpB200::setup_pre_force(int vflag)
 /* FixConp::post_neighbor (reference :468-539): static per-atom data of the locally owned atoms */
 void FixConpB200::post_neighbor()
 {
-  check(conp_post_neighbor(ctx, atom->nlocal, atom->q, atom->type, atom->mask, groupbit | jgroupbit, nullptr));
+  check(conp_post_neighbor(ctx, atom->nlocal, atom->q, atom->type, atom->mask, groupbit | jgroupbit));
 }
 
 /* FixConp::pre_force (reference :543-573) */

@@ -24,7 +24,7 @@ def test_header_symbols_all_exported(lib):
     assert sorted(abi.SYMBOLS) == declared
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.conp_abi_version() == 1
+    assert lib.conp_abi_version() == 2
 
 
 def test_no_cpu_fallback(lib):

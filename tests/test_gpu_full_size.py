@@ -66,3 +66,45 @@ def test_symmetric_product_equals_dense_product_of_the_same_matrix(cfg4):
     ref = S @ v
     got = cfg4.ctx.matvec(v)
     assert np.abs(got - ref).max() <= 1e-13 * np.abs(S).sum(axis=1).max() * np.abs(v).max()
+
+
+def _oracle_step_with_gpu_matrix(fix, name):
+    """The CPU oracle's per-step path (b_cal + update_charge) on the `inv`-file setup
+    (fix_conp.cpp:442-445) with the matrix this GPU built, on jittered positions."""
+    import conp_oracle as O
+    S = fix.ctx.get_matrix()
+    lmp2, arg2 = synthetic(name, mode="pppm", accuracy=1e-4)
+    ref = O.OracleFixConp(lmp2, arg2)
+    ref.setup_preinverted(S)
+    rng = np.random.default_rng(11)
+    x = lmp2.system.x[ref.oth_idx] + rng.normal(0.0, 0.05, (len(ref.oth_idx), 3))
+    lmp2.system.x[ref.oth_idx] = x
+    qr = ref.pre_force().copy()
+    fix.lmp.system.x[fix.owned] = x
+    q = fix.pre_force()
+    b, _ = fix.ctx.get_b()
+    assert np.abs(b - ref.bbb_all).max() <= 5e-11 * np.abs(ref.bbb_all).max()
+    assert np.abs(q - qr).max() <= 1e-9 * np.abs(qr).max() + 1e-12       # north_star: 1e-9 relative, 1e-12 e
+    assert abs(q.sum()) < 1e-12
+    assert abs(fix.scalar_output - ref.scalar_output) <= 1e-9 * abs(ref.scalar_output) + 1e-12
+    # electrode density handed to the force pass (pppm_conp.cpp:385-426)
+    rho_e = fix.ctx.get_density(1)
+    assert np.abs(rho_e - ref.ele_density).max() <= 1e-9 * np.abs(ref.ele_density).max() + 1e-15
+
+
+def test_cfg4_matches_oracle_with_gpu_built_matrix(cfg4):
+    _oracle_step_with_gpu_matrix(cfg4, "cfg4")
+
+
+def test_cfg5_headline_size_matches_oracle():
+    """BASELINE configs[4] (40 000 electrode atoms / 500 000 charges): the configuration bench.py is
+    quoted on.  Full setup on the GPU (Gram + inversion, ~90 s), then one jittered update against the oracle."""
+    lmp, arg = synthetic("cfg5", mode="pppm", accuracy=1e-4)
+    fix = make_fix(lmp, arg)
+    try:
+        fix.setup()
+        info = fix.ctx.info()
+        assert info.n_ele == 40000 and info.n_elyte == 500000 and info.symmetric_matvec == 1
+        _oracle_step_with_gpu_matrix(fix, "cfg5")
+    finally:
+        fix.close()

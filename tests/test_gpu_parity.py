@@ -214,6 +214,35 @@ def test_matrix_file_roundtrip(tmp_path, monkeypatch):
         f2.close()
 
 
+def test_one_electrode_inverse_file_is_projected_after_setq(tmp_path, monkeypatch):
+    """one_electrode + `inv <file>`: the file holds the UNprojected inverse (fix_conp.cpp:958-977) and the
+    projection runs after get_setq (:1115), also for a matrix that was read in."""
+    monkeypatch.chdir(tmp_path)
+
+    def case(extra):
+        lmp, arg = dilute(2)
+        lmp.group_molecule("eleleft", 81, 82)
+        arg[4] = "eleleft"
+        return lmp, arg + extra
+    lmp, arg = case(["matout"])
+    f0 = make_fix(lmp, arg)
+    f0.setup()
+    q0 = f0.pre_force()
+    f0.close()
+    lmp, arg = case(["inv", "inv_a_matrix"])
+    lmp2, arg2 = case(["inv", "inv_a_matrix"])
+    fix = make_fix(lmp, arg)
+    ref = O.OracleFixConp(lmp2, arg2)
+    fix.setup()
+    ref.setup()
+    q, qr = fix.pre_force(), ref.pre_force()
+    assert np.abs(fix.ctx.get_matrix() - ref.S).max() <= 1e-10 * np.abs(ref.S).max()
+    q_close(q, qr)
+    assert abs(q.sum()) < 1e-12                                   # projected: neutral again
+    assert np.abs(q - q0).max() <= 1e-6 * np.abs(q0).max()        # %20.10f text precision
+    fix.close()
+
+
 def test_step_is_repeatable_and_tracks_moving_atoms():
     lmp, arg = synthetic("small", h=1.25, accuracy=1e-4)
     lmp2, arg2 = synthetic("small", h=1.25, accuracy=1e-4)
