@@ -200,6 +200,13 @@ int conp_get_b(conp_ctx *ctx, double *b_out, double *b_kspace_out);
  * on the global periodic mesh [nz][ny][nx]; which = 0 electrolyte, 1 electrode,
  * 2 sum (what the host PPPM force pass consumes). */
 int conp_get_density(conp_ctx *ctx, int which, double *brick_out);
+/* The same hand-off for the part of the mesh ONE host rank owns -- what PPPMCONP::make_rho copies into its
+ * density_brick (pppm_conp.cpp:434-450): mesh indices lo[a] .. hi[a] inclusive per axis (x, y, z; inside
+ * [0, n)), out[(hi[2]-lo[2]+1)][(hi[1]-lo[1]+1)][(hi[0]-lo[0]+1)], x fastest.  No allocation per call and
+ * no full-mesh transfer: planes that hold no charge are written as zeros by the gather kernel, the
+ * device->host copy is the region only.  On several GPUs the ranks first exchange their z-slabs of the
+ * electrolyte density and add up the electrode density (once per solve). [collective] */
+int conp_get_density_region(conp_ctx *ctx, int which, const int lo[3], const int hi[3], double *out);
 /* u_brick (pppm_conp.cpp:260-266) for potential probes. */
 int conp_get_potential_brick(conp_ctx *ctx, double *brick_out);
 
@@ -236,6 +243,15 @@ int conp_matvec(conp_ctx *ctx, const double *v, double *out);
 int conp_plan_symv(int n, int row0, int nrows, int num_sms, int max_strips, int *strips_out, int *nstrips_out,
                    int *slice_len_out);
 int conp_bench_dgemm_tflops(conp_ctx *ctx, int n, double *tflops_out);
+/* Host-only (no GPU needed): the tile decomposition of the owner-computes PPPM spread (replaces the scatter
+ * loop of elyte_make_rho, pppm_conp.cpp:172-228) for a mesh / cell grid: geom_out[12] = {tz, ty, tx, ntz, nty,
+ * ntx, halo_z, halo_y, halo_x, ncx, ncy, ncz}; run_start_out[ntiles + 1] and runs_out[2 * nruns] list, per
+ * tile (z-major, x fastest), the [c0, c1) ranges of sort cells whose charges can reach the tile.  rc = the
+ * cell-grid search radius (cells are rc/2 wide), zin_lo/nzi/zs_lo/zs_n = plane pruning and slab of the rank. */
+int conp_plan_spread(const int mesh[3], int order, double shift, const double boxlo[3], const double prd[3],
+                     const int periodic[3], double slab_volfactor, double rc, int zin_lo, int nzi, int zs_lo,
+                     int zs_n, int num_sms, int *geom_out, int *run_start_out, int max_tiles, int *runs_out,
+                     int max_runs, int *ntiles_out, int *nruns_out);
 
 #ifdef __cplusplus
 }

@@ -26,9 +26,10 @@ SYMBOLS = [
     "conp_set_cell", "conp_set_ewald", "conp_set_pair", "conp_set_electrodes", "conp_pppm_setup", "conp_build_A",
     "conp_load_matrix", "conp_get_matrix", "conp_invert_project", "conp_set_unit_voltage", "conp_post_neighbor",
     "conp_pre_force", "conp_solve_device", "conp_get_charges", "conp_get_b", "conp_get_density",
+    "conp_get_density_region",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
-    "conp_matvec", "conp_plan_symv",
+    "conp_matvec", "conp_plan_symv", "conp_plan_spread",
 ]
 
 
@@ -59,6 +60,27 @@ def plan_symv(n, row0, nrows, num_sms=148):
     if ns.value < 0:
         return None
     return out[:ns.value].copy(), sl.value
+
+
+def plan_spread(mesh, order, shift, boxlo, prd, periodic, slab_volfactor, rc, zin_lo, nzi, zs_lo, zs_n, num_sms=148):
+    """Tile decomposition of the owner-computes PPPM spread (host-only entry point).  Returns a dict with the
+    tile geometry, the sort-cell grid and, per tile, the list of [c0, c1) candidate cell ranges."""
+    L = load_library()
+    m, lo, pr, pe = i32(mesh), f64(boxlo), f64(prd), i32(periodic)
+    geom = np.zeros(12, dtype=np.int32)
+    nt, nr = C.c_int(0), C.c_int(0)
+    args = (_ip(m), int(order), float(shift), _dp(lo), _dp(pr), _ip(pe), float(slab_volfactor), float(rc), int(zin_lo),
+            int(nzi), int(zs_lo), int(zs_n), int(num_sms))
+    rc_ = L.conp_plan_spread(*args, _ip(geom), None, 0, None, 0, C.byref(nt), C.byref(nr))
+    if rc_:
+        raise RuntimeError(f"conp_plan_spread: status {rc_}")
+    rs = np.zeros(nt.value + 1, dtype=np.int32)
+    rr = np.zeros((max(nr.value, 1), 2), dtype=np.int32)
+    L.conp_plan_spread(*args, _ip(geom), _ip(rs), nt.value, _ip(rr), nr.value, C.byref(nt), C.byref(nr))
+    keys = ("tz", "ty", "tx", "ntz", "nty", "ntx", "halo_z", "halo_y", "halo_x", "ncx", "ncy", "ncz")
+    out = {k: int(v) for k, v in zip(keys, geom)}
+    out.update(ntiles=nt.value, run_start=rs, runs=rr[:nr.value])
+    return out
 
 
 class ConpError(RuntimeError):
@@ -110,6 +132,7 @@ def load_library(path: str | None = None):
     L.conp_get_b.argtypes = [vp, c_dp, c_dp]
     L.conp_get_density.argtypes = [vp, C.c_int, c_dp]
     L.conp_get_potential_brick.argtypes = [vp, c_dp]
+    L.conp_get_density_region.argtypes = [vp, C.c_int, c_ip, c_ip, c_dp]
     L.conp_post_force.argtypes = [vp, C.c_double, c_dp, c_dp]
     L.conp_stream.argtypes = [vp]
     L.conp_stream.restype = vp
@@ -122,6 +145,9 @@ def load_library(path: str | None = None):
     L.conp_matvec.argtypes = [vp, c_dp, c_dp]
     L.conp_plan_symv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]
+    L.conp_plan_spread.argtypes = [c_ip, C.c_int, C.c_double, c_dp, c_dp, c_ip, C.c_double, C.c_double, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_ip, C.c_int,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]
     if path is None:
         _lib = L
     return L
@@ -280,6 +306,14 @@ class Context:
     def get_density(self, which):
         out = np.zeros(self.ngrid)
         self._ck(self.L.conp_get_density(self.h, int(which), _dp(out)))
+        return out
+
+    def get_density_region(self, which, lo, hi):
+        """Density on the sub-brick lo..hi (inclusive mesh indices x, y, z); returns [nz][ny][nx]."""
+        lo_, hi_ = i32(lo), i32(hi)
+        shape = tuple(int(hi_[a] - lo_[a] + 1) for a in (2, 1, 0))
+        out = np.zeros(shape)
+        self._ck(self.L.conp_get_density_region(self.h, int(which), _ip(lo_), _ip(hi_), _dp(out)))
         return out
 
     def get_potential_brick(self):

@@ -346,6 +346,25 @@ int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &p
 // rank's slab of input planes; m_bound = upper bound of the number of charges in that range
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
                        const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag);
+// Owner-computes form of the same spread (no atomics): the rank's slab of input planes is cut into tiles of
+// tz x ty x tx mesh points, one warp owns one tile at a time in its private shared memory and stores every
+// mesh point exactly once (also the zeros: no memset of the brick).  plan_pppm_spread_tiles works out, per
+// tile, which x-contiguous runs of cells can hold charges whose stencil reaches the tile.
+struct SpreadPlan {
+  int ntiles = 0, tz = 0, ty = 0, tx = 0, ntz = 0, nty = 0, ntx = 0;
+  int rs = 0, ps = 0;                 // shared-memory row / plane stride in doubles (bank-conflict padding)
+  int halo_z = 0, halo_y = 0, halo_x = 0;  // a tile that spans its whole axis keeps order-1 halo entries (folded on store)
+  const int *run_start = nullptr;     // device [ntiles + 1]
+  const int2 *runs = nullptr;         // device: [c0, c1) ranges of cell indices
+  int *counter = nullptr;             // device: tile scheduler, zeroed before every launch
+  size_t smem = 0;
+  int grid = 0;
+};
+void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sms, std::vector<int> &run_start,
+                            std::vector<int2> &runs, SpreadPlan &plan);
+int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan &plan,
+                             const double *rho_coeff_host /* order x order, host memory */, const PosQ *atoms,
+                             const int *cell_start, double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
 // rhat: spectra of the rank's nzl input planes (compact planes zs_lo..); uhat: (partial) output-plane spectra
 // Launch plan of the z-convolution (built once per rank by plan_pppm_zconv): narrow column groups stage
@@ -390,6 +409,10 @@ int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, int row_beg
                            const double *weights, const double *sb, const double *setq, const double *qinit,
                            const double *scal, double *q_out, double *brick);
 int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out);
+// out[z][y][x] over the sub-brick lo..hi (inclusive) of the periodic mesh: which = 0 electrolyte (compact
+// input planes, all nzi of them), 1 electrode (compact output planes), 2 sum
+int launch_region_gather(cudaStream_t s, const PPPMGeom &g, int which, const int lo[3], const int hi[3],
+                         const double *elyte, const double *ele, double *out);
 
 // ewald.cu -----------------------------------------------------------------
 void ewald_setup_host(EwaldHost &e, double g_ewald, double accuracy, double q2, long long natoms,
@@ -407,23 +430,27 @@ int launch_ewald_bextract(cudaStream_t s, int row_begin, int row_end, const doub
                           double slab_pref, const double *b_real, double *b_kspace, double *b);
 // k-major panel Pt[2*kc][ld]: rows kk / kc+kk = sqrt(2 u_k) {cos, sin}(k.r_i), k = k0+kk; segs = runs of
 // consecutive k with equal (kx,ky) inside the chunk
-// GEMM form of the structure-factor sum and of the b extraction (large systems), see ewald.cu
+// Tensor-core (FP64 DMMA) form of the structure-factor sum and of the b extraction (large systems), see
+// ewald.cu: both are one product of k-major operands through launch_tn_gemm (gram.cu)
 struct EwaldGemm {
-  int nkxy = 0, nkz1 = 0, chunk = 0;
+  int nkxy = 0, nkz1 = 0, chunk = 0, ksplit = 1, kz16 = 0;
   size_t np = 0;                           // nkxy * nkz1
+  size_t wa = 0, wb = 0, wr = 0;           // padded widths: [Fr | Fi], [Cz | Sz], electrode rows
+  size_t pslice = 0;                       // doubles per partial product (2 nkxy x wb)
   DevBuf<short> d_xk, d_yk;                // (kx, ky) of every distinct pair
   DevBuf<int> d_kxyof;                     // pair index of every listed k-vector
-  DevBuf<double> d_fr, d_fi, d_cz, d_sz;   // operands of one chunk of point charges
-  DevBuf<double> d_p, d_a, d_t;            // products P1..P4, combinations A1..A4, Tr/Ti
-  DevBuf<double> d_fxre, d_fxie, d_cze, d_sze;  // static electrode-side operands (own rows)
+  DevBuf<double> d_fa, d_zb;               // operands of one chunk of point charges (one k-row per charge)
+  DevBuf<double> d_p, d_a, d_t;            // partial products [ksplit], W combinations (k-major), [Tr | Ti]
+  DevBuf<double> d_fx, d_ze;               // static electrode-side operands (own rows): e_xy, E_z k-major
 };
-void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, cudaStream_t s);
+void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, int num_sms, cudaStream_t s);
 int ewald_gemm_electrodes(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin, int row_end,
                           const double2 *etab);
-int ewald_gemm_sfac(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int m, const PosQ *atoms,
+// partial S(k) over the sorted charges [j_begin, j_end)
+int ewald_gemm_sfac(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int j_begin, int j_end, const PosQ *atoms,
                     const double2 *tab, const short *kz, double *sfac);
-int ewald_gemm_bextract(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin,
-                        int row_end, const short *kz, const double *ug, const double *sfac, const double *ez,
+int ewald_gemm_bextract(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin, int row_end,
+                        const short *kz, const double *ug, const double *sfac, const double *ez,
                         const double *qz_sum, double slab_pref, const double *b_real, double *b_kspace, double *b);
 int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, int kymax, int kzmax, int k0,
                        int kc, int nseg, const int2 *segs, const short *kx, const short *ky, const short *kz,
@@ -435,6 +462,11 @@ int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, in
 int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
                            const double *panel_all, size_t ld, double *C, size_t pitch, int lower_only);
 int launch_gram_mirror(cudaStream_t s, int n, double *C, size_t pitch);
+// Same DMMA tile kernel as a general product of k-major operands: C[z][i][j] (+)= sum_{k in slice z} A[k][i] B[k][j],
+// i < m, j < n.  A (lda) and B (ldb) are zero-padded to multiples of 128 columns and kdim to a multiple of 16;
+// ksplit slices of k write separate output matrices slice_stride doubles apart.
+int launch_tn_gemm(cudaStream_t s, int m, int n, int kdim, const double *A, size_t lda, const double *B, size_t ldb,
+                   double *C, size_t pitch, int ksplit, size_t slice_stride, int accumulate);
 
 // linalg.cu ----------------------------------------------------------------
 int launch_a_finish(cudaStream_t s, int row_begin, int row_end, int n, double *A_rows, size_t pitch,

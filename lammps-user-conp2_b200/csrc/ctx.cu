@@ -51,11 +51,10 @@ struct conp_ctx {
   DevBuf<short> d_kx, d_ky, d_kz;
   DevBuf<double> d_ug, d_sfac;
   DevBuf<double2> d_etab, d_jtab;
-  // GEMM form of the Ewald sums: -1 automatic (large M*K), 0 never, 1 always (CONP_EWALD_GEMM)
+  // tensor-core form of the Ewald sums: -1 automatic (large M*K), 0 never, 1 always (CONP_EWALD_GEMM)
   EwaldGemm eg;
   int eg_mode = -1;
   bool eg_valid = false;
-  DevBuf<unsigned char> d_blas_ws;
 
   // pair -----------------------------------------------------------------
   int pairmode = 0, ntypes = 0, smartlist = 0;
@@ -118,10 +117,20 @@ struct conp_ctx {
   size_t ngrid = 0, nhalf = 0, plane = 0, ncol = 0;
   std::vector<double> h_ghalf;          // symmetrised greensfn/(nx ny nz), half spectrum (full-mesh path on demand)
   std::vector<int> h_zout;              // output planes (sorted)
+  std::vector<double> h_rho;            // rho_coeff [order][order] (kernel argument of the tile spread)
   DevBuf<double> d_rho, d_brick, d_ubrick, d_ebrick, d_weights, d_Kr;
+  // force-pass hand-off (conp_get_density_region): gathered bricks on several GPUs, staging of the region
+  DevBuf<double> d_brick_all, d_ebrick_all, d_region;
+  bool density_gathered = false;
   DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad, d_zc_wide, d_zc_aout;
   DevBuf<ZconvGroup> d_zc_narrow;
   ZconvPlan zplan;
+  // owner-computes spread (pppm.cu): tiles of the slab + candidate cell runs; CONP_SPREAD_ATOMIC=1 selects
+  // the red.global kernel of round 1 instead (A/B runs)
+  SpreadPlan splan;
+  DevBuf<int> d_sp_runstart, d_sp_counter;
+  DevBuf<int2> d_sp_runs;
+  bool spread_atomic = false;
   DevBuf<double> d_pw;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
@@ -241,6 +250,22 @@ void ensure_static_cells(conp_ctx *c) {
     if (c->pg.zs_n > 0) std::fill(rel.begin() + cz_lo * layer, rel.begin() + (cz_hi + 1) * layer, (unsigned char)1);
     c->d_relevant.upload(rel, c->stream);
     c->have_relevant = true;
+  }
+  if (c->have_pppm) {
+    std::vector<int> rs;
+    std::vector<int2> rr;
+    plan_pppm_spread_tiles(c->pg, c->grid_b, c->num_sms, rs, rr, c->splan);
+    if (rr.empty()) rr.push_back(make_int2(0, 0));
+    c->d_sp_runstart.upload(rs, c->stream);
+    c->d_sp_runs.upload(rr, c->stream);
+    c->d_sp_counter.zero(4, c->stream);
+    c->splan.run_start = c->d_sp_runstart.p;
+    c->splan.runs = c->d_sp_runs.p;
+    c->splan.counter = c->d_sp_counter.p;
+    if (c->debug)
+      fprintf(stderr, "[conp] rank %d spread tiles: %d x %d x %d tiles of %d x %d x %d (z,y,x), %zu cell runs, "
+              "%zu B smem per warp, grid %d\n", c->rank, c->splan.ntz, c->splan.nty, c->splan.ntx, c->splan.tz,
+              c->splan.ty, c->splan.tx, rr.size(), c->splan.smem, c->splan.grid);
   }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->static_cells = true;
@@ -376,7 +401,8 @@ bool use_ewald_gemm(const conp_ctx *c) {
 // operands and workspaces of the GEMM form (outside graph capture: allocates)
 void ensure_ewald_gemm(conp_ctx *c) {
   if (c->eg_valid) return;
-  ewald_gemm_plan(c->eg, c->ew, c->m_total, c->r1 - c->r0, c->stream);
+  // every rank sums its share of the charges (sfac_reduce, km_ewald.cpp:782-786)
+  ewald_gemm_plan(c->eg, c->ew, (c->m_total + c->nranks - 1) / c->nranks, c->r1 - c->r0, c->num_sms, c->stream);
   c->launches += ewald_gemm_electrodes(c->stream, c->eg, c->ew, c->r0, c->r1, c->d_etab.p);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->eg_valid = true;
@@ -402,7 +428,8 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     CUDA_CHECK(cudaStreamWaitEvent(t, c->ev_begin, 0));
   }
   if (kspace_mode == CONP_KSPACE_PPPM) {  // clears of the step's bricks, off the critical path
-    CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)std::max(c->pg.zs_n, 1) * c->plane, t));
+    if (c->spread_atomic)  // the tile kernel stores every point of the brick itself
+      CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)std::max(c->pg.zs_n, 1) * c->plane, t));
     CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), t));
     CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, t));
     if (fork) CUDA_CHECK(cudaEventRecord(c->ev_cleared, t));
@@ -483,7 +510,10 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
     auto kmark = [&](int i) { if (c->stage_timing && c->debug) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
     kmark(0);
-    if (!multi || c->periodic[2]) {
+    if (!c->spread_atomic) {
+      c->launches += launch_pppm_spread_tiles(s, pg, c->splan, c->h_rho.data(), c->d_sorted.p, c->d_cellstart.p,
+                                              c->d_brick.p, c->d_flag.p);
+    } else if (!multi || c->periodic[2]) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
                                         c->d_flag.p);
     } else {
@@ -526,18 +556,23 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   } else {
     const EwaldHost &e = c->ew;
     const bool gemm = use_ewald_gemm(c);
-    c->launches += launch_axis_tables(s, c->m_total, nullptr, nullptr, nullptr, c->d_sorted.p, e.unitk, e.kxmax,
-                                      e.kymax, e.kzmax, c->d_jtab.p);
+    // sincos_b + sfac_reduce (km_ewald.cpp:668-786): every rank holds all charges (sorted), sums the structure
+    // factors of its contiguous share of them and the partial S(k) are added across ranks
+    const int ja = (int)(((long long)c->m_total * c->rank) / c->nranks);
+    const int jb = (int)(((long long)c->m_total * (c->rank + 1)) / c->nranks);
+    const size_t T = (size_t)e.kxmax + e.kymax + e.kzmax + 3;
+    c->launches += launch_axis_tables(s, jb - ja, nullptr, nullptr, nullptr, c->d_sorted.p + ja, e.unitk, e.kxmax,
+                                      e.kymax, e.kzmax, c->d_jtab.p + (size_t)ja * T);
     if (gemm)
-      c->launches += ewald_gemm_sfac(c->blas, s, c->eg, e, c->m_total, c->d_sorted.p, c->d_jtab.p, c->d_kz.p,
-                                     c->d_sfac.p);
+      c->launches += ewald_gemm_sfac(s, c->eg, e, ja, jb, c->d_sorted.p, c->d_jtab.p, c->d_kz.p, c->d_sfac.p);
     else
-      c->launches += launch_ewald_sfac(s, c->m_total, c->d_sorted.p, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax,
-                                       e.kcount, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
+      c->launches += launch_ewald_sfac(s, jb - ja, c->d_sorted.p + ja, c->d_jtab.p + (size_t)ja * T, e.kxmax, e.kymax,
+                                       e.kzmax, e.kcount, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
+    if (multi) comm_allreduce_sum_f64(c->comm, c->d_sfac.p, 2 * (size_t)std::max(e.kcount, 1), s);
     stage_mark(c, 4);
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
     if (gemm)
-      c->launches += ewald_gemm_bextract(c->blas, s, c->eg, e, c->r0, c->r1, c->d_kz.p, c->d_ug.p, c->d_sfac.p,
+      c->launches += ewald_gemm_bextract(s, c->eg, e, c->r0, c->r1, c->d_kz.p, c->d_ug.p, c->d_sfac.p,
                                          c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p);
     else
       c->launches += launch_ewald_bextract(s, c->r0, c->r1, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, e.kcount,
@@ -649,6 +684,7 @@ void solve_device(conp_ctx *c, const double *x_dev, int kspace_mode, int variant
     CUDA_CHECK(cudaGraphLaunch(exec, s));
   }
   c->solved = true;
+  c->density_gathered = false;
   if (c->stage_timing) {
     CUDA_CHECK(cudaStreamSynchronize(s));
     for (int i = 0; i < NSTAGE; ++i) {
@@ -778,6 +814,7 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     if (getenv("CONP_EWALD_GEMM")) c->eg_mode = atoi(getenv("CONP_EWALD_GEMM")) != 0 ? 1 : 0;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
+    c->spread_atomic = getenv("CONP_SPREAD_ATOMIC") != nullptr && atoi(getenv("CONP_SPREAD_ATOMIC")) != 0;
     c->d_scal.zero(16, c->stream);
     c->d_partials.zero(3 * 1024, c->stream);
     c->d_counter.zero(1, c->stream);
@@ -787,11 +824,10 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     c->comm = comm_create(rank, nranks, unique_id);
     CUSOLVER_CHECK(cusolverDnCreate(&c->solver));
     CUSOLVER_CHECK(cusolverDnSetStream(c->solver, c->stream));
+    // cuBLAS only measures the DGEMM ceiling quoted next to the Gram (conp_bench_dgemm_tflops); no product
+    // path calls it
     CUBLAS_CHECK(cublasCreate(&c->blas));
     CUBLAS_CHECK(cublasSetStream(c->blas, c->stream));
-    // user-owned workspace: cuBLAS must not allocate while the step is being captured into a graph
-    c->d_blas_ws.reserve((size_t)64 << 20);
-    CUBLAS_CHECK(cublasSetWorkspace(c->blas, c->d_blas_ws.p, (size_t)64 << 20));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     *out = c;
     return CONP_OK;
@@ -1027,6 +1063,7 @@ int conp_pppm_setup(conp_ctx *c, const int mesh[3], int order, const double *rho
     cudaStream_t s = c->stream;
     std::vector<int> h_krad;
     c->d_rho.upload(rho_coeff, (size_t)order * order, s);
+    c->h_rho.assign(rho_coeff, rho_coeff + (size_t)order * order);
     // half-spectrum Green's function, symmetrised and pre-scaled by 1/(nx ny nz):
     // Re IFFT(G rho^) of the reference's complex transform (pppm_conp.cpp:235-266)
     // equals the real transform with G_sym(k) = (G(k) + G(-k))/2.
@@ -1384,8 +1421,9 @@ int conp_set_unit_voltage(conp_ctx *c, double evscale, const double *q_init, int
     CUDA_CHECK(cudaMemcpyAsync(setz.data(), c->d_setz.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     // with the projection on, e^T S = 0 up to rounding: take that residual off S.d (see charge_epilogue)
-    // (only for a matrix projected here: an `inv` file is used exactly as given)
-    c->neutral_polish = nullneutral != 0 && (c->projected_here || (one_electrode && c->d_fullS.p));
+    // (only for a matrix projected here: an `inv` file is used exactly as given; not for a single electrode,
+    // whose S.d comes from the unprojected inverse and does not sum to zero, fix_conp.cpp:1090-1115)
+    c->neutral_polish = nullneutral != 0 && !one_electrode && c->projected_here;
     c->n_left = 0;
     c->sum_setz = 0;
     double tot = 0, zOAz = 0;
@@ -1556,34 +1594,56 @@ int conp_get_b(conp_ctx *c, double *b_out, double *b_kspace_out) {
   });
 }
 
+int conp_get_density_region(conp_ctx *c, int which, const int lo[3], const int hi[3], double *out);
+
+// whole periodic mesh (diagnostic / single-rank hosts): the region hand-off with lo = 0, hi = n - 1
 int conp_get_density(conp_ctx *c, int which, double *brick_out) {
+  if (!c) return CONP_ERR_ARG;
+  const int lo[3] = {0, 0, 0};
+  const int hi[3] = {c->pg.nx - 1, c->pg.ny - 1, c->pg.nz - 1};
+  if (!c->have_pppm) {
+    c->err = "conp_get_density: no PPPM solve yet";
+    return CONP_ERR_STATE;
+  }
+  return conp_get_density_region(c, which, lo, hi, brick_out);
+}
+
+int conp_get_density_region(conp_ctx *c, int which, const int lo[3], const int hi[3], double *out) {
   return guard(c, [&] {
-    need(c->have_pppm && c->solved, "conp_get_density: no PPPM solve yet");
-    if (which < 0 || which > 2) CONP_THROW(CONP_ERR_ARG, "conp_get_density: which must be 0, 1 or 2");
-    cudaStream_t s = c->stream;
+    need(c->have_pppm && c->solved, "conp_get_density_region: no PPPM solve yet");
+    if (which < 0 || which > 2 || !lo || !hi || !out) CONP_THROW(CONP_ERR_ARG, "conp_get_density_region: bad arguments");
     const PPPMGeom &g = c->pg;
-    // the solver keeps only the planes that can be non-zero; expand to the full mesh here
-    DevBuf<double> full;
-    full.zero(c->ngrid, s);
-    if (which == 0 || which == 2) {
-      // every rank holds its slab of the electrolyte density; the sum of the expanded slabs is the brick
-      c->launches += launch_expand_planes(s, c->plane, g.zs_n, g.nz, g.zin_lo + g.zs_lo, nullptr, c->d_brick.p,
-                                          full.p);
-      if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);
+    const int n[3] = {g.nx, g.ny, g.nz};
+    for (int a = 0; a < 3; ++a)
+      if (lo[a] < 0 || hi[a] < lo[a] || hi[a] >= n[a])
+        CONP_THROW(CONP_ERR_ARG, "conp_get_density_region: region outside the mesh");
+    cudaStream_t s = c->stream;
+    const double *elyte = c->d_brick.p, *ele = c->d_ebrick.p;
+    if (c->nranks > 1) {
+      // once per solve: every rank's z-slab of the electrolyte density -> all nzi planes; the electrode
+      // density is the sum of the ranks' own rows
+      if (!c->density_gathered) {
+        c->d_brick_all.reserve((size_t)std::max(g.nzi, 1) * c->plane);
+        c->d_ebrick_all.reserve((size_t)std::max(g.nzo, 1) * c->plane);
+        std::vector<size_t> bytes(c->nranks), offs(c->nranks);
+        for (int r = 0; r < c->nranks; ++r) {
+          const int z0 = (int)(((long long)g.nzi * r) / c->nranks), z1 = (int)(((long long)g.nzi * (r + 1)) / c->nranks);
+          bytes[r] = (size_t)(z1 - z0) * c->plane * sizeof(double);
+          offs[r] = (size_t)z0 * c->plane * sizeof(double);
+        }
+        comm_allgatherv(c->comm, c->d_brick.p, c->d_brick_all.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
+        CUDA_CHECK(cudaMemcpyAsync(c->d_ebrick_all.p, c->d_ebrick.p, sizeof(double) * (size_t)g.nzo * c->plane,
+                                   cudaMemcpyDeviceToDevice, s));
+        comm_allreduce_sum_f64(c->comm, c->d_ebrick_all.p, (size_t)g.nzo * c->plane, s);
+        c->density_gathered = true;
+      }
+      elyte = c->d_brick_all.p;
+      ele = c->d_ebrick_all.p;
     }
-    if (which == 1) {
-      c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, full.p);
-      if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);  // ranks spread their own rows
-    }
-    if (which == 2) {
-      DevBuf<double> fe;
-      fe.zero(c->ngrid, s);
-      c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, fe.p);
-      if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, fe.p, c->ngrid, s);
-      c->launches += launch_add_bricks(s, c->ngrid, full.p, fe.p, full.p);
-      CUDA_CHECK(cudaStreamSynchronize(s));
-    }
-    CUDA_CHECK(cudaMemcpyAsync(brick_out, full.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, s));
+    const size_t cnt = (size_t)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+    c->d_region.reserve(cnt);
+    c->launches += launch_region_gather(s, g, which, lo, hi, elyte, ele, c->d_region.p);
+    CUDA_CHECK(cudaMemcpyAsync(out, c->d_region.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
   });
 }
@@ -1761,6 +1821,37 @@ int conp_plan_symv(int n, int row0, int nrows, int num_sms, int max_strips, int 
       strips_out[2 * s] = strips[s].x;
       strips_out[2 * s + 1] = strips[s].y;
     }
+  return CONP_OK;
+}
+
+int conp_plan_spread(const int mesh[3], int order, double shift, const double boxlo[3], const double prd[3],
+                     const int periodic[3], double slab_volfactor, double rc, int zin_lo, int nzi, int zs_lo,
+                     int zs_n, int num_sms, int *geom_out, int *run_start_out, int max_tiles, int *runs_out,
+                     int max_runs, int *ntiles_out, int *nruns_out) {
+  if (!mesh || !boxlo || !prd || !periodic || !geom_out || !ntiles_out || !nruns_out || order < 1 || order > 7)
+    return CONP_ERR_ARG;
+  PPPMGeom g;
+  std::memset(&g, 0, sizeof(g));
+  g.nx = mesh[0]; g.ny = mesh[1]; g.nz = mesh[2]; g.order = order;
+  g.nlower = -((order - 1) / 2);
+  const double prd_slab[3] = {prd[0], prd[1], prd[2] * slab_volfactor};
+  for (int a = 0; a < 3; ++a) { g.boxlo[a] = boxlo[a]; g.delinv[a] = mesh[a] / prd_slab[a]; }
+  g.shift = shift;
+  g.zin_lo = zin_lo; g.nzi = nzi; g.zs_lo = zs_lo; g.zs_n = zs_n;
+  const CellGrid cells = make_cell_grid(boxlo, prd, periodic, rc);
+  std::vector<int> rs;
+  std::vector<int2> rr;
+  SpreadPlan sp;
+  plan_pppm_spread_tiles(g, cells, num_sms, rs, rr, sp);
+  const int geom[12] = {sp.tz, sp.ty, sp.tx, sp.ntz, sp.nty, sp.ntx, sp.halo_z, sp.halo_y, sp.halo_x,
+                        cells.nc[0], cells.nc[1], cells.nc[2]};
+  std::memcpy(geom_out, geom, sizeof(geom));
+  *ntiles_out = sp.ntiles;
+  *nruns_out = (int)rr.size();
+  if (run_start_out)
+    for (int i = 0; i < (int)rs.size() && i <= max_tiles; ++i) run_start_out[i] = rs[i];
+  if (runs_out)
+    for (int i = 0; i < (int)rr.size() && i < max_runs; ++i) { runs_out[2 * i] = rr[i].x; runs_out[2 * i + 1] = rr[i].y; }
   return CONP_OK;
 }
 

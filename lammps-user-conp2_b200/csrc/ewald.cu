@@ -225,27 +225,34 @@ bextract_kernel(int row_begin, int row_end, const double2 *__restrict__ etab, in
 }
 
 // ---------------------------------------------------------------------------
-// GEMM form of the two O(M K) / O(N K) sums (large systems).  A k-vector's phase factorises,
+// Tensor-core form of the two O(M K) / O(N K) sums (large systems).  A k-vector's phase factorises,
 // exp(i k.r) = [E_x[kx] E_y[ky]] E_z[kz], and the k list is every (kx,ky) pair times a range of kz, so
 //     S(kxy, +-m) = sum_j f_j(kxy) E_z,j[m]^(+-1),   f_j(kxy) = q_j E_x,j[kx] E_y,j[ky]
 // is a (pairs x atoms) by (atoms x harmonics) matrix product.  With f = fr + i fi, E_z[m] = c + i s the
 // four real products P1 = Fr C^T, P2 = Fi S^T, P3 = Fr S^T, P4 = Fi C^T give both signs of kz:
 //     S(+m) = (P1 - P2) + i (P3 + P4),   S(-m) = (P1 + P2) + i (P4 - P3).
-// The products run as cuBLAS DGEMMs (plain library GEMMs on the FP64 tensor cores); the kernels below
-// build the operands from the per-atom axis tables and pick the listed k-vectors out of the result.
+// All four are blocks of ONE product [Fr | Fi]^T [C | S] of k-major operands (one row per point charge),
+// which is exactly the contraction the A-matrix Gram kernel does (gram.cu, FP64 DMMA): launch_tn_gemm
+// with the charge index as the contraction dimension, split over CTAs (and over ranks: every rank sums
+// its share of the charges, the partial S(k) are then added -- sfac_reduce, km_ewald.cpp:782-786).
 // The dense product also covers the (kxy, m) combinations outside the cut-off sphere (about half);
 // they are never read.  b extraction is the transposed problem with W_k = 2 u_k S_k:
 //     T_i(kxy) = sum_m [W(kxy,+m) conj(E_z,i[m]) + W(kxy,-m) E_z,i[m]],  b_i = -sum_kxy Re(conj(e_xy,i) T_i)
+// again one product, over the (harmonic, cos|sin) index: [Tr | Ti] = [Cz_e ; Sz_e]^T [A1 A3 ; A2 A4].
 // ---------------------------------------------------------------------------
-// operands of one chunk of point charges: Fr/Fi[j][nkxy], Cz/Sz[j][nkz1] (atom-major = column-major
-// (nkxy x chunk) and (nkz1 x chunk)); one block per atom
+// operands of one chunk of point charges, one block per charge (row): A row = [Fr | Fi], B row = [Cz | Sz];
+// rows jn .. (padding of the contraction dimension to 16) are zero
 __global__ void __launch_bounds__(128)
 eg_fill_atoms_kernel(int j0, int jn, const PosQ *__restrict__ atoms, const double2 *__restrict__ tab, int T, int kxmax,
                      int kymax, int nkxy, const short *__restrict__ xk, const short *__restrict__ yk, int nkz1,
-                     double *__restrict__ Fr, double *__restrict__ Fi, double *__restrict__ Cz,
-                     double *__restrict__ Sz) {
+                     double *__restrict__ FA, size_t wa, double *__restrict__ ZB, size_t wb) {
   const int jl = blockIdx.x;
-  if (jl >= jn) return;
+  double *fa = FA + (size_t)jl * wa, *zb = ZB + (size_t)jl * wb;
+  if (jl >= jn) {
+    for (int t = threadIdx.x; t < 2 * nkxy; t += blockDim.x) fa[t] = 0.0;
+    for (int m = threadIdx.x; m < 2 * nkz1; m += blockDim.x) zb[m] = 0.0;
+    return;
+  }
   const int j = j0 + jl;
   const double2 *row = tab + (size_t)j * T;
   const double q = atoms[j].q;  // q == 0 (km_ewald.cpp:686) gives exact zeros
@@ -254,22 +261,22 @@ eg_fill_atoms_kernel(int j0, int jn, const PosQ *__restrict__ atoms, const doubl
     const double2 ex = row[xk[t]];
     double2 ey = row[kxmax + 1 + (ky < 0 ? -ky : ky)];
     if (ky < 0) ey.y = -ey.y;
-    Fr[(size_t)jl * nkxy + t] = q * (ex.x * ey.x - ex.y * ey.y);
-    Fi[(size_t)jl * nkxy + t] = q * (ex.x * ey.y + ex.y * ey.x);
+    fa[t] = q * (ex.x * ey.x - ex.y * ey.y);
+    fa[nkxy + t] = q * (ex.x * ey.y + ex.y * ey.x);
   }
   for (int m = threadIdx.x; m < nkz1; m += blockDim.x) {
     const double2 ez = row[kxmax + kymax + 2 + m];
-    Cz[(size_t)jl * nkz1 + m] = ez.x;
-    Sz[(size_t)jl * nkz1 + m] = ez.y;
+    zb[m] = ez.x;
+    zb[nkz1 + m] = ez.y;
   }
 }
 
-// static electrode-side operands for the rows [row_begin, row_end): unit-charge e_xy and E_z tables
+// static electrode-side operands for the rows [row_begin, row_end): unit-charge e_xy (row-major, read by the
+// final reduction) and the E_z tables k-major: ZE[m][i] = cos, ZE[nkz1 + m][i] = sin (rows up to kz16 zero)
 __global__ void __launch_bounds__(128)
 eg_fill_electrodes_kernel(int row_begin, int nrows, const double2 *__restrict__ etab, int T, int kxmax, int kymax,
                           int nkxy, const short *__restrict__ xk, const short *__restrict__ yk, int nkz1,
-                          double *__restrict__ Fxr, double *__restrict__ Fxi, double *__restrict__ Cz,
-                          double *__restrict__ Sz) {
+                          double *__restrict__ FX, double *__restrict__ ZE, size_t wr) {
   const int il = blockIdx.x;
   if (il >= nrows) return;
   const double2 *row = etab + (size_t)(row_begin + il) * T;
@@ -278,61 +285,67 @@ eg_fill_electrodes_kernel(int row_begin, int nrows, const double2 *__restrict__ 
     const double2 ex = row[xk[t]];
     double2 ey = row[kxmax + 1 + (ky < 0 ? -ky : ky)];
     if (ky < 0) ey.y = -ey.y;
-    Fxr[(size_t)il * nkxy + t] = ex.x * ey.x - ex.y * ey.y;
-    Fxi[(size_t)il * nkxy + t] = ex.x * ey.y + ex.y * ey.x;
+    FX[(size_t)il * 2 * nkxy + t] = ex.x * ey.x - ex.y * ey.y;
+    FX[(size_t)il * 2 * nkxy + nkxy + t] = ex.x * ey.y + ex.y * ey.x;
   }
   for (int m = threadIdx.x; m < nkz1; m += blockDim.x) {
     const double2 ez = row[kxmax + kymax + 2 + m];
-    Cz[(size_t)il * nkz1 + m] = ez.x;
-    Sz[(size_t)il * nkz1 + m] = ez.y;
+    ZE[(size_t)m * wr + il] = ez.x;
+    ZE[(size_t)(nkz1 + m) * wr + il] = ez.y;
   }
 }
 
-// S(k) of the listed k-vectors out of the four products (column-major nkxy x nkz1, stride np apart)
+// S(k) of the listed k-vectors out of the product's four blocks; the ksplit partial products are added in
+// slice order (deterministic)
 __global__ void __launch_bounds__(256)
-eg_sfac_gather_kernel(int kcount, const int *__restrict__ kxyof, const short *__restrict__ kzs, int nkxy, size_t np,
-                      const double *__restrict__ P, double *__restrict__ sfac) {
+eg_sfac_gather_kernel(int kcount, const int *__restrict__ kxyof, const short *__restrict__ kzs, int nkxy, int nkz1,
+                      size_t wb, int ksplit, size_t slice, const double *__restrict__ P, double *__restrict__ sfac) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= kcount) return;
-  const int kz = kzs[k];
-  const size_t at = (size_t)kxyof[k] + (size_t)nkxy * (kz < 0 ? -kz : kz);
-  const double p1 = P[at], p2 = P[np + at], p3 = P[2 * np + at], p4 = P[3 * np + at];
+  const int kz = kzs[k], m = kz < 0 ? -kz : kz, a = kxyof[k];
+  double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+  for (int z = 0; z < ksplit; ++z) {
+    const double *Pz = P + (size_t)z * slice;
+    p1 += Pz[(size_t)a * wb + m];
+    p3 += Pz[(size_t)a * wb + nkz1 + m];
+    p4 += Pz[(size_t)(nkxy + a) * wb + m];
+    p2 += Pz[(size_t)(nkxy + a) * wb + nkz1 + m];
+  }
   sfac[2 * (size_t)k] = kz >= 0 ? p1 - p2 : p1 + p2;
   sfac[2 * (size_t)k + 1] = kz >= 0 ? p3 + p4 : p4 - p3;
 }
 
-// W_k = 2 u_k S_k scattered into the four combinations the transposed products need (A zeroed
-// before): A1 = Wr+ + Wr-, A2 = Wi+ - Wi-, A3 = Wi+ + Wi-, A4 = Wr- - Wr+.  An entry receives at most
-// two addends (kz = +-m), so the atomic sum does not depend on their order.
+// W_k = 2 u_k S_k scattered into the four combinations the transposed product needs (A zeroed before),
+// k-major over (harmonic, cos|sin): rows m pair with cos E_z, rows nkz1 + m with sin E_z; columns a give
+// Tr, columns nkxy + a give Ti:  A1 = Wr+ + Wr-, A2 = Wi+ - Wi-, A3 = Wi+ + Wi-, A4 = Wr- - Wr+.  An entry
+// receives at most two addends (kz = +-m), so the atomic sum does not depend on their order.
 __global__ void __launch_bounds__(256)
-eg_scatter_w_kernel(int kcount, const int *__restrict__ kxyof, const short *__restrict__ kzs, int nkxy, size_t np,
-                    const double *__restrict__ ug, const double *__restrict__ sfac, double *__restrict__ A) {
+eg_scatter_w_kernel(int kcount, const int *__restrict__ kxyof, const short *__restrict__ kzs, int nkxy, int nkz1,
+                    size_t wa, const double *__restrict__ ug, const double *__restrict__ sfac, double *__restrict__ A) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= kcount) return;
-  const int kz = kzs[k];
-  const size_t at = (size_t)kxyof[k] + (size_t)nkxy * (kz < 0 ? -kz : kz);
+  const int kz = kzs[k], m = kz < 0 ? -kz : kz, a = kxyof[k];
   const double u2 = 2.0 * ug[k];
   const double wr = u2 * sfac[2 * (size_t)k], wi = u2 * sfac[2 * (size_t)k + 1];
-  atomicAdd(A + at, wr);
-  atomicAdd(A + np + at, kz >= 0 ? wi : -wi);
-  atomicAdd(A + 2 * np + at, wi);
-  atomicAdd(A + 3 * np + at, kz >= 0 ? -wr : wr);
+  atomicAdd(A + (size_t)m * wa + a, wr);
+  atomicAdd(A + (size_t)(nkz1 + m) * wa + a, kz >= 0 ? wi : -wi);
+  atomicAdd(A + (size_t)m * wa + nkxy + a, wi);
+  atomicAdd(A + (size_t)(nkz1 + m) * wa + nkxy + a, kz >= 0 ? -wr : wr);
 }
 
 // b_i = -sum_kxy (e_xy,r Tr + e_xy,i Ti) - z_i * slabcorr ; b = b_k + b_real.  One warp per row.
 __global__ void __launch_bounds__(256)
-eg_b_reduce_kernel(int row_begin, int nrows, int nkxy, const double *__restrict__ Fxr, const double *__restrict__ Fxi,
-                   const double *__restrict__ Tr, const double *__restrict__ Ti, const double *__restrict__ ez,
-                   const double *__restrict__ qz_sum, double slab_pref, const double *__restrict__ b_real,
-                   double *__restrict__ b_kspace, double *__restrict__ b) {
+eg_b_reduce_kernel(int row_begin, int nrows, int nkxy, const double *__restrict__ FX, const double *__restrict__ Tm,
+                   size_t wa, const double *__restrict__ ez, const double *__restrict__ qz_sum, double slab_pref,
+                   const double *__restrict__ b_real, double *__restrict__ b_kspace, double *__restrict__ b) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int il = blockIdx.x * 8 + warp;
   if (il >= nrows) return;
-  const size_t o = (size_t)il * nkxy;
+  const double *fx = FX + (size_t)il * 2 * nkxy, *tr = Tm + (size_t)il * wa;
   double acc = 0.0;
   for (int t = lane; t < nkxy; t += 32) {
-    acc = fma(Fxr[o + t], Tr[o + t], acc);
-    acc = fma(Fxi[o + t], Ti[o + t], acc);
+    acc = fma(fx[t], tr[t], acc);
+    acc = fma(fx[nkxy + t], tr[nkxy + t], acc);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -416,8 +429,12 @@ int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, in
   return 1;
 }
 
-// ---- GEMM form: host side ---------------------------------------------------------------------------
-void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, cudaStream_t s) {
+// ---- tensor-core form: host side -------------------------------------------------------------------
+namespace {
+size_t up_to(size_t v, size_t m) { return (v + m - 1) / m * m; }
+}  // namespace
+
+void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, int num_sms, cudaStream_t s) {
   // distinct (kx, ky) pairs in list order (the list is (kx, ky) major, kz minor)
   std::vector<short> xk, yk;
   std::vector<int> kxyof(e.kcount);
@@ -436,23 +453,29 @@ void ewald_gemm_plan(EwaldGemm &g, const EwaldHost &e, int m_total, int nrows, c
   g.d_xk.upload(xk, s);
   g.d_yk.upload(yk, s);
   g.d_kxyof.upload(kxyof, s);
-  // chunk of point charges whose operands fit ~1 GB
-  const size_t per_atom = sizeof(double) * 2 * ((size_t)g.nkxy + g.nkz1);
-  size_t chunk = ((size_t)1 << 30) / std::max<size_t>(per_atom, 1);
-  chunk = std::max<size_t>(1024, chunk / 256 * 256);
-  g.chunk = (int)std::min<size_t>(chunk, (size_t)std::max(m_total, 1));
-  g.d_fr.reserve((size_t)g.chunk * g.nkxy);
-  g.d_fi.reserve((size_t)g.chunk * g.nkxy);
-  g.d_cz.reserve((size_t)g.chunk * g.nkz1);
-  g.d_sz.reserve((size_t)g.chunk * g.nkz1);
-  g.d_p.reserve(4 * std::max<size_t>(g.np, 1));
-  g.d_a.reserve(4 * std::max<size_t>(g.np, 1));
+  g.wa = up_to(2 * (size_t)std::max(g.nkxy, 1), 128);
+  g.wb = up_to(2 * (size_t)g.nkz1, 128);
+  g.kz16 = (int)up_to(2 * (size_t)g.nkz1, 16);
   const size_t nr = (size_t)std::max(nrows, 1);
-  g.d_t.reserve(2 * nr * g.nkxy);
-  g.d_fxre.reserve(nr * g.nkxy);
-  g.d_fxie.reserve(nr * g.nkxy);
-  g.d_cze.reserve(nr * g.nkz1);
-  g.d_sze.reserve(nr * g.nkz1);
+  g.wr = up_to(nr, 128);
+  // chunk of point charges whose operands fit ~1 GB; multiple of 16 (contraction tile)
+  const size_t per_atom = sizeof(double) * (g.wa + g.wb);
+  size_t chunk = ((size_t)1 << 30) / per_atom;
+  chunk = std::max<size_t>(1024, chunk / 256 * 256);
+  g.chunk = (int)std::min<size_t>(chunk, up_to((size_t)std::max(m_total, 1), 16));
+  // split the charge dimension over CTAs so that the grid is one full wave (the tile kernel runs one CTA
+  // per SM), with at least 8 contraction tiles per slice
+  const size_t tiles = (g.wa / 128) * (g.wb / 128);
+  const int want = (int)((size_t)num_sms / tiles);
+  g.ksplit = std::max(1, std::min(std::min(want, 64), std::max(g.chunk / 128, 1)));
+  g.pslice = 2 * (size_t)std::max(g.nkxy, 1) * g.wb;
+  g.d_fa.zero((size_t)g.chunk * g.wa, s);
+  g.d_zb.zero((size_t)g.chunk * g.wb, s);
+  g.d_p.zero((size_t)g.ksplit * g.pslice, s);
+  g.d_a.zero((size_t)g.kz16 * g.wa, s);
+  g.d_ze.zero((size_t)g.kz16 * g.wr, s);
+  g.d_t.zero(nr * g.wa, s);
+  g.d_fx.zero(nr * 2 * (size_t)std::max(g.nkxy, 1), s);
 }
 
 int ewald_gemm_electrodes(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin, int row_end,
@@ -461,71 +484,56 @@ int ewald_gemm_electrodes(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int 
   if (n <= 0 || g.nkxy <= 0) return 0;
   const int T = e.kxmax + e.kymax + e.kzmax + 3;
   eg_fill_electrodes_kernel<<<n, 128, 0, s>>>(row_begin, n, etab, T, e.kxmax, e.kymax, g.nkxy, g.d_xk.p, g.d_yk.p,
-                                              g.nkz1, g.d_fxre.p, g.d_fxie.p, g.d_cze.p, g.d_sze.p);
+                                              g.nkz1, g.d_fx.p, g.d_ze.p, g.wr);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int ewald_gemm_sfac(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int m, const PosQ *atoms,
+int ewald_gemm_sfac(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int j_begin, int j_end, const PosQ *atoms,
                     const double2 *tab, const short *kz, double *sfac) {
   if (e.kcount <= 0) return 0;
+  const int m = j_end - j_begin;
   if (m <= 0) {
     CUDA_CHECK(cudaMemsetAsync(sfac, 0, sizeof(double) * 2 * (size_t)e.kcount, s));  // km_ewald.cpp:160-161
     return 0;
   }
   const int T = e.kxmax + e.kymax + e.kzmax + 3;
-  const double one = 1.0, zero = 0.0;
   int launched = 0;
-  double *P1 = g.d_p.p, *P2 = P1 + g.np, *P3 = P2 + g.np, *P4 = P3 + g.np;
   for (int j0 = 0; j0 < m; j0 += g.chunk) {
     const int jn = std::min(g.chunk, m - j0);
-    eg_fill_atoms_kernel<<<jn, 128, 0, s>>>(j0, jn, atoms, tab, T, e.kxmax, e.kymax, g.nkxy, g.d_xk.p, g.d_yk.p,
-                                            g.nkz1, g.d_fr.p, g.d_fi.p, g.d_cz.p, g.d_sz.p);
+    const int jn16 = (int)up_to(jn, 16);
+    eg_fill_atoms_kernel<<<jn16, 128, 0, s>>>(j_begin + j0, jn, atoms, tab, T, e.kxmax, e.kymax, g.nkxy, g.d_xk.p,
+                                              g.d_yk.p, g.nkz1, g.d_fa.p, g.wa, g.d_zb.p, g.wb);
     CUDA_CHECK(cudaGetLastError());
-    const double *beta = j0 == 0 ? &zero : &one;
-    // P (nkxy x nkz1, column-major) (+)= F (nkxy x jn) * Z^T, Z stored as (nkz1 x jn) column-major
-    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fr.p, g.nkxy, g.d_cz.p,
-                             g.nkz1, beta, P1, g.nkxy));
-    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fi.p, g.nkxy, g.d_sz.p,
-                             g.nkz1, beta, P2, g.nkxy));
-    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fr.p, g.nkxy, g.d_sz.p,
-                             g.nkz1, beta, P3, g.nkxy));
-    CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_T, g.nkxy, g.nkz1, jn, &one, g.d_fi.p, g.nkxy, g.d_cz.p,
-                             g.nkz1, beta, P4, g.nkxy));
-    launched += 5;
+    // P[z] (2 nkxy x 2 nkz1) (+)= [Fr | Fi]^T [Cz | Sz] over the charges of slice z
+    launched += 1 + launch_tn_gemm(s, 2 * g.nkxy, 2 * g.nkz1, jn16, g.d_fa.p, g.wa, g.d_zb.p, g.wb, g.d_p.p, g.wb,
+                                   g.ksplit, g.pslice, j0 > 0);
   }
-  eg_sfac_gather_kernel<<<(e.kcount + 255) / 256, 256, 0, s>>>(e.kcount, g.d_kxyof.p, kz, g.nkxy, g.np, g.d_p.p, sfac);
+  eg_sfac_gather_kernel<<<(e.kcount + 255) / 256, 256, 0, s>>>(e.kcount, g.d_kxyof.p, kz, g.nkxy, g.nkz1, g.wb,
+                                                               g.ksplit, g.pslice, g.d_p.p, sfac);
   CUDA_CHECK(cudaGetLastError());
   return launched + 1;
 }
 
-int ewald_gemm_bextract(cublasHandle_t blas, cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin,
-                        int row_end, const short *kz, const double *ug, const double *sfac, const double *ez,
+int ewald_gemm_bextract(cudaStream_t s, EwaldGemm &g, const EwaldHost &e, int row_begin, int row_end,
+                        const short *kz, const double *ug, const double *sfac, const double *ez,
                         const double *qz_sum, double slab_pref, const double *b_real, double *b_kspace, double *b) {
   const int n = row_end - row_begin;
   if (n <= 0) return 0;
-  const double one = 1.0, zero = 0.0;
-  CUDA_CHECK(cudaMemsetAsync(g.d_a.p, 0, sizeof(double) * 4 * g.np, s));
+  CUDA_CHECK(cudaMemsetAsync(g.d_a.p, 0, sizeof(double) * (size_t)g.kz16 * g.wa, s));
+  int launched = 0;
   if (e.kcount > 0) {
-    eg_scatter_w_kernel<<<(e.kcount + 255) / 256, 256, 0, s>>>(e.kcount, g.d_kxyof.p, kz, g.nkxy, g.np, ug, sfac,
-                                                               g.d_a.p);
+    eg_scatter_w_kernel<<<(e.kcount + 255) / 256, 256, 0, s>>>(e.kcount, g.d_kxyof.p, kz, g.nkxy, g.nkz1, g.wa, ug,
+                                                               sfac, g.d_a.p);
     CUDA_CHECK(cudaGetLastError());
+    ++launched;
   }
-  double *A1 = g.d_a.p, *A2 = A1 + g.np, *A3 = A2 + g.np, *A4 = A3 + g.np;
-  double *Tr = g.d_t.p, *Ti = Tr + (size_t)n * g.nkxy;
-  // T (nkxy x n, column-major) = A (nkxy x nkz1) * Z_e (nkz1 x n)
-  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A1, g.nkxy, g.d_cze.p, g.nkz1,
-                           &zero, Tr, g.nkxy));
-  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A2, g.nkxy, g.d_sze.p, g.nkz1,
-                           &one, Tr, g.nkxy));
-  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A3, g.nkxy, g.d_cze.p, g.nkz1,
-                           &zero, Ti, g.nkxy));
-  CUBLAS_CHECK(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, g.nkxy, n, g.nkz1, &one, A4, g.nkxy, g.d_sze.p, g.nkz1,
-                           &one, Ti, g.nkxy));
-  eg_b_reduce_kernel<<<(n + 7) / 8, 256, 0, s>>>(row_begin, n, g.nkxy, g.d_fxre.p, g.d_fxie.p, Tr, Ti, ez, qz_sum,
-                                                 slab_pref, b_real, b_kspace, b);
+  // [Tr | Ti] (n x 2 nkxy) = [Cz_e ; Sz_e]^T (n x kz16) . A (kz16 x 2 nkxy)
+  launched += launch_tn_gemm(s, n, 2 * g.nkxy, g.kz16, g.d_ze.p, g.wr, g.d_a.p, g.wa, g.d_t.p, g.wa, 1, 0, 0);
+  eg_b_reduce_kernel<<<(n + 7) / 8, 256, 0, s>>>(row_begin, n, g.nkxy, g.d_fx.p, g.d_t.p, g.wa, ez, qz_sum, slab_pref,
+                                                 b_real, b_kspace, b);
   CUDA_CHECK(cudaGetLastError());
-  return 6;
+  return launched + 1;
 }
 
 

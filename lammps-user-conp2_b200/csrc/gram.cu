@@ -11,6 +11,8 @@
 // 3-stage cp.async pipeline.  Bound: FP64 tensor pipe; flops = 2*nrows*n*kdim.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace conp {
 
 namespace {
@@ -41,19 +43,26 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// panel_r: k-major panel whose columns are this rank's rows (pointer already
-// offset to row_begin); panel_a: same panel from column 0.  Both are padded
-// with zeros to multiples of the tile, so loads need no bounds checks.
+// C[i][j] (+)= sum_k A[k][i] B[k][j] for k-major operands (row k of A holds column k of A^T): the general
+// form of the Gram contraction.  panel_r / panel_a: the two operands (for the Gram both point into the same
+// panel: its columns of this rank's rows, and all columns), lda / ldb doubles per k-row.  Both are padded
+// with zeros to multiples of the tile, so loads need no bounds checks.  gridDim.z splits the k range:
+// slice z handles a contiguous range of k-tiles and writes its own output matrix Cmat + z * slice_stride
+// (partial sums, added up by the consumer in a fixed order).  accumulate == 0 overwrites C.
 __global__ void __launch_bounds__(THREADS, 1)
 gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, const double *__restrict__ panel_a,
-            size_t ld, double *__restrict__ Cmat, size_t pitch, int lower_only) {
+            size_t lda, size_t ldb, double *__restrict__ Cmat, size_t pitch, size_t slice_stride, int lower_only,
+            int accumulate) {
   if (lower_only && blockIdx.x > blockIdx.y) return;  // tile strictly above the diagonal: mirrored later
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GramSmem &sm = *reinterpret_cast<GramSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps -> 64 x 32 per warp
   const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
-  const int nk = kdim / BK;
+  const int nk_all = kdim / BK;
+  const int kt0 = (int)(((long long)nk_all * blockIdx.z) / gridDim.z);
+  const int nk = (int)(((long long)nk_all * (blockIdx.z + 1)) / gridDim.z) - kt0;
+  Cmat += (size_t)blockIdx.z * slice_stride;
 
   double acc[8][4][2];
 #pragma unroll
@@ -68,9 +77,9 @@ gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, cons
       const int chunk = tid + c * THREADS;  // 0..1023
       const int kr = chunk >> 6;            // 64 chunks per k-row
       const int col = (chunk & 63) * 2;
-      const size_t goff = (size_t)(kt * BK + kr) * ld;
-      cp_async16(&sm.a[st][kr][col], panel_r + goff + i0 + col);
-      cp_async16(&sm.b[st][kr][col], panel_a + goff + j0 + col);
+      const size_t krow = (size_t)((kt0 + kt) * BK + kr);
+      cp_async16(&sm.a[st][kr][col], panel_r + krow * lda + i0 + col);
+      cp_async16(&sm.b[st][kr][col], panel_a + krow * ldb + j0 + col);
     }
   };
 
@@ -112,12 +121,12 @@ gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, cons
       const int j = j0 + wn * 32 + b * 8 + 2 * fk;
       double *p = Cmat + (size_t)i * pitch + j;
       if (j + 1 < n) {
-        double2 v = *reinterpret_cast<double2 *>(p);
+        double2 v = accumulate ? *reinterpret_cast<double2 *>(p) : make_double2(0.0, 0.0);
         v.x += acc[a][b][0];
         v.y += acc[a][b][1];
         *reinterpret_cast<double2 *>(p) = v;
       } else if (j < n) {
-        p[0] += acc[a][b][0];
+        p[0] = (accumulate ? p[0] : 0.0) + acc[a][b][0];
       }
     }
   }
@@ -156,8 +165,21 @@ int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const dou
   if (kdim % BK) CONP_THROW(CONP_ERR_ARG, "gram: kdim must be a multiple of %d", BK);
   ensure_dynamic_smem(gram_kernel, sizeof(GramSmem));
   dim3 grid((n + BN - 1) / BN, (nrows + BM - 1) / BM);
-  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, C, pitch,
-                                                      lower_only);
+  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, ld, C, pitch, 0,
+                                                      lower_only, 1);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_tn_gemm(cudaStream_t s, int m, int n, int kdim, const double *A, size_t lda, const double *B, size_t ldb,
+                   double *C, size_t pitch, int ksplit, size_t slice_stride, int accumulate) {
+  if (m <= 0 || n <= 0 || kdim <= 0) return 0;
+  if (kdim % BK) CONP_THROW(CONP_ERR_ARG, "tn_gemm: kdim must be a multiple of %d", BK);
+  if (pitch % 2) CONP_THROW(CONP_ERR_ARG, "tn_gemm: pitch must be even");
+  ensure_dynamic_smem(gram_kernel, sizeof(GramSmem));
+  dim3 grid((n + BN - 1) / BN, (m + BM - 1) / BM, std::max(ksplit, 1));
+  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(m, n, kdim, A, B, lda, ldb, C, pitch, slice_stride, 0,
+                                                      accumulate);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

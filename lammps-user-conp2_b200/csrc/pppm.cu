@@ -26,6 +26,8 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace conp {
@@ -103,6 +105,248 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
       atomicAdd(row + mx, x0 * rho1d(rc, order, l, dx));
       mx = (mx + 1 == g.nx) ? 0 : mx + 1;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Owner-computes spread (the per-step default): no atomics, every mesh point stored exactly once.
+//
+// The rank's slab of input planes is cut into tiles of tz x ty x tx points.  One warp (= one CTA) owns a
+// tile at a time, accumulated in its private shared memory: a warp never shares a tile, so plain
+// load / FMA / store replaces the 125 red.global per charge of spread_kernel (the SM's red issue rate,
+// ~1.3 cycles per lane, was that kernel's bound; shared-memory atomics are slower still).  For every tile the
+// host has listed the x-contiguous runs of cells whose charges can reach it (plan_pppm_spread_tiles); the
+// warp reads those charges 32 at a time, each lane works out its charge's stencil origin relative to the
+// tile and its 3 x order weights (into a per-lane scratch row), and the charges that overlap are then
+// visited one after another by the whole warp: lane (m, l) owns the point (y0 + m, x0 + l) of the
+// stencil footprint and walks the valid z-planes (a charge straddling a tile border is visited by both
+// tiles, each adding only its own points).  Positions inside the tile are affine in the stencil index:
+// a tile that spans a whole periodic axis carries order-1 halo entries that are folded back before the
+// store, any other tile is so much shorter than the mesh that the valid indices form one interval.
+// Summation order is the order of the sorted charges: deterministic for a given sort.
+// ---------------------------------------------------------------------------
+// RS_ / PS_: compile-time row / plane strides of the default tile shape (0: run-time strides from the plan),
+// so that the five plane accesses of a visit are immediate offsets from one address.
+struct RhoCoeff {  // by-value kernel argument: the Horner coefficients come from the constant bank
+  double c[MAXORDER * MAXORDER];
+};
+
+template <int P>
+__device__ __forceinline__ double rho1d_c(const RhoCoeff &rc, int k, double d) {
+  double r = 0.0;
+#pragma unroll
+  for (int l = P - 1; l >= 0; --l) r = rc.c[l * P + k] + r * d;
+  return r;
+}
+
+// v in [-2n, 2n) -> [0, n) without an integer division
+__device__ __forceinline__ int wrap2(int v, int n) {
+  v += (v < 0) ? n : 0;
+  v += (v < 0) ? n : 0;
+  v -= (v >= n) ? n : 0;
+  return v;
+}
+
+template <int P, int RS_, int PS_>
+__global__ void __launch_bounds__(32)
+spread_tile_kernel(PPPMGeom g, SpreadPlan sp, RhoCoeff rc, const PosQ *__restrict__ atoms,
+                   const int *__restrict__ cell_start, double *__restrict__ brick, int *__restrict__ range_flag) {
+  constexpr int P2 = P * P;
+  constexpr int NR = (P2 + 31) / 32;
+  constexpr int WS = (3 * P) | 1;  // odd stride: the 32 scratch rows fall into distinct banks
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char spt_smem[];
+  double *tile = reinterpret_cast<double *>(spt_smem);
+  const int az = sp.tz + sp.halo_z, ay = sp.ty + sp.halo_y;  // allocated planes / rows
+  const int rs = RS_ ? RS_ : sp.rs, ps = PS_ ? PS_ : sp.ps;
+  const int tile_len = az * ps;
+  double *wsc = tile + tile_len;  // [32][WS]: z0*wz[P] | wy[P] | wx[P] of the lane's charge
+  const int lane = threadIdx.x;
+  int lm[NR], ll[NR], lconst[NR];
+  bool lin[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int item = lane + 32 * r;
+    lin[r] = item < P2;
+    lm[r] = item / P;
+    ll[r] = item - lm[r] * P;
+    lconst[r] = 8 * (lm[r] * rs + ll[r]);  // bytes
+  }
+  char *const tile_b = reinterpret_cast<char *>(tile);
+  const int NX = g.nx, NY = g.ny, NZ = g.nz;
+
+  for (;;) {
+    int tile_id = 0;
+    if (lane == 0) tile_id = atomicAdd(sp.counter, 1);
+    tile_id = __shfl_sync(FULL, tile_id, 0);
+    if (tile_id >= sp.ntiles) break;
+    const int ix = tile_id % sp.ntx, iyz = tile_id / sp.ntx;
+    const int iy = iyz % sp.nty, iz = iyz / sp.nty;
+    const int t0 = iz * sp.tz, y0 = iy * sp.ty, x0 = ix * sp.tx;
+    const int ez = min(sp.tz, g.zs_n - t0), ey = min(sp.ty, NY - y0), ex = min(sp.tx, NX - x0);
+    const int ezv = ez + sp.halo_z, eyv = ey + sp.halo_y, exv = ex + sp.halo_x;  // valid positions incl. halo
+    const int rb = sp.run_start[tile_id], re = sp.run_start[tile_id + 1];
+    for (int i = lane; i < tile_len; i += 32) tile[i] = 0.0;
+    __syncwarp();
+
+    for (int rbase = rb; rbase < re; rbase += 32) {
+      // the charges of up to 32 cell runs, as one flat sequence of 32-charge chunks: lane i keeps run i's
+      // range of sorted charges, an inclusive scan of the chunk counts maps a chunk number to its run
+      int my_jb = 0, my_je = 0;
+      if (rbase + lane < re) {
+        const int2 run = sp.runs[rbase + lane];
+        my_jb = cell_start[run.x];
+        my_je = cell_start[run.y];
+      }
+      const int my_nch = (my_je - my_jb + 31) >> 5;
+      int incl = my_nch;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += u;
+      }
+      const int nchunks = __shfl_sync(FULL, incl, 31);
+      // chunk c -> (first charge, end of its run)
+      auto locate = [&](int c, int &j0, int &je) {
+        const unsigned mk = __ballot_sync(FULL, incl > c);
+        const int i = __ffs(mk) - 1;
+        const int jb_i = __shfl_sync(FULL, my_jb, i), excl_i = __shfl_sync(FULL, incl - my_nch, i);
+        je = __shfl_sync(FULL, my_je, i);
+        j0 = jb_i + ((c - excl_i) << 5);
+      };
+      PosQ nxt = {0.0, 0.0, 0.0, 0.0};
+      if (nchunks > 0) {
+        int j0, je;
+        locate(0, j0, je);
+        if (j0 + lane < je) nxt = atoms[j0 + lane];
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        const PosQ p = nxt;  // q == 0 also marks "no charge in this lane"
+        nxt.q = 0.0;
+        if (c + 1 < nchunks) {  // the next chunk's loads fly while this one is spread
+          int j0, je;
+          locate(c + 1, j0, je);
+          if (j0 + lane < je) nxt = atoms[j0 + lane];
+        }
+        bool hit = false;
+        int my_yx = 0, my_ob = 0;
+        if (p.q != 0.0) {  // pppm_conp.cpp:161
+          const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
+          const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
+          const double fz = (p.z - g.boxlo[2]) * g.delinv[2];
+          if (!(fabs(fx) < OFFSET / 2 && fabs(fy) < OFFSET / 2 && fabs(fz) < OFFSET / 2)) {
+            *range_flag = 1;  // "Out of range atoms - cannot compute PPPM", pppm_conp.cpp:167
+          } else {
+            const int nx = (int)(fx + g.shift) - OFFSET;  // :146-148
+            const int ny = (int)(fy + g.shift) - OFFSET;
+            const int nz = (int)(fz + g.shift) - OFFSET;
+            const int uz = nz + g.nlower - g.zin_lo, uy = ny + g.nlower - y0, ux = nx + g.nlower - x0;
+            // positions are wrapped into the box along periodic axes, so |u| < 2 n there; anything else is a
+            // charge far outside a non-periodic box
+            if (uz < -NZ || uz >= 2 * NZ || uy < -2 * NY || uy >= 2 * NY || ux < -2 * NX || ux >= 2 * NX) {
+              *range_flag = 1;
+            } else {
+              const int zi0 = wrap2(uz, NZ);  // compact input plane of the first stencil plane
+              if (g.nzi < NZ && zi0 + P > g.nzi) {
+                *range_flag = 1;  // a plane outside what the box can reach: "Out of range atoms"
+              } else {
+                // signed start of the stencil relative to the tile, per axis (see header comment)
+                int rz = wrap2(zi0 - g.zs_lo - t0, NZ), ry = wrap2(uy, NY), rx = wrap2(ux, NX);
+                if (!sp.halo_z && rz >= ez) rz -= NZ;
+                if (!sp.halo_y && ry >= ey) ry -= NY;
+                if (!sp.halo_x && rx >= ex) rx -= NX;
+                const int ka = max(0, -rz), kb = min(P, ezv - rz);
+                hit = ka < kb && ry > -P && ry < eyv && rx > -P && rx < exv;
+                if (hit) {
+                  const double dx = nx + g.shiftone - fx;  // :199-201
+                  const double dy = ny + g.shiftone - fy;
+                  const double dz = nz + g.shiftone - fz;
+                  const double z0 = g.delvolinv * p.q;  // :205
+                  double *w = wsc + lane * WS;
+#pragma unroll
+                  for (int k = 0; k < P; ++k) {
+                    w[k] = z0 * rho1d_c<P>(rc, k, dz);
+                    w[P + k] = rho1d_c<P>(rc, k, dy);
+                    w[2 * P + k] = rho1d_c<P>(rc, k, dx);
+                  }
+                  // plane mask (bit n: plane rz + n lies in the tile) | ry + 8 | rx + 8, and the byte offset of
+                  // the stencil origin in the tile (may be negative: the valid points are not)
+                  my_yx = ((int)(((1u << kb) - 1u) & ~((1u << ka) - 1u)) << 24) | ((ry + 8) << 12) | (rx + 8);
+                  my_ob = 8 * (rz * ps + ry * rs + rx);
+                }
+              }
+            }
+          }
+        }
+        unsigned mask = __ballot_sync(FULL, hit);
+        __syncwarp();
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const unsigned yx = (unsigned)__shfl_sync(FULL, my_yx, src);
+          const int ob = __shfl_sync(FULL, my_ob, src);
+          const unsigned pm = yx >> 24;
+          const int ry = (int)((yx >> 12) & 0xfffu) - 8, rx = (int)(yx & 0xfffu) - 8;
+          const double *w = wsc + src * WS;
+#pragma unroll
+          for (int r2 = 0; r2 < NR; ++r2) {
+            const int row = ry + lm[r2], col = rx + ll[r2];
+            if (lin[r2] && (unsigned)row < (unsigned)eyv && (unsigned)col < (unsigned)exv) {
+              const double wyx = w[P + lm[r2]] * w[2 * P + ll[r2]];
+              char *t = tile_b + (ob + lconst[r2]);
+              double v[P];
+#pragma unroll
+              for (int n = 0; n < P; ++n)
+                if (pm & (1u << n)) v[n] = *reinterpret_cast<double *>(t + n * 8 * ps);
+#pragma unroll
+              for (int n = 0; n < P; ++n)
+                if (pm & (1u << n)) v[n] = fma(w[n], wyx, v[n]);
+#pragma unroll
+              for (int n = 0; n < P; ++n)
+                if (pm & (1u << n)) *reinterpret_cast<double *>(t + n * 8 * ps) = v[n];
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+    // fold the halo of a whole-axis tile back onto the periodic images (x, then y, then z: corners add up)
+    if (sp.halo_x) {
+      for (int i = lane; i < az * ay * sp.halo_x; i += 32) {
+        const int h = i % sp.halo_x, pr = i / sp.halo_x;
+        const int row = pr % ay, pl = pr / ay;
+        double *q = tile + pl * ps + row * rs;
+        q[h] += q[ex + h];
+      }
+      __syncwarp();
+    }
+    if (sp.halo_y) {
+      for (int i = lane; i < az * sp.halo_y * ex; i += 32) {
+        const int col = i % ex, pr = i / ex;
+        const int h = pr % sp.halo_y, pl = pr / sp.halo_y;
+        double *q = tile + pl * ps + col;
+        q[h * rs] += q[(ey + h) * rs];
+      }
+      __syncwarp();
+    }
+    if (sp.halo_z) {
+      for (int i = lane; i < sp.halo_z * ey * ex; i += 32) {
+        const int col = i % ex, pr = i / ex;
+        const int row = pr % ey, h = pr / ey;
+        double *q = tile + row * rs + col;
+        q[h * ps] += q[(ez + h) * ps];
+      }
+      __syncwarp();
+    }
+    // one plain store per mesh point of the tile
+    for (int pr = 0; pr < ez * ey; ++pr) {
+      const int pl = pr / ey, row = pr - pl * ey;
+      const double *q = tile + pl * ps + row * rs;
+      double *dst = brick + ((size_t)(t0 + pl) * NY + (y0 + row)) * NX + x0;
+      for (int col = lane; col < ex; col += 32) dst[col] = q[col];
+    }
+    __syncwarp();
   }
 }
 
@@ -264,6 +508,29 @@ expand_planes_kernel(size_t plane, int nplanes, int nz, int lo, const int *__res
   full[(size_t)mz * plane + r] = compact[i];
 }
 
+// sub-brick [lo, hi] of the full periodic mesh out of the compact bricks: electrolyte planes zi <->
+// (zin_lo + zi) mod nz, electrode planes zmap[mz]; a plane that is not stored is zero
+__global__ void __launch_bounds__(256)
+region_gather_kernel(PPPMGeom g, int which, int lx, int ly, int lz, int ex, int ey, int ez,
+                     const double *__restrict__ elyte, const double *__restrict__ ele, double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ex * ey * ez) return;
+  const int x = lx + (int)(i % ex);
+  const size_t r = i / ex;
+  const int y = ly + (int)(r % ey), z = lz + (int)(r / ey);
+  const size_t inplane = (size_t)y * g.nx + x;
+  double v = 0.0;
+  if (which != 1) {
+    const int zi = wrapi(z - g.zin_lo, g.nz);
+    if (zi < g.nzi) v += elyte[(size_t)zi * g.ny * g.nx + inplane];
+  }
+  if (which != 0) {
+    const int zo = g.zmap[z];
+    if (zo >= 0) v += ele[(size_t)zo * g.ny * g.nx + inplane];
+  }
+  out[i] = v;
+}
+
 __global__ void __launch_bounds__(256)
 green_mul_kernel(size_t n, cufftDoubleComplex *__restrict__ work, const double *__restrict__ ghalf) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,6 +689,146 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
   }
   if (smem > 0) ensure_dynamic_smem(spread_kernel, smem);
   spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, brick, range_flag);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+// Tile decomposition of the rank's slab of input planes and, per tile, the x-contiguous runs of cells
+// whose charges can reach it.  A charge with stencil origin n (per axis, n = int(f + shift) - OFFSET, f the
+// position in mesh units) touches the mesh indices n + nlower .. n + nlower + order - 1 (mod the mesh), so
+// the tile [g0, g0 + e) is reached from f in [g0 - nlower - (order-1) - s, g0 + e - nlower - s), s = 0.5
+// for odd orders and 0 for even ones; the interval is widened by 0.01 mesh cells against rounding, mapped
+// to cell indices (floor(f * cinv / delinv), the same expression the sort uses up to that margin) and,
+// along periodic axes, also taken one period up and down.  The kernel re-tests every charge exactly.
+void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sms, std::vector<int> &run_start,
+                            std::vector<int2> &runs, SpreadPlan &plan) {
+  const int P = g.order;
+  int T[3] = {32, 8, 8};  // x, y, z
+  if (const char *e = getenv("CONP_SPREAD_TILE")) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { T[2] = a; T[1] = b; T[0] = c; }
+  }
+  const int len[3] = {g.nx, g.ny, g.zs_n};
+  const int mod[3] = {g.nx, g.ny, g.nz};
+  // can a stencil wrap around inside this rank's index range?  x, y: always (periodic mesh); z: only if the
+  // slab is the whole periodic mesh
+  const bool wraps[3] = {true, true, g.zs_n == g.nz};
+  int nt[3], te[3], halo[3];
+  for (int a = 0; a < 3; ++a) {
+    if (len[a] <= T[a] + P - 1) {
+      nt[a] = 1; te[a] = std::max(len[a], 1); halo[a] = wraps[a] ? P - 1 : 0;
+    } else {
+      nt[a] = (len[a] + T[a] - 1) / T[a]; te[a] = T[a]; halo[a] = 0;
+    }
+  }
+  plan = SpreadPlan();
+  run_start.clear();
+  runs.clear();
+  if (g.zs_n <= 0) { run_start.push_back(0); return; }
+  plan.tx = te[0]; plan.ty = te[1]; plan.tz = te[2];
+  plan.ntx = nt[0]; plan.nty = nt[1]; plan.ntz = nt[2];
+  plan.halo_x = halo[0]; plan.halo_y = halo[1]; plan.halo_z = halo[2];
+  plan.ntiles = nt[0] * nt[1] * nt[2];
+  // row stride == order (mod 16) doubles: the order x order footprint of one charge then covers distinct
+  // 8-byte bank pairs (two wavefronts for 25 lanes, the minimum)
+  const int ax = te[0] + halo[0], ay = te[1] + halo[1], az = te[2] + halo[2];
+  plan.rs = ax + (((P - ax) % 16) + 16) % 16;
+  plan.ps = ay * plan.rs;
+  plan.smem = sizeof(double) * ((size_t)az * plan.ps + 32 * (size_t)((3 * P) | 1));
+  const double s = g.shift - 16384.0;
+  auto axis_cells = [&](int a, int g0, int e, std::vector<int> &out) {
+    out.clear();
+    const int nc = cells.nc[a];
+    const double ratio = cells.cinv[a] / g.delinv[a];
+    const double fa = (double)(g0 - g.nlower - (P - 1)) - s - 0.01, fb = (double)(g0 + e - g.nlower) - s + 0.01;
+    std::vector<char> mark(nc, 0);
+    if (cells.periodic[a]) {
+      const double period = cells.prd[a] * g.delinv[a];  // positions are wrapped into [0, period) mesh units
+      if (fb - fa >= mod[a]) {
+        std::fill(mark.begin(), mark.end(), 1);
+      } else {
+        for (int j = -1; j <= 1; ++j) {
+          const double a0 = fa + j * (double)mod[a], b0 = fb + j * (double)mod[a];
+          if (b0 < 0.0 || a0 > period) continue;
+          const int lo = std::max(0, (int)std::floor(a0 * ratio)), hi = std::min(nc - 1, (int)std::floor(b0 * ratio));
+          for (int c = lo; c <= hi; ++c) mark[c] = 1;
+        }
+      }
+    } else {  // charges beyond the box sit in the edge cells (cell_coord clamps)
+      const int lo = std::max(0, std::min(nc - 1, (int)std::floor(fa * ratio)));
+      const int hi = std::max(0, std::min(nc - 1, (int)std::floor(fb * ratio)));
+      for (int c = lo; c <= hi; ++c) mark[c] = 1;
+    }
+    for (int c = 0; c < nc; ++c)
+      if (mark[c]) out.push_back(c);
+  };
+  std::vector<std::vector<int>> cx(nt[0]), cy(nt[1]), cz(nt[2]);
+  for (int i = 0; i < nt[0]; ++i) axis_cells(0, i * te[0], std::min(te[0], len[0] - i * te[0]), cx[i]);
+  for (int i = 0; i < nt[1]; ++i) axis_cells(1, i * te[1], std::min(te[1], len[1] - i * te[1]), cy[i]);
+  for (int i = 0; i < nt[2]; ++i)
+    axis_cells(2, g.zin_lo + g.zs_lo + i * te[2], std::min(te[2], len[2] - i * te[2]), cz[i]);
+  for (int iz = 0; iz < nt[2]; ++iz)
+    for (int iy = 0; iy < nt[1]; ++iy)
+      for (int ix = 0; ix < nt[0]; ++ix) {
+        run_start.push_back((int)runs.size());
+        const size_t first = runs.size();
+        for (int z : cz[iz])
+          for (int y : cy[iy]) {
+            const int base = (z * cells.nc[1] + y) * cells.nc[0];
+            const std::vector<int> &xs = cx[ix];
+            for (size_t k = 0; k < xs.size();) {
+              size_t k2 = k + 1;
+              while (k2 < xs.size() && xs[k2] == xs[k2 - 1] + 1) ++k2;
+              const int c0 = base + xs[k], c1 = base + xs[k2 - 1] + 1;
+              if (runs.size() > first && runs.back().y == c0) runs.back().y = c1;  // contiguous in cell order
+              else runs.push_back(make_int2(c0, c1));
+              k = k2;
+            }
+          }
+      }
+  run_start.push_back((int)runs.size());
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(227 * 1024 - 1024) / (plan.smem + 1024)));
+  plan.grid = std::min(plan.ntiles, num_sms * per_sm);
+}
+
+int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan &plan, const double *rho_coeff_host,
+                             const PosQ *atoms, const int *cell_start, double *brick, int *range_flag) {
+  if (plan.ntiles <= 0 || g.zs_n <= 0) return 0;
+  CUDA_CHECK(cudaMemsetAsync(plan.counter, 0, sizeof(int), s));
+  RhoCoeff rho_coeff;
+  std::memset(&rho_coeff, 0, sizeof(rho_coeff));
+  std::memcpy(rho_coeff.c, rho_coeff_host, sizeof(double) * g.order * g.order);
+  // LAMMPS' default order with the default tile shape: strides known at compile time
+  constexpr int RS5 = 37, PS5 = 8 * 37;
+  if (g.order == 5 && plan.rs == RS5 && plan.ps == PS5) {
+    ensure_dynamic_smem(spread_tile_kernel<5, RS5, PS5>, plan.smem);
+    spread_tile_kernel<5, RS5, PS5><<<plan.grid, 32, plan.smem, s>>>(g, plan, rho_coeff, atoms, cell_start, brick,
+                                                                     range_flag);
+    CUDA_CHECK(cudaGetLastError());
+    return 1;
+  }
+#define CONP_SPT_CASE(P_)                                                                                        \
+  case P_:                                                                                                       \
+    ensure_dynamic_smem(spread_tile_kernel<P_, 0, 0>, plan.smem);                                                \
+    spread_tile_kernel<P_, 0, 0><<<plan.grid, 32, plan.smem, s>>>(g, plan, rho_coeff, atoms, cell_start, brick, \
+                                                                  range_flag);                                  \
+    break;
+  switch (g.order) {
+    CONP_SPT_CASE(1) CONP_SPT_CASE(2) CONP_SPT_CASE(3) CONP_SPT_CASE(4) CONP_SPT_CASE(5) CONP_SPT_CASE(6)
+    CONP_SPT_CASE(7)
+    default: CONP_THROW(CONP_ERR_ARG, "PPPM order %d not supported", g.order);
+  }
+#undef CONP_SPT_CASE
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_region_gather(cudaStream_t s, const PPPMGeom &g, int which, const int lo[3], const int hi[3],
+                         const double *elyte, const double *ele, double *out) {
+  const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
+  const size_t n = (size_t)ex * ey * ez;
+  region_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, which, lo[0], lo[1], lo[2], ex, ey, ez, elyte,
+                                                                  ele, out);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

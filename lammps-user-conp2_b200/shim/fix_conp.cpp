@@ -17,6 +17,7 @@
 #include "variable.h"
 
 #include "conp_b200.h"
+#include "pppm_conp.h"
 
 #include <cmath>
 #include <cstring>
@@ -27,7 +28,8 @@ using namespace FixConst;
 
 /* keyword parsing: same tokens and messages as reference fix_conp.cpp:86-176 */
 FixConpB200::FixConpB200(LAMMPS *lmp, int narg, char **arg) :
-    Fix(lmp, narg, arg), ctx(nullptr), potdiffstr(nullptr), potdiffvar(-1), tag2eleall(nullptr), coulpair(nullptr)
+    Fix(lmp, narg, arg), ctx(nullptr), potdiffstr(nullptr), potdiffvar(-1), tag2eleall(nullptr), coulpair(nullptr),
+    pppm(nullptr), outf(nullptr)
 {
   if (narg < 8) error->all(FLERR, "Illegal fix conp command (too few input parameters)");
   everynum = utils::inumeric(FLERR, arg[3], false, lmp);
@@ -66,7 +68,7 @@ FixConpB200::FixConpB200(LAMMPS *lmp, int narg, char **arg) :
       for (int i = 0; i < n; ++i) {
         if (++iarg >= narg) error->all(FLERR, "Invalid fix conp command (Insufficient input entries for etypes)");
         const int t = utils::inumeric(FLERR, arg[iarg], false, lmp);
-        if (t > atom->ntypes) error->all(FLERR, "Invalid fix conp command (Invalid atom type in etypes)");
+        if (t < 1 || t > atom->ntypes) error->all(FLERR, "Invalid fix conp command (Invalid atom type in etypes)");
         is_eletype[t] = 1;
       }
       smartlist = true;
@@ -81,25 +83,37 @@ FixConpB200::FixConpB200(LAMMPS *lmp, int narg, char **arg) :
   }
   scalar_flag = 1; extscalar = 0; global_freq = 1;
   scalar_output = 0.0;
-  postforceflag = setup_done = false;
+  postforceflag = init_done = setup_done = false;
   one_electrode_flag = false;
   elenum_all = 0; maxtag_all = 0;
+  Btime = Ctime = Ktime = pair_share = kspace_share = 0.0;
+  stage_samples = 0;
+  if (comm->me == 0) outf = fopen(logfile.c_str(), "w");   // reference fix_conp.cpp:119
 
   /* one context per MPI rank / GPU; rank 0 makes the NCCL id, MPI_Bcast on `world` carries it
      (replaces nothing in the reference: its collectives run on `world` directly) */
   char uid[CONP_UNIQUE_ID_BYTES];
   if (comm->me == 0 && comm->nprocs > 1) check(conp_get_unique_id(uid));
   MPI_Bcast(uid, CONP_UNIQUE_ID_BYTES, MPI_BYTE, 0, world);
-  int ndev_local = 1;
+  /* one GPU per rank: node-local rank -> device index (CONP_GPUS_PER_NODE overrides the device count) */
+  MPI_Comm node;
+  MPI_Comm_split_type(world, MPI_COMM_TYPE_SHARED, comm->me, MPI_INFO_NULL, &node);
+  int local_rank = 0, ndev = 0;
+  MPI_Comm_rank(node, &local_rank);
+  MPI_Comm_free(&node);
   const char *v = getenv("CONP_GPUS_PER_NODE");
-  if (v) ndev_local = atoi(v);
-  const int status = conp_create(&ctx, comm->me % ndev_local, comm->me, comm->nprocs, comm->nprocs > 1 ? uid : nullptr);
-  if (status) error->all(FLERR, conp_last_error(nullptr));
+  if (v) ndev = atoi(v);
+  else conp_device_count(&ndev);
+  if (ndev < 1) error->all(FLERR, "fix conp (B200): no sm_100 CUDA device on this node; there is no CPU fallback");
+  int status = conp_create(&ctx, local_rank % ndev, comm->me, comm->nprocs, comm->nprocs > 1 ? uid : nullptr), any = 0;
+  MPI_Allreduce(&status, &any, 1, MPI_INT, MPI_MAX, world);
+  if (any) error->all(FLERR, status ? conp_last_error(nullptr) : "conp_create failed on another rank");
 }
 
 FixConpB200::~FixConpB200()
 {
   conp_destroy(ctx);
+  if (outf) fclose(outf);   // reference :208
   delete[] potdiffstr;
   delete[] tag2eleall;
 }
@@ -154,9 +168,15 @@ int FixConpB200::modify_param(int narg, char **arg)
   return 0;
 }
 
-/* FixConp::linalg_init + linalg_setup (reference fix_conp.cpp:393-464) */
-void FixConpB200::one_time_setup()
+/* FixConp::linalg_init (reference fix_conp.cpp:393-424): everything that does not need the k-space style
+   to be set up -- geometry, pair data, the global electrode list */
+void FixConpB200::linalg_init()
 {
+  if (pppmflag) {   // reference :400-404
+    pppm = dynamic_cast<PPPMCONPB200 *>(force->kspace);
+    if (pppm == nullptr)
+      error->all(FLERR, "Fix conp couldn't detect a pppm/conp kspace style (which is required with the pppm flag)");
+  }
   const int nlocal = atom->nlocal;
   int *mask = atom->mask, *type = atom->type;
   tagint *tag = atom->tag;
@@ -234,10 +254,20 @@ void FixConpB200::one_time_setup()
                       pairmode == CONP_PAIR_EHGO ? eta_ij.data() : nullptr, pairmode == CONP_PAIR_EHGO ? fo_ij.data() : nullptr,
                       pairmode == CONP_PAIR_EHGO ? u0_i.data() : nullptr, smartlist, smartlist ? is_eletype.data() : nullptr));
   check(conp_set_electrodes(ctx, elenum_all, eleall2tag.data(), eleall_type.data(), eleall_side.data(), eleall_x.data()));
+  if (pppm) pppm->attach(ctx);   // its next setup() hands the mesh tables over (KSpaceModule::register_fix, :409)
+  init_done = true;
+}
 
+/* FixConp::linalg_setup (reference fix_conp.cpp:426-464): A matrix, inverse, unit-voltage charges */
+void FixConpB200::linalg_setup()
+{
   /* A matrix: a_cal / a_read (reference fix_conp.cpp:438-445, 721-861) */
   if (a_matrix_f == 0) {
+    if (outf) fprintf(outf, "A matrix calculating ...\n");   // reference :787
     check(conp_build_A(ctx));
+    conp_info info;
+    conp_get_info(ctx, &info);
+    if (outf) fprintf(outf, "A matrix calculation time  = %g\n", info.setup_build_ms * 1e-3);   // reference :857
   } else {
     /* rank 0 reads the `%20d` tag row + N rows (reference :725-748), permutes to eleall order, broadcasts */
     std::vector<double> full((size_t) elenum_all * elenum_all);
@@ -260,15 +290,24 @@ void FixConpB200::one_time_setup()
   setup_done = true;
 }
 
+/* reference fix_conp.cpp:382-385 */
 void FixConpB200::setup_post_neighbor()
 {
-  if (!setup_done) one_time_setup();
+  if (!init_done) linalg_init();
   post_neighbor();
 }
 
+/* reference fix_conp.cpp:387-391.  kspace->setup() is where `pppm/conp` hands its mesh tables to the library;
+   conp_pppm_setup invalidates the per-rank atom data (the exchange buffers depend on the mesh), so the
+   post_neighbor hand-over is repeated before the first solve. */
 void FixConpB200::setup_pre_force(int vflag)
 {
   force->kspace->setup();
+  if (!setup_done) linalg_setup();
+  post_neighbor();
+  /* event-timed stage breakdown of the first solves: feeds the reference's Log-file timer lines */
+  conp_stage_times(ctx, 1, nullptr);
+  stage_samples = 8;
   pre_force(vflag);
 }
 
@@ -289,8 +328,36 @@ void FixConpB200::pre_force(int)
      the previous one; LAMMPS' own per-step collectives normally guarantee that, the barrier makes it
      unconditional (a few microseconds against a step of hundreds). */
   if (comm->nprocs > 1) MPI_Barrier(world);
+  const double t1 = MPI_Wtime();
   check(conp_pre_force(ctx, &atom->x[0][0], mode, variant(), potdiff, eleallq.data(), &scalar_output));
+  Btime += MPI_Wtime() - t1;
+  if (stage_samples > 0 && --stage_samples == 0) {   // back to the CUDA-graph replay
+    double st[8];
+    conp_stage_times(ctx, 0, st);
+    /* st: pack, bin, pair, kspace, gather, exchange, gemv, epilogue [ms] */
+    double tot = 0.0;
+    for (double v : st) tot += v;
+    pair_share = tot > 0.0 ? st[2] / tot : 0.0;
+    kspace_share = tot > 0.0 ? (st[3] + st[4]) / tot : 0.0;
+  }
+  if (pppm) pppm->charges_updated();
   scatter_charges();
+  /* reference :553-568: timers written at the last step of the run.  Btime is this rank's wall time inside
+     conp_pre_force (b_cal, matvec and epilogue are one call here); the Coulomb / k-space lines are its
+     shares measured with CUDA events on the first solves of the run. */
+  if (update->laststep == update->ntimestep) {
+    double Btime_all = 0.0;
+    MPI_Reduce(&Btime, &Btime_all, 1, MPI_DOUBLE, MPI_SUM, 0, world);
+    if (outf) {
+      Btime = Btime_all / comm->nprocs;
+      Ctime = Btime * pair_share;
+      Ktime = Btime * kspace_share;
+      fprintf(outf, "B vector calculation time = %g\n", Btime);
+      fprintf(outf, "Coulomb calculation time = %g\n", Ctime);
+      fprintf(outf, "Kspace calculation time = %g\n", Ktime);
+      fflush(outf);
+    }
+  }
 }
 
 /* charges of local AND ghost electrode atoms (reference :1153-1158) */

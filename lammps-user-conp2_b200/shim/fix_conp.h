@@ -19,6 +19,7 @@ FixStyle(cond,FixCondB200)
 
 #include "fix.h"
 
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -46,7 +47,8 @@ class FixConpB200 : public Fix {
  protected:
   virtual int variant() const { return 0; }  // CONP_VARIANT_CONP
   void check(int status);                    // non-zero status -> error->all(FLERR, conp_last_error())
-  void one_time_setup();
+  void linalg_init();                        // reference linalg_init  (fix_conp.cpp:393-424)
+  void linalg_setup();                       // reference linalg_setup (fix_conp.cpp:426-464)
   void scatter_charges();
   void read_matrix_file(std::vector<double> &full);             // `org` / `inv` (reference a_read :721-773)
   void write_matrix(const char *name, const char *fmt);          // `matout` (reference :833-849, 960-977)
@@ -59,7 +61,7 @@ class FixConpB200 : public Fix {
   int potdiffvar;
   int ff_flag, a_matrix_f, pairmode;
   bool smartlist, zneutrflag, matoutflag, pppmflag, qinitflag, lowmemflag, nullneutralflag;
-  bool one_electrode_flag, postforceflag, setup_done;
+  bool one_electrode_flag, postforceflag, init_done, setup_done;
   std::string a_matrix_file, logfile;
   std::vector<int> is_eletype;            // etypes keyword
   std::vector<double> eta_i, u0_i;        // fix_modify ... ehgo coeff
@@ -71,6 +73,10 @@ class FixConpB200 : public Fix {
   int *tag2eleall;
   int maxtag_all;
   class Pair *coulpair;
+  class PPPMCONPB200 *pppm;               // force->kspace when the `pppm` keyword is given
+  FILE *outf;                             // the fix's log file (arg 7), rank 0 only
+  double Btime, Ctime, Ktime, pair_share, kspace_share;   // reference timers (fix_conp.cpp:553-568)
+  int stage_samples;
 };
 
 class FixConqB200 : public FixConpB200 {

@@ -1,5 +1,8 @@
 #pragma once
 #include "pointers.h"
+#include "error.h"
+#include "group.h"
+#define FixStyle(key, Class)
 namespace LAMMPS_NS {
 class NeighList;
 namespace FixConst {
@@ -11,7 +14,11 @@ class Fix : protected Pointers {
   char *id, *style;
   int igroup, groupbit;
   int scalar_flag, extscalar, global_freq, nevery, vector_flag, size_vector;
-  Fix(LAMMPS *l, int, char **) : Pointers(l) {}
+  Fix(LAMMPS *l, int, char **arg) : Pointers(l), id(arg[0]), style(arg[2]) {  // fix ID group-ID style ...
+    igroup = group->find(arg[1]);
+    if (igroup == -1) error->all(FLERR, "Could not find fix group ID");
+    groupbit = group->bitmask[igroup];
+  }
   virtual int setmask() = 0;
   virtual void init() {}
   virtual void init_list(int, NeighList *) {}

@@ -5,6 +5,6 @@ class Variable;
 class Input : protected Pointers {
  public:
   Variable *variable;
-  Input(LAMMPS *l) : Pointers(l) {}
+  Input(LAMMPS *l) : Pointers(l), variable(nullptr) {}
 };
 }  // namespace LAMMPS_NS
