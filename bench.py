@@ -313,6 +313,9 @@ def main():
     fix = make_fix(lmp, arg, device=local_rank, rank=rank, nranks=world, unique_id=uid)
     if args.fast_setup:
         fix.setup_post_neighbor()
+        if fix.args.pppmflag:
+            t = lmp.pppm_tables()
+            fix.ctx.pppm_setup(t.mesh, t.order, t.rho_coeff, t.greensfn, t.shift, t.shiftone)
         Sr = synthetic_matrix(fix.N)
         fix.ctx.load_matrix(Sr, True)
         del Sr

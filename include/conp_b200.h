@@ -210,6 +210,23 @@ int conp_get_density_region(conp_ctx *ctx, int which, const int lo[3], const int
 /* u_brick (pppm_conp.cpp:260-266) for potential probes. */
 int conp_get_potential_brick(conp_ctx *ctx, double *brick_out);
 
+/* `compute potential/atom` (compute_potential_atom.cpp:120-182), the diagnostic that reuses the charge solve's
+ * mesh and erfc pair kernels.
+ * conp_mesh_potential: the mesh sum of PPPMCONP::compute_particle_potential (pppm_conp.cpp:452-484) at n
+ * arbitrary positions, u_out[i] = sum_stencil w u_brick, with u_brick the potential of ALL charges of the
+ * last solve (electrolyte + updated electrode charges) -- what LAMMPS' PPPM holds after a force pass with
+ * per-atom energy; internal units e/Angstrom, no self or slab term.
+ * conp_electrode_potential: the complete compute for the electrode atoms (eleall order), in the
+ * reference's units (qqr2e/qe2f applied by the caller: the value returned here is in e/Angstrom):
+ * pairflag -> compute_pair_potential (:223-318) with the `eta` keyword's Gaussian terms, kspaceflag ->
+ * mesh sum, -2 g q/sqrt(pi) self term, +eta q sqrt(2)/sqrt(pi), and slabcorr (:333-358; qsumflag = the
+ * `noqsum` keyword off).  In conp runs the result is +-dV/2 (plus a common shift) on the two electrodes:
+ * an on-device residual check of the solve.  Both need `kspace_style pppm/conp` (same error message as the
+ * reference without it). [collective] */
+int conp_mesh_potential(conp_ctx *ctx, int n, const double *xyz, double *u_out);
+int conp_electrode_potential(conp_ctx *ctx, int pairflag, int kspaceflag, double eta, int qsumflag,
+                             double *phi_out);
+
 /* FixConp::post_force -> force_cal (fix_conp.cpp:1163-1201, 1368-1444).
  * f_out (nlocal x 3, may be NULL) receives the Gaussian-correction force on
  * this rank's non-electrode atoms (zero rows for electrode atoms);

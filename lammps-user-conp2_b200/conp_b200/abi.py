@@ -26,7 +26,7 @@ SYMBOLS = [
     "conp_set_cell", "conp_set_ewald", "conp_set_pair", "conp_set_electrodes", "conp_pppm_setup", "conp_build_A",
     "conp_load_matrix", "conp_get_matrix", "conp_invert_project", "conp_set_unit_voltage", "conp_post_neighbor",
     "conp_pre_force", "conp_solve_device", "conp_get_charges", "conp_get_b", "conp_get_density",
-    "conp_get_density_region",
+    "conp_get_density_region", "conp_mesh_potential", "conp_electrode_potential",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
     "conp_matvec", "conp_plan_symv", "conp_plan_spread",
@@ -133,6 +133,8 @@ def load_library(path: str | None = None):
     L.conp_get_density.argtypes = [vp, C.c_int, c_dp]
     L.conp_get_potential_brick.argtypes = [vp, c_dp]
     L.conp_get_density_region.argtypes = [vp, C.c_int, c_ip, c_ip, c_dp]
+    L.conp_mesh_potential.argtypes = [vp, C.c_int, c_dp, c_dp]
+    L.conp_electrode_potential.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, c_dp]
     L.conp_post_force.argtypes = [vp, C.c_double, c_dp, c_dp]
     L.conp_stream.argtypes = [vp]
     L.conp_stream.restype = vp
@@ -314,6 +316,18 @@ class Context:
         shape = tuple(int(hi_[a] - lo_[a] + 1) for a in (2, 1, 0))
         out = np.zeros(shape)
         self._ck(self.L.conp_get_density_region(self.h, int(which), _ip(lo_), _ip(hi_), _dp(out)))
+        return out
+
+    def mesh_potential(self, xyz):
+        x = f64(xyz).reshape(-1, 3)
+        out = np.zeros(x.shape[0])
+        self._ck(self.L.conp_mesh_potential(self.h, int(x.shape[0]), _dp(x), _dp(out)))
+        return out
+
+    def electrode_potential(self, pair=True, kspace=True, eta=0.0, qsum=True):
+        out = np.zeros(self.n_ele)
+        self._ck(self.L.conp_electrode_potential(self.h, int(bool(pair)), int(bool(kspace)), float(eta),
+                                                 int(bool(qsum)), _dp(out)))
         return out
 
     def get_potential_brick(self):

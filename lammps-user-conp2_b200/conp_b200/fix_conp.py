@@ -158,9 +158,6 @@ class FixConp:
             ctx.set_pair(self.pairmode, a.eta, lmp.cut_coul, s.ntypes, lmp.cutsq, eta_ij, fo_ij, u0, a.smartlist,
                          is_eletype if a.smartlist else None)
             ctx.set_electrodes(s.id[self.ele_idx], s.type[self.ele_idx], self.side, s.x[self.ele_idx])
-            if a.pppmflag:
-                t = lmp.pppm_tables()
-                ctx.pppm_setup(t.mesh, t.order, t.rho_coeff, t.greensfn, t.shift, t.shiftone)
         self.post_neighbor()
 
     def post_neighbor(self):
@@ -175,6 +172,11 @@ class FixConp:
         a, ctx = self.args, self.ctx
         s = self.lmp.system
         if self.runstage == 0:
+            if a.pppmflag:
+                # force->kspace->setup() (fix_conp.cpp:388): `pppm/conp` hands its mesh tables over here, i.e.
+                # AFTER the first post_neighbor -- the order the LAMMPS shim produces (shim/fix_conp.cpp)
+                t = self.lmp.pppm_tables()
+                ctx.pppm_setup(t.mesh, t.order, t.rho_coeff, t.greensfn, t.shift, t.shiftone)
             if a.a_matrix_f == 0:
                 ctx.build_A()
             else:
@@ -248,6 +250,14 @@ class FixConp:
     def compute_scalar(self):
         return self.scalar_output
 
+    def compute_potential_atom(self, eta=None, pair=True, kspace=True, qsum=True):
+        """``compute ID <electrode groups> potential/atom [pair] [kspace] eta <eta> <molL> <molR> [noqsum]``
+        (compute_potential_atom.cpp:47-182) for the electrode atoms, in volts: the potential the solve is
+        supposed to have made constant on each electrode."""
+        eta = self.args.eta if eta is None else eta
+        phi = self.ctx.electrode_potential(pair, kspace, eta, qsum)
+        return phi * (self.lmp.qqr2e / self.lmp.qe2f)   # evscale of the compute, :106
+
     def close(self):
         self.ctx.close()
 
@@ -262,9 +272,48 @@ class FixCond(FixConp):
     style = "cond"
 
 
+class FixZmirror:
+    """``fix ID group zmirror Nevery group2`` (fix_zmirror.cpp:30-64, 124-220): the atoms of group2 become
+    the mirror image, in the plane z = (zlo + zhi)/2, of the atoms of ``group``, matched by tag offset.
+    Host-side position plumbing of the doubled-cell decks; mirrors shim/fix_zmirror.cpp."""
+
+    def __init__(self, lmp, arg):
+        if len(arg) != 5:
+            raise FixError("Illegal fix zmirror command (incorrect no. of parameters)")
+        if arg[1] not in lmp.groups:
+            raise FixError("Could not find fix group ID")
+        if arg[4] not in lmp.groups:
+            raise FixError("Fix zmirror group ID does not exist")
+        self.lmp, self.everynum = lmp, int(arg[3])
+        self.g1, self.g2 = lmp.groups[arg[1]], lmp.groups[arg[4]]
+
+    def setup(self):
+        tag = self.lmp.system.id
+        t1, t2 = tag[self.g1], tag[self.g2]
+        self.send_mintag, self.recv_mintag = int(t1.min()), int(t2.min())
+        if int(t1.max()) - self.send_mintag != int(t2.max()) - self.recv_mintag:
+            raise FixError("Groups do not have same number of tags")
+
+    def post_integrate(self, ntimestep=0):
+        if ntimestep % self.everynum:
+            return
+        s = self.lmp.system
+        zoffset = 2.0 * s.boxlo[2] + s.prd[2]
+        src = np.nonzero(self.g1)[0]
+        dst = np.nonzero(self.g2)[0]
+        table = {int(s.id[i]) - self.send_mintag: s.x[i].copy() for i in src}
+        if len(table) != len(dst):
+            raise FixError("Incorrect number of atoms communicated")
+        for i in dst:
+            x = table[int(s.id[i]) - self.recv_mintag]
+            s.x[i] = (x[0], x[1], zoffset - x[2])
+
+
 def make_fix(lmp, arg, **kw):
     """``fix`` command dispatch on the style token (FixStyle(conp|conq|cond))."""
     style = str(arg[2])
+    if style == "zmirror":
+        return FixZmirror(lmp, arg)
     cls = {"conp": FixConp, "conq": FixConq, "cond": FixCond}.get(style)
     if cls is None:
         raise FixError(f"Unknown fix style {style}")

@@ -335,6 +335,12 @@ int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const
                   const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
                   const double *ez, const int *etype, const int *run_start, const PairRun *runs, double *A_rows,
                   size_t pitch);
+// phi[i] = sum_j q_ele[j] dudq_A(r_ij) over the electrode atoms j != i (and the periodic images of i), rows
+// [row_begin, row_end): the electrode-electrode pair part of compute potential/atom
+int launch_pair_P(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
+                  const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
+                  const double *ez, const int *etype, const int *run_start, const PairRun *runs,
+                  const double *q_ele, double *phi);
 int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e,
                           const EPos *esorted, const int *cell_start, const double *q_ele, const PosQ *packed,
                           const int *packed_type, const int *near_list, const int *near_count, int max_near,
@@ -358,13 +364,19 @@ struct SpreadPlan {
   const int2 *runs = nullptr;         // device: [c0, c1) ranges of cell indices
   int *counter = nullptr;             // device: tile scheduler, zeroed before every launch
   size_t smem = 0;
-  int grid = 0;
+  int grid = 0, grid_mma = 0;
+  // tensor-core kernel (spread_mma_kernel): in = allowed, out = chosen; per-charge stencil origins / weights
+  int use_mma = 0;
+  int4 *origin = nullptr;
+  double *weights = nullptr;
 };
 void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sms, std::vector<int> &run_start,
                             std::vector<int2> &runs, SpreadPlan &plan);
 int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan &plan,
                              const double *rho_coeff_host /* order x order, host memory */, const PosQ *atoms,
-                             const int *cell_start, double *brick, int *range_flag);
+                             const int *cell_start, int m_bound /* upper bound of the sorted charges */,
+                             const int *count_ptr /* device: their actual number, or nullptr */, double *brick,
+                             int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
 // rhat: spectra of the rank's nzl input planes (compact planes zs_lo..); uhat: (partial) output-plane spectra
 // Launch plan of the z-convolution (built once per rank by plan_pppm_zconv): narrow column groups stage
@@ -409,6 +421,10 @@ int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, int row_beg
                            const double *weights, const double *sb, const double *setq, const double *qinit,
                            const double *scal, double *q_out, double *brick);
 int launch_add_bricks(cudaStream_t s, size_t n, const double *a, const double *b, double *out);
+// out[i] = sum over the order^3 stencil of point i (weights from its position, pppm_conp.cpp:452-484) of the
+// full-mesh potential u[nz][ny][nx]
+int launch_mesh_potential(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *xyz,
+                          const double *u_full, double *out);
 // out[z][y][x] over the sub-brick lo..hi (inclusive) of the periodic mesh: which = 0 electrolyte (compact
 // input planes, all nzi of them), 1 electrode (compact output planes), 2 sum
 int launch_region_gather(cudaStream_t s, const PPPMGeom &g, int which, const int lo[3], const int hi[3],

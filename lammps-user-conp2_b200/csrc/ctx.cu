@@ -91,6 +91,7 @@ struct conp_ctx {
 
   // atoms ------------------------------------------------------------------------
   int nlocal = 0, m_local = 0, m_total = 0;
+  double qsum_elyte = 0;  // sum of the non-electrode charges, all ranks (compute potential/atom, slab term)
   int mpad = 0, m_slots = 0;  // multi-GPU: every rank's packed block has mpad slots (last one carries sum q z)
   std::vector<int> h_idx, m_counts, m_offsets;
   DevBuf<int> d_mcounts;
@@ -130,7 +131,10 @@ struct conp_ctx {
   SpreadPlan splan;
   DevBuf<int> d_sp_runstart, d_sp_counter;
   DevBuf<int2> d_sp_runs;
+  DevBuf<int4> d_sp_origin;
+  DevBuf<double> d_sp_weights;
   bool spread_atomic = false;
+  int spread_mode = -1;  // CONP_SPREAD = atomic | smem | mma (default: by size, see conp_post_neighbor)
   DevBuf<double> d_pw;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
@@ -254,6 +258,7 @@ void ensure_static_cells(conp_ctx *c) {
   if (c->have_pppm) {
     std::vector<int> rs;
     std::vector<int2> rr;
+    c->splan.use_mma = c->spread_mode != 1;
     plan_pppm_spread_tiles(c->pg, c->grid_b, c->num_sms, rs, rr, c->splan);
     if (rr.empty()) rr.push_back(make_int2(0, 0));
     c->d_sp_runstart.upload(rs, c->stream);
@@ -511,8 +516,11 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     auto kmark = [&](int i) { if (c->stage_timing && c->debug) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
     kmark(0);
     if (!c->spread_atomic) {
+      // the sorted charges: all of them on one GPU, the relevant subset (count in cell_start[ncells]) on several
       c->launches += launch_pppm_spread_tiles(s, pg, c->splan, c->h_rho.data(), c->d_sorted.p, c->d_cellstart.p,
-                                              c->d_brick.p, c->d_flag.p);
+                                              multi ? c->m_slots : c->m_total,
+                                              multi ? c->d_cellstart.p + g.ncells : nullptr, c->d_brick.p,
+                                              c->d_flag.p);
     } else if (!multi || c->periodic[2]) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
                                         c->d_flag.p);
@@ -743,6 +751,39 @@ void store_rows_from_full(conp_ctx *c, double *full) {
                                  cudaMemcpyDeviceToDevice, c->stream));
 }
 
+// Full periodic mesh potential on demand (the per-step path only evaluates the electrode planes): the
+// reference's 3-D transform, pppm_conp.cpp:230-267, of the electrolyte density or (include_ele) of the
+// electrolyte + electrode density -- what PPPM's u_brick holds after a force pass with per-atom energy.
+void full_mesh_potential(conp_ctx *c, bool include_ele, DevBuf<double> &full) {
+  cudaStream_t s = c->stream;
+  const PPPMGeom &g = c->pg;
+  DevBuf<double> gd;
+  DevBuf<cufftDoubleComplex> work;
+  full.zero(c->ngrid, s);
+  work.reserve(c->nhalf);
+  gd.upload(c->h_ghalf, s);
+  c->launches += launch_expand_planes(s, c->plane, g.zs_n, g.nz, g.zin_lo + g.zs_lo, nullptr, c->d_brick.p, full.p);
+  if (include_ele) {
+    DevBuf<double> fe;
+    fe.zero(c->ngrid, s);
+    c->launches += launch_expand_planes(s, c->plane, g.nzo, g.nz, 0, c->d_zout.p, c->d_ebrick.p, fe.p);
+    c->launches += launch_add_bricks(s, c->ngrid, full.p, fe.p, full.p);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);  // z-slabs / own rows of every rank
+  cufftHandle pf, pb;
+  CUFFT_CHECK(cufftPlan3d(&pf, g.nz, g.ny, g.nx, CUFFT_D2Z));
+  CUFFT_CHECK(cufftPlan3d(&pb, g.nz, g.ny, g.nx, CUFFT_Z2D));
+  CUFFT_CHECK(cufftSetStream(pf, s));
+  CUFFT_CHECK(cufftSetStream(pb, s));
+  CUFFT_CHECK(cufftExecD2Z(pf, full.p, work.p));
+  c->launches += launch_pppm_green_mul(s, c->nhalf, work.p, gd.p);
+  CUFFT_CHECK(cufftExecZ2D(pb, work.p, full.p));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  cufftDestroy(pf);
+  cufftDestroy(pb);
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -814,7 +855,9 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     if (getenv("CONP_EWALD_GEMM")) c->eg_mode = atoi(getenv("CONP_EWALD_GEMM")) != 0 ? 1 : 0;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
-    c->spread_atomic = getenv("CONP_SPREAD_ATOMIC") != nullptr && atoi(getenv("CONP_SPREAD_ATOMIC")) != 0;
+    if (const char *e = getenv("CONP_SPREAD"))
+      c->spread_mode = !strcmp(e, "atomic") ? 0 : !strcmp(e, "smem") ? 1 : !strcmp(e, "mma") ? 2 : -1;
+    if (getenv("CONP_SPREAD_ATOMIC") != nullptr && atoi(getenv("CONP_SPREAD_ATOMIC")) != 0) c->spread_mode = 0;
     c->d_scal.zero(16, c->stream);
     c->d_partials.zero(3 * 1024, c->stream);
     c->d_counter.zero(1, c->stream);
@@ -1485,16 +1528,20 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     c->m_counts.assign(c->nranks, 0);
     c->m_offsets.assign(c->nranks, 0);
     c->m_counts[c->rank] = c->m_local;
+    c->qsum_elyte = 0.0;
+    for (int j : c->h_idx) c->qsum_elyte += q[j];
     if (c->nranks > 1) {
       DevBuf<double> cnt;
-      cnt.zero(c->nranks, s);
-      const double mine = c->m_local;
-      CUDA_CHECK(cudaMemcpyAsync(cnt.p + c->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
-      comm_allreduce_sum_f64(c->comm, cnt.p, c->nranks, s);
-      std::vector<double> h(c->nranks);
-      CUDA_CHECK(cudaMemcpyAsync(h.data(), cnt.p, sizeof(double) * c->nranks, cudaMemcpyDeviceToHost, s));
+      cnt.zero(c->nranks + 1, s);
+      const double mine[2] = {(double)c->m_local, c->qsum_elyte};
+      CUDA_CHECK(cudaMemcpyAsync(cnt.p + c->rank, &mine[0], sizeof(double), cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(cnt.p + c->nranks, &mine[1], sizeof(double), cudaMemcpyHostToDevice, s));
+      comm_allreduce_sum_f64(c->comm, cnt.p, c->nranks + 1, s);
+      std::vector<double> h(c->nranks + 1);
+      CUDA_CHECK(cudaMemcpyAsync(h.data(), cnt.p, sizeof(double) * (c->nranks + 1), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK(cudaStreamSynchronize(s));
       for (int r = 0; r < c->nranks; ++r) c->m_counts[r] = (int)std::llround(h[r]);
+      c->qsum_elyte = h[c->nranks];
     }
     int tot = 0, cmax = 0;
     for (int r = 0; r < c->nranks; ++r) { tot += c->m_counts[r]; cmax = std::max(cmax, c->m_counts[r]); }
@@ -1533,6 +1580,18 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
     ensure_static_cells(c);
+    // Which spread: measured on a B200 (profiles/r02_spread_kernels.md) the three kernels are within ~25 % of
+    // each other; the owner-computes tensor-core kernel wins from a few 1e5 charges per GPU upward, the
+    // red.global kernel below (fewer fixed costs: no per-step stencil pass, no tile scan).
+    c->spread_atomic = c->spread_mode == 0 ||
+                       (c->spread_mode < 0 && (long long)c->m_total / c->nranks < 250000LL);
+    if (c->have_pppm && c->splan.use_mma) {  // per-charge stencil origins / weights of the tensor-core spread
+      const size_t mm = (size_t)std::max(c->m_slots, 1);
+      c->d_sp_origin.reserve(mm);
+      c->d_sp_weights.reserve(mm * 3 * c->pg.order);
+      c->splan.origin = c->d_sp_origin.p;
+      c->splan.weights = c->d_sp_weights.p;
+    }
     c->d_cellcount.zero((size_t)c->grid_b.ncells + 8, s);
     c->d_cellstart.zero((size_t)c->grid_b.ncells + 8, s);
     drop_graphs(c);
@@ -1651,29 +1710,138 @@ int conp_get_density_region(conp_ctx *c, int which, const int lo[3], const int h
 int conp_get_potential_brick(conp_ctx *c, double *brick_out) {
   return guard(c, [&] {
     need(c->have_pppm && c->solved, "conp_get_potential_brick: no PPPM solve yet");
-    // full-mesh potential on demand (the per-step path only evaluates the electrode planes):
-    // the reference's 3-D transform, pppm_conp.cpp:230-267
+    DevBuf<double> full;
+    full_mesh_potential(c, false, full);
+    CUDA_CHECK(cudaMemcpyAsync(brick_out, full.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int conp_mesh_potential(conp_ctx *c, int n, const double *xyz, double *u_out) {
+  return guard(c, [&] {
+    if (!c->have_pppm) CONP_THROW(CONP_ERR_STATE, "Compute requires a compatible KSpace provider like pppm/conp");
+    need(c->solved, "conp_mesh_potential: no solve yet");
+    if (n < 0 || (n > 0 && (!xyz || !u_out))) CONP_THROW(CONP_ERR_ARG, "conp_mesh_potential: bad arguments");
+    if (n == 0) return;
     cudaStream_t s = c->stream;
-    const PPPMGeom &g = c->pg;
-    DevBuf<double> full, gd;
-    DevBuf<cufftDoubleComplex> work;
-    full.zero(c->ngrid, s);
-    work.reserve(c->nhalf);
-    gd.upload(c->h_ghalf, s);
-    c->launches += launch_expand_planes(s, c->plane, g.zs_n, g.nz, g.zin_lo + g.zs_lo, nullptr, c->d_brick.p, full.p);
-    if (c->nranks > 1) comm_allreduce_sum_f64(c->comm, full.p, c->ngrid, s);
-    cufftHandle pf, pb;
-    CUFFT_CHECK(cufftPlan3d(&pf, g.nz, g.ny, g.nx, CUFFT_D2Z));
-    CUFFT_CHECK(cufftPlan3d(&pb, g.nz, g.ny, g.nx, CUFFT_Z2D));
-    CUFFT_CHECK(cufftSetStream(pf, s));
-    CUFFT_CHECK(cufftSetStream(pb, s));
-    CUFFT_CHECK(cufftExecD2Z(pf, full.p, work.p));
-    c->launches += launch_pppm_green_mul(s, c->nhalf, work.p, gd.p);
-    CUFFT_CHECK(cufftExecZ2D(pb, work.p, full.p));
-    CUDA_CHECK(cudaMemcpyAsync(brick_out, full.p, sizeof(double) * c->ngrid, cudaMemcpyDeviceToHost, s));
+    DevBuf<double> full, dx, dout;
+    full_mesh_potential(c, true, full);
+    dx.upload(xyz, 3 * (size_t)n, s);
+    dout.reserve(n);
+    c->launches += launch_mesh_potential(s, c->pg, c->d_rho.p, n, dx.p, full.p, dout.p);
+    CUDA_CHECK(cudaMemcpyAsync(u_out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    cufftDestroy(pf);
-    cufftDestroy(pb);
+  });
+}
+
+int conp_electrode_potential(conp_ctx *c, int pairflag, int kspaceflag, double eta, int qsumflag, double *phi_out) {
+  return guard(c, [&] {
+    need(c->solved, "conp_electrode_potential: no solve yet");
+    if (!phi_out) CONP_THROW(CONP_ERR_ARG, "conp_electrode_potential: null output");
+    if (kspaceflag && !c->have_pppm)  // compute_potential_atom.cpp:111-113
+      CONP_THROW(CONP_ERR_STATE, "Compute requires a compatible KSpace provider like pppm/conp");
+    cudaStream_t s = c->stream;
+    const int N = c->N, nr = c->r1 - c->r0;
+    std::vector<double> phi(N, 0.0), q(N);
+    CUDA_CHECK(cudaMemcpyAsync(q.data(), c->d_q.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (pairflag) {
+      // compute_pair_potential (:223-318): every pair inside cutsq and cut_coulsq, erfc(g r)/r minus the
+      // Gaussian term erfc(eta r)/r (one electrode atom) or erfc(eta r / sqrt 2)/r (two); no `etypes` filter
+      const int n1 = c->ntypes + 1;
+      double cut_coulsq = c->cut_coul * c->cut_coul;
+      const double cut_erfc = ERFC_MAX * ERFC_MAX / (c->g_ewald * c->g_ewald);
+      if (cut_coulsq > cut_erfc) cut_coulsq = cut_erfc;
+      std::vector<double> call((size_t)n1 * n1, 0.0);
+      double mx = 0.0;
+      for (int it = 1; it <= c->ntypes; ++it)
+        for (int jt = 1; jt <= c->ntypes; ++jt) {
+          call[(size_t)it * n1 + jt] = std::min(c->h_cutsq[(size_t)it * n1 + jt], cut_coulsq);
+          mx = std::max(mx, call[(size_t)it * n1 + jt]);
+        }
+      DevBuf<double> dcut, dp1, dp2;
+      dcut.upload(call, s);
+      dp1.zero(c->vlen, s);
+      dp2.zero(c->vlen, s);
+      PairTables pt = pair_tables(c, dcut.p);
+      pt.pairmode = CONP_PAIR_ETA;  // the compute knows one Gaussian width only
+      pt.eta = eta;
+      const double rc = std::sqrt(mx);
+      if (rc > 0.0 && nr > 0) {
+        // electrolyte -> electrode: the step's cell-sorted charges, traversal lists rebuilt for this radius
+        if (c->m_total > 0) {
+          CellGrid g = c->grid_b;
+          g.rc = rc;
+          for (int a = 0; a < 3; ++a) g.smax[a] = g.periodic[a] ? (int)std::ceil(g.rc / g.prd[a]) + 1 : 0;
+          std::vector<int> run_start;
+          std::vector<PairRun> runs;
+          build_pair_runs(g, c->r0, c->r1, c->h_xyz.data(), run_start, runs);
+          DevBuf<int> drs;
+          DevBuf<PairRun> druns;
+          drs.upload(run_start, s);
+          druns.upload(runs, s);
+          c->launches += launch_pair_b(s, g, pt, c->r0, c->r1, c->d_ex.p, c->d_ey.p, c->d_ez.p, c->d_etype.p, drs.p,
+                                       druns.p, c->d_sorted.p, c->d_stype.p, c->d_sortedf.p, c->d_cellstart.p, dp1.p);
+          CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+        // electrode -> electrode (all images)
+        CellGrid g = make_cell_grid(c->boxlo, c->prd, c->periodic, rc);
+        std::vector<EPos> sorted;
+        std::vector<int> cs, run_start;
+        std::vector<PairRun> runs;
+        build_electrode_cells(g, 0, N, c->h_xyz.data(), c->h_type.data(), sorted, cs);
+        build_pair_runs(g, c->r0, c->r1, c->h_xyz.data(), run_start, runs);
+        DevBuf<EPos> dsorted;
+        DevBuf<int> dcs, drs;
+        DevBuf<PairRun> druns;
+        dsorted.upload(sorted, s);
+        dcs.upload(cs, s);
+        drs.upload(run_start, s);
+        druns.upload(runs, s);
+        c->launches += launch_pair_P(s, g, pt, dsorted.p, dcs.p, c->r0, c->r1, c->d_ex.p, c->d_ey.p, c->d_ez.p,
+                                     c->d_etype.p, drs.p, druns.p, c->d_q.p, dp2.p);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+      }
+      if (c->nranks > 1) {
+        comm_allgather(c->comm, dp1.p + c->r0, dp1.p, sizeof(double) * c->rpr, s);
+        comm_allgather(c->comm, dp2.p + c->r0, dp2.p, sizeof(double) * c->rpr, s);
+      }
+      std::vector<double> p1(N), p2(N);
+      CUDA_CHECK(cudaMemcpyAsync(p1.data(), dp1.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaMemcpyAsync(p2.data(), dp2.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (int i = 0; i < N; ++i) phi[i] += -p1[i] + p2[i];  // launch_pair_b returns -sum q dudq
+    }
+    if (kspaceflag) {
+      // potential[i] -= compute_particle_potential(i) = -(mesh sum) + 2 g q_i / sqrt(pi)  (pppm_conp.cpp:452-488),
+      // + eta q_i sqrt(2)/sqrt(pi) for the Gaussian (electrode) atoms (:168)
+      DevBuf<double> full, dout;
+      full_mesh_potential(c, true, full);
+      dout.reserve(N);
+      c->launches += launch_mesh_potential(s, c->pg, c->d_rho.p, N, c->d_exyz.p, full.p, dout.p);
+      std::vector<double> u(N);
+      double qz = 0.0;
+      CUDA_CHECK(cudaMemcpyAsync(u.data(), dout.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaMemcpyAsync(&qz, c->scal(2), sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (int i = 0; i < N; ++i) {
+        phi[i] += u[i] - 2.0 * c->g_ewald * q[i] / MY_PIS;
+        if (eta != 0.0) phi[i] += eta * q[i] * std::sqrt(2.0) / MY_PIS;
+      }
+      if (c->slabflag) {  // ComputePotentialAtom::slabcorr (:333-358): all atoms, electrode and electrolyte
+        const double volume = c->prd[0] * c->prd[1] * c->prd[2] * c->slab_volfactor;
+        const double pi2vol = 2.0 * MY_PI / volume;
+        double dip = qz, qsum = c->qsum_elyte;
+        for (int i = 0; i < N; ++i) { dip += q[i] * c->h_xyz[3 * i + 2]; qsum += q[i]; }
+        const double slabcorr = 2.0 * pi2vol * dip;
+        for (int i = 0; i < N; ++i) {
+          const double z = c->h_xyz[3 * i + 2];
+          phi[i] += z * slabcorr;
+          if (qsumflag) phi[i] -= pi2vol * qsum * z * z;
+        }
+      }
+    }
+    std::memcpy(phi_out, phi.data(), sizeof(double) * N);
   });
 }
 

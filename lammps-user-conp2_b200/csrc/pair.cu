@@ -55,7 +55,7 @@ __device__ __forceinline__ double ferfcr_sqrt(double a2_r2) {
   return 0.0;
 }
 
-enum { MODE_B = 0, MODE_A = 1 };
+enum { MODE_B = 0, MODE_A = 1, MODE_P = 2 };  // MODE_P: MODE_A's pairs, summed with the partners' charges
 
 // dudq of fix_conp.cpp:1263-1264 / 1335-1336; (it, jt) = (electrode type, partner type)
 template <int MODE>
@@ -391,7 +391,8 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
             const PairRun *__restrict__ runs,
             const PosQ *__restrict__ sorted, const int *__restrict__ sorted_type,  // MODE_B targets
             const float4 *__restrict__ sorted_f, float cutmax_f,
-            const EPos *__restrict__ esorted,                                      // MODE_A targets
+            const EPos *__restrict__ esorted,                                      // MODE_A / MODE_P targets
+            const double *__restrict__ q_ele,                                      // MODE_P: charges (eleall order)
             double *__restrict__ out, size_t pitch) {
   __shared__ WarpQueue queues[PAIR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -414,8 +415,10 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
       const double dx = xi - (p.x + wq.rsq[e]), dy = yi - (p.y + wq.aux[e]), dz = zi - (p.z + wq.shz[e]);
       const double rsq = dx * dx + dy * dy + dz * dz;
       if (rsq < __ldg(cut_row + jt)) acc = fma(p.q, dudq_pair<MODE_B>(pt, rsq, it, jt), acc);
-    } else {
+    } else if (MODE == MODE_A) {
       atomicAdd(A_row + wq.i[e], dudq_pair<MODE_A>(pt, wq.rsq[e], it, wq.t[e]));
+    } else {  // MODE_P: potential of the other electrode charges (compute_potential_atom.cpp:286-316)
+      acc = fma(__ldg(q_ele + wq.i[e]), dudq_pair<MODE_A>(pt, wq.rsq[e], it, wq.t[e]), acc);
     }
   };
   const int r0 = run_start[i - row_begin], r1 = run_start[i - row_begin + 1];
@@ -463,10 +466,10 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
   }
   __syncwarp();
   if (lane < qn) consume(lane);
-  if (MODE == MODE_B) {
+  if (MODE != MODE_A) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[i] = -acc;
+    if (lane == 0) out[i] = MODE == MODE_B ? -acc : acc;
   }
 }
 
@@ -774,7 +777,7 @@ int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int r
   const float cutmax_f = (float)(g.rc * g.rc + slack);
   pair_kernel<MODE_B><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
       g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, run_start, runs, sorted, sorted_type, sorted_f,
-      cutmax_f, nullptr, b_real, 0);
+      cutmax_f, nullptr, nullptr, b_real, 0);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -787,7 +790,20 @@ int launch_pair_A(cudaStream_t s, const CellGrid &g, const PairTables &pt, const
   if (n <= 0) return 0;
   pair_kernel<MODE_A><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
       g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, run_start, runs, nullptr, nullptr, nullptr, 0.0f,
-      esorted, A_rows, pitch);
+      esorted, nullptr, A_rows, pitch);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_pair_P(cudaStream_t s, const CellGrid &g, const PairTables &pt, const EPos *esorted,
+                  const int *cell_start, int row_begin, int row_end, const double *ex, const double *ey,
+                  const double *ez, const int *etype, const int *run_start, const PairRun *runs,
+                  const double *q_ele, double *phi) {
+  const int n = row_end - row_begin;
+  if (n <= 0) return 0;
+  pair_kernel<MODE_P><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
+      g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, run_start, runs, nullptr, nullptr, nullptr, 0.0f,
+      esorted, q_ele, phi, 0);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

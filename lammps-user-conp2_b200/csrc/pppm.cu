@@ -186,7 +186,11 @@ spread_tile_kernel(PPPMGeom g, SpreadPlan sp, RhoCoeff rc, const PosQ *__restric
     const int ez = min(sp.tz, g.zs_n - t0), ey = min(sp.ty, NY - y0), ex = min(sp.tx, NX - x0);
     const int ezv = ez + sp.halo_z, eyv = ey + sp.halo_y, exv = ex + sp.halo_x;  // valid positions incl. halo
     const int rb = sp.run_start[tile_id], re = sp.run_start[tile_id + 1];
-    for (int i = lane; i < tile_len; i += 32) tile[i] = 0.0;
+    {
+      double2 *t2 = reinterpret_cast<double2 *>(tile);
+      for (int i = lane; i < (tile_len >> 1); i += 32) t2[i] = make_double2(0.0, 0.0);
+      if ((tile_len & 1) && lane == 0) tile[tile_len - 1] = 0.0;
+    }
     __syncwarp();
 
     for (int rbase = rb; rbase < re; rbase += 32) {
@@ -229,7 +233,8 @@ spread_tile_kernel(PPPMGeom g, SpreadPlan sp, RhoCoeff rc, const PosQ *__restric
           if (j0 + lane < je) nxt = atoms[j0 + lane];
         }
         bool hit = false;
-        int my_yx = 0, my_ob = 0;
+        unsigned my_lo = 0, my_hi = 0;
+        int my_ob = 0;
         if (p.q != 0.0) {  // pppm_conp.cpp:161
           const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
           const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
@@ -269,9 +274,18 @@ spread_tile_kernel(PPPMGeom g, SpreadPlan sp, RhoCoeff rc, const PosQ *__restric
                     w[P + k] = rho1d_c<P>(rc, k, dy);
                     w[2 * P + k] = rho1d_c<P>(rc, k, dx);
                   }
-                  // plane mask (bit n: plane rz + n lies in the tile) | ry + 8 | rx + 8, and the byte offset of
-                  // the stencil origin in the tile (may be negative: the valid points are not)
-                  my_yx = ((int)(((1u << kb) - 1u) & ~((1u << ka) - 1u)) << 24) | ((ry + 8) << 12) | (rx + 8);
+                  // which of the order x order footprint points (item m * order + l) and which of the `order`
+                  // planes lie in the tile, and the byte offset of the stencil origin in the tile (may be
+                  // negative: the valid points are not)
+                  // (valid rows and columns are intervals: the footprint mask is the column mask repeated per row)
+                  const int la = max(0, -rx), lb = min(P, exv - rx), ma = max(0, -ry), mb = min(P, eyv - ry);
+                  const unsigned long long colmask = ((1u << lb) - 1u) & ~((1u << la) - 1u);
+                  unsigned long long items = 0ull;
+#pragma unroll
+                  for (int m = 0; m < P; ++m)
+                    if (m >= ma && m < mb) items |= colmask << (m * P);
+                  my_lo = (unsigned)items;
+                  my_hi = (unsigned)(items >> 32) | ((((1u << kb) - 1u) & ~((1u << ka) - 1u)) << 24);
                   my_ob = 8 * (rz * ps + ry * rs + rx);
                 }
               }
@@ -283,15 +297,14 @@ spread_tile_kernel(PPPMGeom g, SpreadPlan sp, RhoCoeff rc, const PosQ *__restric
         while (mask) {
           const int src = __ffs(mask) - 1;
           mask &= mask - 1;
-          const unsigned yx = (unsigned)__shfl_sync(FULL, my_yx, src);
+          const unsigned lo = __shfl_sync(FULL, my_lo, src);
+          const unsigned hi = __shfl_sync(FULL, my_hi, src);  // items 32.. in bits 0..16, plane mask in bits 24..30
           const int ob = __shfl_sync(FULL, my_ob, src);
-          const unsigned pm = yx >> 24;
-          const int ry = (int)((yx >> 12) & 0xfffu) - 8, rx = (int)(yx & 0xfffu) - 8;
+          const unsigned pm = hi >> 24;
           const double *w = wsc + src * WS;
 #pragma unroll
           for (int r2 = 0; r2 < NR; ++r2) {
-            const int row = ry + lm[r2], col = rx + ll[r2];
-            if (lin[r2] && (unsigned)row < (unsigned)eyv && (unsigned)col < (unsigned)exv) {
+            if (lin[r2] && (((r2 == 0 ? lo : hi) >> lane) & 1u)) {
               const double wyx = w[P + lm[r2]] * w[2 * P + ll[r2]];
               char *t = tile_b + (ob + lconst[r2]);
               double v[P];
@@ -340,13 +353,222 @@ spread_tile_kernel(PPPMGeom g, SpreadPlan sp, RhoCoeff rc, const PosQ *__restric
       __syncwarp();
     }
     // one plain store per mesh point of the tile
-    for (int pr = 0; pr < ez * ey; ++pr) {
-      const int pl = pr / ey, row = pr - pl * ey;
-      const double *q = tile + pl * ps + row * rs;
-      double *dst = brick + ((size_t)(t0 + pl) * NY + (y0 + row)) * NX + x0;
-      for (int col = lane; col < ex; col += 32) dst[col] = q[col];
+    for (int pl = 0; pl < ez; ++pl) {
+      const double *q = tile + pl * ps + lane;
+      double *dst = brick + ((size_t)(t0 + pl) * NY + y0) * NX + x0 + lane;
+      for (int row = 0; row < ey; ++row, q += rs, dst += NX)
+        for (int col = lane; col < ex; col += 32) dst[col - lane] = q[col - lane];
     }
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The same owner-computes spread with the accumulation on the FP64 tensor cores.
+//
+// On a z-plane the charge assignment of a group of charges is a small matrix product,
+//     rho_n[y][x] += sum_a (zw_a[n] wy_a[y]) * wx_a[x],
+// with the stencil weights zero outside the `order` points a charge touches: C (8 x 8) += A (8 x 4) . B (4 x 8)
+// is one mma.sync.m8n8k4.f64 (SASS DMMA) for 4 charges, 8 mesh rows and 8 mesh columns.  A warp owns a tile
+// of TZ planes x 8 rows x 32 columns as TZ x 4 accumulator fragments IN REGISTERS: no shared-memory
+// read-modify-write and no dependent load/store chain per charge, only independent DMMAs.
+//
+// Two kernels.  stencil_prepass_kernel runs once per step over the cell-sorted charges: stencil origin
+// (pppm_conp.cpp:146-148), the 3 x order weights (:199-203, z weights pre-multiplied by q/dV) and the
+// "Out of range atoms" check (:167), so no charge can be dropped silently and nothing is recomputed per
+// tile.  spread_mma_kernel then reads, per tile, the 16-byte origins of the charges in the tile's candidate
+// cell runs (plan_pppm_spread_tiles), 32 at a time; the ones that overlap get a zero-padded copy of their
+// weights in tile coordinates in a shared scratch row (zw over the TZ planes, wy over the 8 rows, wx over
+// the 32 columns) and are taken in groups of 4 consecutive charges -- neighbours in the cell-sorted order,
+// so a group touches few planes and column blocks, and only those (plane, block) fragments get a DMMA
+// (warp-uniform masks).  Products and sums are exact FP64 FMAs; the summation order is the order of the
+// sorted charges.  Used when no tile spans a whole periodic axis (spread_tile_kernel keeps those meshes).
+// ---------------------------------------------------------------------------
+constexpr int SM_TY = 8, SM_TX = 32, SM_NXB = SM_TX / 8;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// origin[j] = (nx, ny, zi0, ok): mesh index of the stencil's first point along x and y (unwrapped), compact
+// input plane of its first plane, ok = 0 for q == 0 or an out-of-range charge; weights[j][3 P]
+template <int P>
+__global__ void __launch_bounds__(256)
+stencil_prepass_kernel(PPPMGeom g, RhoCoeff rc, int m_bound, const int *__restrict__ count_ptr,
+                       const PosQ *__restrict__ atoms, int4 *__restrict__ origin, double *__restrict__ weights,
+                       int *__restrict__ range_flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = count_ptr ? min(m_bound, *count_ptr) : m_bound;
+  if (j >= m) return;
+  const PosQ p = atoms[j];
+  int4 o = make_int4(0, 0, 0, 0);
+  if (p.q != 0.0) {  // pppm_conp.cpp:161
+    const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
+    const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
+    const double fz = (p.z - g.boxlo[2]) * g.delinv[2];
+    if (!(fabs(fx) < OFFSET / 2 && fabs(fy) < OFFSET / 2 && fabs(fz) < OFFSET / 2)) {
+      *range_flag = 1;  // "Out of range atoms - cannot compute PPPM", pppm_conp.cpp:167
+    } else {
+      const int nx = (int)(fx + g.shift) - OFFSET;  // :146-148
+      const int ny = (int)(fy + g.shift) - OFFSET;
+      const int nz = (int)(fz + g.shift) - OFFSET;
+      const int zi0 = wrapi(nz + g.nlower - g.zin_lo, g.nz);
+      if (g.nzi < g.nz && zi0 + P > g.nzi) {
+        *range_flag = 1;  // a plane outside what the box can reach: "Out of range atoms"
+      } else {
+        o = make_int4(wrapi(nx + g.nlower, g.nx), wrapi(ny + g.nlower, g.ny), zi0, 1);
+        const double dx = nx + g.shiftone - fx;  // :199-201
+        const double dy = ny + g.shiftone - fy;
+        const double dz = nz + g.shiftone - fz;
+        const double z0 = g.delvolinv * p.q;  // :205
+        double *w = weights + (size_t)j * (3 * P);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          w[k] = z0 * rho1d_c<P>(rc, k, dz);
+          w[P + k] = rho1d_c<P>(rc, k, dy);
+          w[2 * P + k] = rho1d_c<P>(rc, k, dx);
+        }
+      }
+    }
+  }
+  origin[j] = o;
+}
+
+template <int P, int TZ>
+__global__ void __launch_bounds__(32)
+spread_mma_kernel(PPPMGeom g, SpreadPlan sp, const int4 *__restrict__ origin, const double *__restrict__ weights,
+                  const int *__restrict__ cell_start, double *__restrict__ brick) {
+  constexpr int WS = (TZ + SM_TY + SM_TX) | 1;  // scratch row: zw[TZ] | wy[8] | wx[32], odd stride
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ double wsc[32 * WS];
+  __shared__ unsigned masks[32];  // per overlapping charge: plane mask | column-block mask << 16
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int fy = lane >> 2, fa = lane & 3;  // fragment row (A: mesh row, B: mesh column) / charge of the group
+  const int NX = g.nx, NY = g.ny, NZ = g.nz;
+
+  for (;;) {
+    int tile_id = 0;
+    if (lane == 0) tile_id = atomicAdd(sp.counter, 1);
+    tile_id = __shfl_sync(FULL, tile_id, 0);
+    if (tile_id >= sp.ntiles) break;
+    const int ix = tile_id % sp.ntx, iyz = tile_id / sp.ntx;
+    const int iy = iyz % sp.nty, iz = iyz / sp.nty;
+    const int t0 = iz * TZ, y0 = iy * SM_TY, x0 = ix * SM_TX;
+    const int ez = min(TZ, g.zs_n - t0), ey = min(SM_TY, NY - y0), ex = min(SM_TX, NX - x0);
+    const int rb = sp.run_start[tile_id], re = sp.run_start[tile_id + 1];
+    double acc[TZ][SM_NXB][2];
+#pragma unroll
+    for (int n = 0; n < TZ; ++n)
+#pragma unroll
+      for (int b = 0; b < SM_NXB; ++b) acc[n][b][0] = acc[n][b][1] = 0.0;
+
+    for (int rbase = rb; rbase < re; rbase += 32) {
+      // flat sequence of 32-charge chunks over up to 32 cell runs (see spread_tile_kernel)
+      int my_jb = 0, my_je = 0;
+      if (rbase + lane < re) {
+        const int2 run = sp.runs[rbase + lane];
+        my_jb = cell_start[run.x];
+        my_je = cell_start[run.y];
+      }
+      const int my_nch = (my_je - my_jb + 31) >> 5;
+      int incl = my_nch;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += u;
+      }
+      const int nchunks = __shfl_sync(FULL, incl, 31);
+      auto locate = [&](int c) {  // index of this lane's charge in chunk c, or -1
+        const unsigned mk = __ballot_sync(FULL, incl > c);
+        const int i = __ffs(mk) - 1;
+        const int jb_i = __shfl_sync(FULL, my_jb, i), excl_i = __shfl_sync(FULL, incl - my_nch, i);
+        const int je = __shfl_sync(FULL, my_je, i);
+        const int j = jb_i + ((c - excl_i) << 5) + lane;
+        return j < je ? j : -1;
+      };
+      int jn = nchunks > 0 ? locate(0) : -1;
+      int4 on = make_int4(0, 0, 0, 0);
+      if (jn >= 0) on = origin[jn];
+      for (int c = 0; c < nchunks; ++c) {
+        const int j = jn;
+        const int4 o = on;
+        jn = -1;
+        on.w = 0;
+        if (c + 1 < nchunks) {  // the next chunk's origins fly while this one is spread
+          jn = locate(c + 1);
+          if (jn >= 0) on = origin[jn];
+        }
+        // signed start of the stencil relative to the tile (tiles are shorter than the mesh by at least the
+        // stencil, so the touched points form one interval per axis)
+        int rz = o.z - g.zs_lo - t0, ry = o.y - y0, rx = o.x - x0;
+        rz += rz < 0 ? NZ : 0;   // o.z in [0, NZ), zs_lo + t0 in [0, NZ)
+        ry += ry < 0 ? NY : 0;
+        rx += rx < 0 ? NX : 0;
+        if (rz >= ez) rz -= NZ;
+        if (ry >= ey) ry -= NY;
+        if (rx >= ex) rx -= NX;
+        const bool hit = o.w != 0 && rz > -P && rz < ez && ry > -P && ry < ey && rx > -P && rx < ex;
+        const unsigned hits = __ballot_sync(FULL, hit);
+        const int nh = __popc(hits);
+        // clear the scratch rows that will be used, then drop the weights at their tile coordinates
+        for (int t = lane; t < nh * WS; t += 32) wsc[t] = 0.0;
+        __syncwarp();
+        if (hit) {
+          const int r = __popc(hits & lt_mask);
+          const double *w = weights + (size_t)j * (3 * P);
+          double *row = wsc + r * WS;
+          unsigned planes = 0u, blocks = 0u;
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            const double wz = w[k], wy = w[P + k], wx = w[2 * P + k];
+            if ((unsigned)(rz + k) < (unsigned)ez) { row[rz + k] = wz; planes |= 1u << (rz + k); }
+            if ((unsigned)(ry + k) < (unsigned)ey) row[TZ + ry + k] = wy;
+            if ((unsigned)(rx + k) < (unsigned)ex) { row[TZ + SM_TY + rx + k] = wx; blocks |= 1u << ((rx + k) >> 3); }
+          }
+          masks[r] = planes | (blocks << 16);
+        }
+        __syncwarp();
+        for (int g0 = 0; g0 < nh; g0 += 4) {
+          const int row = g0 + fa;
+          const bool have = row < nh;
+          unsigned pbg = have ? masks[row] : 0u;
+          pbg |= __shfl_xor_sync(FULL, pbg, 1);
+          pbg |= __shfl_xor_sync(FULL, pbg, 2);  // union over the 4 charges: identical in every lane
+          const double *w = wsc + row * WS;
+          const double ay = have ? w[TZ + fy] : 0.0;  // A fragment: row fy of the tile, charge fa
+          double bx[SM_NXB];
+#pragma unroll
+          for (int b = 0; b < SM_NXB; ++b)  // B fragment: column 8 b + fy of the tile, charge fa
+            bx[b] = (have && (pbg & (0x10000u << b))) ? w[TZ + SM_TY + 8 * b + fy] : 0.0;
+#pragma unroll
+          for (int n = 0; n < TZ; ++n) {
+            if (pbg & (1u << n)) {
+              const double a = ay * (have ? w[n] : 0.0);
+#pragma unroll
+              for (int b = 0; b < SM_NXB; ++b)
+                if (pbg & (0x10000u << b)) dmma884(acc[n][b][0], acc[n][b][1], a, bx[b]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // C fragment: row = lane / 4, columns 2 (lane % 4) + {0, 1} of the 8 x 8 block: one plain store per point
+#pragma unroll
+    for (int n = 0; n < TZ; ++n) {
+      if (n < ez && fy < ey) {
+        double *dst = brick + ((size_t)(t0 + n) * NY + (y0 + fy)) * NX + x0;
+#pragma unroll
+        for (int b = 0; b < SM_NXB; ++b) {
+          const int col = 8 * b + 2 * fa;
+          if (col < ex) dst[col] = acc[n][b][0];
+          if (col + 1 < ex) dst[col + 1] = acc[n][b][1];
+        }
+      }
+    }
   }
 }
 
@@ -664,6 +886,35 @@ ele_spread_kernel(PPPMGeom g, int n_ele, int row_begin, int row_end, const int *
   for (int l = 0; l < order; ++l) atomicAdd(row + wi[l], x0 * w[l]);
 }
 
+// PPPMCONP::compute_particle_potential, the mesh sum (pppm_conp.cpp:452-484): one warp per point, lanes over
+// the order^3 stencil, weights by Horner from the point's position; u is the full periodic mesh
+__global__ void __launch_bounds__(256)
+mesh_potential_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int n, const double *__restrict__ xyz,
+                      const double *__restrict__ u, double *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= n) return;
+  const int order = g.order, npts = order * order * order;
+  const double fx = (xyz[3 * i] - g.boxlo[0]) * g.delinv[0];
+  const double fy = (xyz[3 * i + 1] - g.boxlo[1]) * g.delinv[1];
+  const double fz = (xyz[3 * i + 2] - g.boxlo[2]) * g.delinv[2];
+  const int nx = (int)(fx + g.shift) - OFFSET, ny = (int)(fy + g.shift) - OFFSET, nz = (int)(fz + g.shift) - OFFSET;
+  const double dx = nx + g.shiftone - fx, dy = ny + g.shiftone - fy, dz = nz + g.shiftone - fz;
+  double acc = 0.0;
+  for (int t = lane; t < npts; t += 32) {
+    const int nn = t / (order * order), r = t - nn * order * order;
+    const int m = r / order, l = r - m * order;
+    const double z0 = rho1d(rho_coeff, order, nn, dz);
+    const double y0 = z0 * rho1d(rho_coeff, order, m, dy);
+    const double x0 = y0 * rho1d(rho_coeff, order, l, dx);
+    const int mz = wrapi(nn + g.nlower + nz, g.nz), my = wrapi(m + g.nlower + ny, g.ny), mx = wrapi(l + g.nlower + nx, g.nx);
+    acc = fma(x0, u[((size_t)mz * g.ny + my) * g.nx + mx], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[i] = acc;
+}
+
 __global__ void __launch_bounds__(256)
 add_bricks_kernel(size_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -703,11 +954,13 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
 void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sms, std::vector<int> &run_start,
                             std::vector<int2> &runs, SpreadPlan &plan) {
   const int P = g.order;
-  int T[3] = {32, 8, 8};  // x, y, z
+  int T[3] = {32, 8, 4};  // x, y, z
   if (const char *e = getenv("CONP_SPREAD_TILE")) {
     int a = 0, b = 0, c = 0;
     if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { T[2] = a; T[1] = b; T[0] = c; }
   }
+  // tensor-core kernel: 8 rows x 32 columns x (4 | 8) planes in registers, no whole-axis tiles
+  const bool mma_shape = T[0] == SM_TX && T[1] == SM_TY && (T[2] == 4 || T[2] == 8);
   const int len[3] = {g.nx, g.ny, g.zs_n};
   const int mod[3] = {g.nx, g.ny, g.nz};
   // can a stencil wrap around inside this rank's index range?  x, y: always (periodic mesh); z: only if the
@@ -721,6 +974,7 @@ void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sm
       nt[a] = (len[a] + T[a] - 1) / T[a]; te[a] = T[a]; halo[a] = 0;
     }
   }
+  const int want_mma = plan.use_mma;  // set by the caller (an input): may the tensor-core kernel be used?
   plan = SpreadPlan();
   run_start.clear();
   runs.clear();
@@ -789,15 +1043,46 @@ void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sm
   run_start.push_back((int)runs.size());
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(227 * 1024 - 1024) / (plan.smem + 1024)));
   plan.grid = std::min(plan.ntiles, num_sms * per_sm);
+  plan.use_mma = want_mma && mma_shape && !halo[0] && !halo[1] && !halo[2] && nt[0] * te[0] >= len[0] &&
+                 te[0] == SM_TX && te[1] == SM_TY && (te[2] == 4 || te[2] == 8);
+  // the tensor-core kernel keeps its tile in registers: one-warp CTAs, as many as the register file holds
+  plan.grid_mma = std::min(plan.ntiles, num_sms * (plan.tz == 4 ? 16 : 9));
 }
 
 int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan &plan, const double *rho_coeff_host,
-                             const PosQ *atoms, const int *cell_start, double *brick, int *range_flag) {
+                             const PosQ *atoms, const int *cell_start, int m_bound, const int *count_ptr,
+                             double *brick, int *range_flag) {
   if (plan.ntiles <= 0 || g.zs_n <= 0) return 0;
   CUDA_CHECK(cudaMemsetAsync(plan.counter, 0, sizeof(int), s));
   RhoCoeff rho_coeff;
   std::memset(&rho_coeff, 0, sizeof(rho_coeff));
   std::memcpy(rho_coeff.c, rho_coeff_host, sizeof(double) * g.order * g.order);
+  // no whole-axis tiles, default shape: accumulate on the FP64 tensor cores (CONP_SPREAD_SMEM=1: A/B run of
+  // the shared-memory tile kernel)
+  if (plan.use_mma) {
+    const int mb = m_bound;
+    if (mb <= 0) {
+      CUDA_CHECK(cudaMemsetAsync(brick, 0, sizeof(double) * (size_t)g.zs_n * g.ny * g.nx, s));
+      return 0;
+    }
+#define CONP_SPM_CASE(P_)                                                                                          \
+  case P_:                                                                                                         \
+    stencil_prepass_kernel<P_><<<(mb + 255) / 256, 256, 0, s>>>(g, rho_coeff, mb, count_ptr, atoms, plan.origin,  \
+                                                                plan.weights, range_flag);                        \
+    if (plan.tz == 4)                                                                                              \
+      spread_mma_kernel<P_, 4><<<plan.grid_mma, 32, 0, s>>>(g, plan, plan.origin, plan.weights, cell_start, brick); \
+    else                                                                                                           \
+      spread_mma_kernel<P_, 8><<<plan.grid_mma, 32, 0, s>>>(g, plan, plan.origin, plan.weights, cell_start, brick); \
+    break;
+    switch (g.order) {
+      CONP_SPM_CASE(1) CONP_SPM_CASE(2) CONP_SPM_CASE(3) CONP_SPM_CASE(4) CONP_SPM_CASE(5) CONP_SPM_CASE(6)
+      CONP_SPM_CASE(7)
+      default: CONP_THROW(CONP_ERR_ARG, "PPPM order %d not supported", g.order);
+    }
+#undef CONP_SPM_CASE
+    CUDA_CHECK(cudaGetLastError());
+    return 2;
+  }
   // LAMMPS' default order with the default tile shape: strides known at compile time
   constexpr int RS5 = 37, PS5 = 8 * 37;
   if (g.order == 5 && plan.rs == RS5 && plan.ps == PS5) {
@@ -990,6 +1275,14 @@ int launch_pppm_ele_spread(cudaStream_t s, const PPPMGeom &g, int n, int row_beg
   const long long threads = (long long)n * g.order * g.order;
   ele_spread_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, n, row_begin, row_end, widx, weights, sb,
                                                                      setq, qinit, scal, q_out, brick);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+int launch_mesh_potential(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int n, const double *xyz,
+                          const double *u_full, double *out) {
+  if (n <= 0) return 0;
+  mesh_potential_kernel<<<(n + 7) / 8, 256, 0, s>>>(g, rho_coeff, n, xyz, u_full, out);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -24,6 +24,8 @@ import sys
 
 import numpy as np
 
+MY_PIS = 1.77245385090551602729  # sqrt(pi), math_const.h
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.normpath(os.path.join(_HERE, "..", "lammps-user-conp2_b200"))
 if _PKG not in sys.path:
@@ -502,6 +504,77 @@ class OracleFixConp:
 
     def compute_scalar(self):
         return self.scalar_output
+
+    # -- compute potential/atom for the electrode atoms ---------------------------
+    def mesh_potential(self, xyz):
+        """Mesh sum of PPPMCONP::compute_particle_potential (pppm_conp.cpp:452-484) at positions xyz with
+        u_brick = potential of the total (electrolyte + electrode) density of the last update."""
+        t = self.pppm
+        s = self.lmp.system
+        u_tot = pppm_poisson(self.elyte_density + self.ele_density, t.greensfn, t.mesh, self.fft_workers)
+        xyz = f64(xyz).reshape(-1, 3)
+        n = xyz.shape[0]
+        p2g = np.zeros((n, 3), dtype=np.int32)
+        w = np.zeros((n, 3, t.order))
+        self.L.orc_pppm_map_ele(ip(self.mesh), t.order, dp(f64(s.boxlo)), dp(self.prd_slab), dp(self._rho), n,
+                                dp(xyz), ip(p2g), dp(w))
+        out = np.zeros(n)
+        self.L.orc_pppm_gather_b(ip(self.mesh), t.order, n, ip(p2g), dp(w), dp(u_tot), dp(out))
+        return -out
+
+    def potential_atom(self, eta, pair=True, kspace=True, qsum=True):
+        """ComputePotentialAtom::compute_peratom (compute_potential_atom.cpp:120-182) for the electrode
+        atoms after update_charge, in volts: compute_pair_potential (:223-318) by brute force over all
+        periodic images, the k-space part (:161-171) with the mesh potential of ALL charges, slabcorr
+        (:333-358)."""
+        lmp = self.lmp
+        s = lmp.system
+        N = self.N
+        x, q, typ = f64(s.x), f64(s.q), s.type
+        is_ele = np.zeros(s.natoms, dtype=bool)
+        is_ele[self.ele_idx] = True
+        phi = np.zeros(N)
+        g = self.g_ewald
+        EWALD_P, A = 0.3275911, (0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429)
+
+        def erfc_poly(a_r):   # the polynomial both the fix and the compute use (:296-299)
+            tt = 1.0 / (1.0 + EWALD_P * a_r)
+            return tt * (A[0] + tt * (A[1] + tt * (A[2] + tt * (A[3] + tt * A[4])))) * np.exp(-a_r * a_r)
+        if pair:
+            cut_coulsq = min(lmp.cut_coul ** 2, 5.8 ** 2 / (g * g))
+            smax = [int(np.ceil(np.sqrt(cut_coulsq) / s.prd[a])) if lmp.periodic[a] else 0 for a in range(3)]
+            shifts = [(i, j, k) for i in range(-smax[0], smax[0] + 1) for j in range(-smax[1], smax[1] + 1)
+                      for k in range(-smax[2], smax[2] + 1)]
+            for a, i in enumerate(self.ele_idx):
+                acc = 0.0
+                for sh in shifts:
+                    d = x[i] - (x + np.array(sh) * s.prd)
+                    rsq = np.maximum((d * d).sum(axis=1), 1e-10)
+                    m = (rsq < lmp.cutsq[typ[i], typ]) & (rsq < cut_coulsq) & ((q[i] != 0) | (q != 0))
+                    if sh == (0, 0, 0):
+                        m[i] = False
+                    r = np.sqrt(rsq[m])
+                    dudq = erfc_poly(g * r) / r
+                    if eta != 0.0:
+                        etar = np.where(is_ele[m], eta * r / np.sqrt(2.0), eta * r)
+                        dudq = dudq - np.where(etar < 5.8, erfc_poly(etar) / r, 0.0)
+                    acc += float((q[m] * dudq).sum())
+                phi[a] += acc
+        if kspace:
+            if self.pppm is None:
+                raise FixError("Compute requires a compatible KSpace provider like pppm/conp")
+            qe = q[self.ele_idx]
+            phi += self.mesh_potential(x[self.ele_idx]) - 2.0 * g * qe / MY_PIS
+            if eta != 0.0:
+                phi += eta * qe * np.sqrt(2.0) / MY_PIS
+            if lmp.slabflag:
+                pi2vol = 2.0 * np.pi / self.volume
+                slabcorr = 2.0 * pi2vol * float((q * x[:, 2]).sum())
+                z = x[self.ele_idx, 2]
+                phi += z * slabcorr
+                if qsum:
+                    phi -= pi2vol * float(q.sum()) * z * z
+        return phi * (lmp.qqr2e / lmp.qe2f)
 
 
 # -- matout / org / inv file formats (fix_conp.cpp:721-773, 833-849, 960-977) ---

@@ -21,6 +21,8 @@ class Fix : protected Pointers {
   }
   virtual int setmask() = 0;
   virtual void init() {}
+  virtual void setup(int) {}
+  virtual void post_integrate() {}
   virtual void init_list(int, NeighList *) {}
   virtual void setup_post_neighbor() {}
   virtual void setup_pre_force(int) {}

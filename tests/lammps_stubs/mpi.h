@@ -11,6 +11,7 @@ typedef int MPI_Info;
 #define MPI_BYTE 1
 #define MPI_SUM 1
 #define MPI_MAX 2
+#define MPI_MIN 3
 #define MPI_COMM_WORLD 0
 #define MPI_COMM_TYPE_SHARED 1
 #define MPI_INFO_NULL 0

@@ -303,3 +303,40 @@ def test_ewald_gemm_form(case, monkeypatch):
     fix.pre_force()
     q_close(fix.pre_force(), qr)
     fix.close()
+
+
+def test_compute_potential_atom_on_the_electrodes():
+    """`compute potential/atom` (compute_potential_atom.cpp:120-182, pppm_conp.cpp:452-488) for the electrode
+    atoms: GPU vs the oracle's restatement (brute-force image sum + full-mesh Poisson solve), and the
+    physics it exists for: after the solve every atom of an electrode sits at the same potential and the
+    two electrodes differ by the applied dV (to the accuracy of PPPM vs the Ewald-built A matrix)."""
+    lmp, arg = dilute(0, pppm=True)      # slab, conp dV = 1.0 V
+    lmp2, arg2 = dilute(0, pppm=True)
+    fix = make_fix(lmp, arg)
+    ref = O.OracleFixConp(lmp2, arg2)
+    fix.setup()
+    ref.setup()
+    q, qr = fix.pre_force(), ref.pre_force()
+    q_close(q, qr)
+    eta = fix.args.eta
+    for kw in (dict(), dict(pair=False), dict(kspace=False), dict(qsum=False)):
+        phi = fix.compute_potential_atom(eta, **kw)
+        phir = ref.potential_atom(eta, **kw)
+        assert np.abs(phi - phir).max() <= 1e-8 * np.abs(phir).max() + 1e-10, kw
+    x = lmp.system.x[fix.ele_idx]
+    u = fix.ctx.mesh_potential(x + 0.3)                       # arbitrary positions, not only electrode sites
+    assert np.abs(u - ref.mesh_potential(x + 0.3)).max() <= 1e-9 * np.abs(u).max()
+    phi = fix.compute_potential_atom(eta)
+    left, right = phi[fix.side == 1], phi[fix.side == -1]
+    assert np.ptp(left) < 2e-3 and np.ptp(right) < 2e-3       # equipotential electrodes (PPPM-level agreement)
+    assert abs((right.mean() - left.mean()) - 1.0) < 2e-3     # ... dV apart (group2 is the positive side)
+    fix.close()
+    # Ewald mode: the reference's compute refuses without a pppm/conp style
+    lmp, arg = dilute(0)
+    fix = make_fix(lmp, arg)
+    fix.setup()
+    fix.pre_force()
+    with pytest.raises(abi.ConpError) as e:
+        fix.compute_potential_atom(eta)
+    assert "compatible KSpace provider" in str(e.value)
+    fix.close()

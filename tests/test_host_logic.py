@@ -154,3 +154,28 @@ def test_gloo_world2_rank_plumbing():
         assert p.exitcode == 0
     assert all(r[1] == bytes(range(128)) for r in res)
     assert all(r[2] == 2.0 for r in res)
+
+
+def test_fix_zmirror_mirrors_group2_by_tag_offset():
+    """fix zmirror (fix_zmirror.cpp:124-220): group2 <- mirror image of group in z = (zlo+zhi)/2, by tag offset."""
+    import numpy as np
+    from conp_b200.fix_conp import make_fix, FixError
+    from conp_b200 import MockLammps, load_reference_case
+    s = load_reference_case("dilute").doubled_cell(sym=False, molleft=81, molright=82, molmax=82)
+    lmp = MockLammps(s, "p p p")
+    n = s.natoms // 2
+    lmp.groups["lower"] = np.arange(s.natoms) < n
+    lmp.groups["upper"] = np.arange(s.natoms) >= n
+    rng = np.random.default_rng(2)
+    s.x[:n] += rng.normal(0, 0.1, (n, 3))
+    fix = make_fix(lmp, "zm lower zmirror 1 upper".split())
+    fix.setup()
+    fix.post_integrate(0)
+    zoff = 2 * s.boxlo[2] + s.prd[2]
+    assert np.array_equal(s.x[n:, :2], s.x[:n, :2])
+    assert np.allclose(s.x[n:, 2], zoff - s.x[:n, 2], rtol=0, atol=0)
+    lmp.groups["short"] = np.arange(s.natoms) >= n + 1
+    bad = make_fix(lmp, "zm lower zmirror 1 short".split())
+    import pytest
+    with pytest.raises(FixError, match="same number of tags"):
+        bad.setup()

@@ -124,3 +124,20 @@ def test_il_onelayer_runs_and_is_neutral():
     assert fix.N == 832
     assert abs(q.sum()) < 1e-12
     assert q[fix.side == 1].sum() > 0
+
+
+def test_potential_atom_twin_gives_equipotential_electrodes():
+    """The oracle's restatement of `compute potential/atom` (compute_potential_atom.cpp:120-182) is pinned
+    by the physics it measures: after a conp solve the potential is constant on each electrode and the two
+    electrodes differ by the applied dV = 1.0 V (to the PPPM-vs-Ewald consistency level)."""
+    import numpy as np
+    import conp_oracle as O
+    from cases import dilute
+    lmp, arg = dilute(0, pppm=True)
+    ref = O.OracleFixConp(lmp, arg)
+    ref.setup()
+    ref.pre_force()
+    phi = ref.potential_atom(ref.args.eta)
+    left, right = phi[ref.side == 1], phi[ref.side == -1]
+    assert np.ptp(left) < 1e-4 and np.ptp(right) < 1e-4
+    assert abs((right.mean() - left.mean()) - 1.0) < 1e-4

@@ -13,13 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = os.path.join(ROOT, "lammps-user-conp2_b200", "shim")
 
 
-@pytest.mark.parametrize("unit", ["fix_conp.cpp", "pppm_conp.cpp"])
+@pytest.mark.parametrize("unit", ["fix_conp.cpp", "pppm_conp.cpp", "fix_zmirror.cpp"])
 def test_shim_unit_compiles_against_the_abi(unit):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
     cmd = [gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "lammps_stubs"),
-           "-I", os.path.join(ROOT, "include"), os.path.join(SHIM, unit)]
+           "-I", os.path.join(ROOT, "include"), "-I", SHIM, os.path.join(SHIM, unit)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
 
@@ -31,3 +31,4 @@ def test_shim_registers_the_reference_style_names():
     for name in ("conp", "conq", "cond"):
         assert f"FixStyle({name}," in fix_h
     assert "KSpaceStyle(pppm/conp," in open(os.path.join(SHIM, "pppm_conp.h")).read()
+    assert "FixStyle(zmirror," in open(os.path.join(SHIM, "fix_zmirror.h")).read()   # fix_zmirror.h:16
