@@ -198,7 +198,7 @@ def cpu_port_updates_per_s(fix, lmp, sets, budget_s):
     return n / el, n
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """Reference arm: CPU port of the reference's per-step path, all host cores."""
     if rank != 0:
         return
@@ -233,7 +233,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference algorithm (oracle/), not the reference binary: LAMMPS is not available",
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 def gather_matrix_to_rank0(ctx, info, N, rank, world):
@@ -263,7 +263,32 @@ def gather_matrix_to_rank0(ctx, info, N, rank, world):
     return S
 
 
+class QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torch.distributed) write to
+    file descriptor 1 on their own, so everything goes to stderr until the line is printed."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
+    with QuietStdout() as out:
+        run(out)
+
+
+def run(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -287,7 +312,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -530,7 +555,7 @@ def main():
                                         "sample": f"{n} full updates of the same workload with the GPU-built S"}
             del S
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     fix.close()
     bad = rank == 0 and "parity" in line and not line["parity"]["ok"]
     if world > 1:

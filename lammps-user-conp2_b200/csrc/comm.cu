@@ -243,11 +243,13 @@ p2p_reduce_bcast_kernel(char *const *__restrict__ arena, int rank, int nranks, s
 // completed those stores; optionally one double (*value) is first copied to byte offset value_off of
 // every rank's arena (the rank's sum(q z), which only exists once the whole producer grid is done).
 __global__ void __launch_bounds__(32)
-p2p_signal_kernel(PeerSync ps, size_t value_off, const double *__restrict__ value) {
+p2p_signal_kernel(PeerSync ps, size_t value_off, const double *__restrict__ value, size_t count_off,
+                  const int *__restrict__ counts) {
   const int r = threadIdx.x;
   if (r >= ps.nranks) return;
   ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(ps.arena[ps.rank]);
   if (value) *reinterpret_cast<double *>(ps.arena[r] + value_off) = __ldcg(value);
+  if (counts) reinterpret_cast<int *>(ps.arena[r] + count_off)[ps.rank] = __ldcg(counts + r);
   if (r == ps.rank) return;
   const unsigned long long e = mine->epoch[ps.chan] + 1ull;
   __threadfence_system();
@@ -437,8 +439,10 @@ PeerSync p2p_sync(PeerArena *a, int chan) {
   return ps;
 }
 
-int p2p_signal(PeerArena *a, int chan, cudaStream_t s, size_t value_off, const double *value) {
-  p2p_signal_kernel<<<1, 32, 0, s>>>(p2p_sync(a, chan), value ? arena_off(value_off) : 0, value);
+int p2p_signal(PeerArena *a, int chan, cudaStream_t s, size_t value_off, const double *value, size_t count_off,
+               const int *counts) {
+  p2p_signal_kernel<<<1, 32, 0, s>>>(p2p_sync(a, chan), value ? arena_off(value_off) : 0, value,
+                                     counts ? arena_off(count_off) : 0, counts);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

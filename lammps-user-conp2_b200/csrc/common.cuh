@@ -238,7 +238,8 @@ int p2p_error(PeerArena *);  // non-zero after a wait timed out
 PeerSync p2p_sync(PeerArena *, int chan);
 // flags of `chan` for a producer kernel that did not signal itself; value != nullptr: *value is first
 // stored at payload offset value_off of every rank's arena
-int p2p_signal(PeerArena *, int chan, cudaStream_t, size_t value_off = 0, const double *value = nullptr);
+int p2p_signal(PeerArena *, int chan, cudaStream_t, size_t value_off = 0, const double *value = nullptr,
+               size_t count_off = 0, const int *counts = nullptr /* counts[r] -> rank r, slot `rank` at count_off */);
 int p2p_wait_sync(const PeerSync &, cudaStream_t);  // stand-alone wait on a PeerSync
 
 // Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per device (one process may hold
@@ -325,7 +326,14 @@ int launch_cell_scatter(cudaStream_t s, const CellGrid &g, int m, const PosQ *pa
                         int *sorted_src, float4 *sorted_f);
 // charges sitting in a cell within reach of an electrode atom (near_count must be zeroed); post_force only
 int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const unsigned char *near_mask,
-                     int *near_list, int *near_count);
+                     int *near_list, int *near_count, const int *counts = nullptr, int mpad = 1);
+// several GPUs, routed exchange: own[j] = wrapped charge j of this rank; a copy goes into the inbox (arena
+// regions off_packed / off_ptype / off_psrc, sender block `rank`) of every rank whose rel_all row marks the
+// charge's cell; send_count[r] (zeroed by the caller) ends up as the number sent to rank r
+int launch_pack_route(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx, const double *q,
+                      const int *type, PosQ *own, int rank, int nranks, int mpad, const unsigned char *rel_all,
+                      const PeerSync &ps, size_t off_packed, size_t off_ptype, size_t off_psrc, int *send_count,
+                      double *qz_sum);
 // b_real[i] = -sum_j q_j dudq(r_ij), rows [row_begin,row_end), against the cell-sorted point charges
 int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int row_begin, int row_end,
                   const double *ex, const double *ey, const double *ez, const int *etype, const int *run_start,
@@ -345,7 +353,8 @@ int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &p
                           const EPos *esorted, const int *cell_start, const double *q_ele, const PosQ *packed,
                           const int *packed_type, const int *near_list, const int *near_count, int max_near,
                           const double *cutsq_listed, double *f_packed /* m x 3 */, double *energies /* 8 */,
-                          int num_sms);
+                          int num_sms, const int *psrc = nullptr /* routed exchange: sender-local index */,
+                          int mpad = 1);
 
 // pppm.cu ------------------------------------------------------------------
 // spreads the sorted charges of cells [cell_lo, cell_hi) (all of them if cell_start == nullptr) onto the
@@ -474,9 +483,10 @@ int launch_ewald_panel(cudaStream_t s, int n, const double2 *etab, int kxmax, in
 
 // gram.cu ------------------------------------------------------------------
 // C[i][j] += sum_k Pt[k][row_begin+i] * Pt[k][j] (k-major panel, ld doubles per k-row); FP64 tensor cores
-// lower_only: skip tiles strictly above the diagonal (single-GPU build; completed by launch_gram_mirror)
+// Only the tiles touching the cyclic half band (j - i) mod n in [0, n/2] of the rows [row0, row0 + nrows) are
+// computed (same work for every row block); launch_gram_mirror completes the assembled n x n matrix
 int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
-                           const double *panel_all, size_t ld, double *C, size_t pitch, int lower_only);
+                           const double *panel_all, size_t ld, double *C, size_t pitch, int row0);
 int launch_gram_mirror(cudaStream_t s, int n, double *C, size_t pitch);
 // Same DMMA tile kernel as a general product of k-major operands: C[z][i][j] (+)= sum_{k in slice z} A[k][i] B[k][j],
 // i < m, j < n.  A (lda) and B (ldb) are zero-padded to multiples of 128 columns and kdim to a multiple of 16;

@@ -33,6 +33,12 @@ struct conp_ctx {
   // in an IPC-mapped arena that every peer writes into; nullptr => NCCL collectives
   PeerArena *p2p = nullptr;
   size_t p2p_bytes = 0, off_b = 0, off_sb = 0, off_uhat = 0, off_stage = 0, off_packed = 0, off_parts = 0;
+  // routed position exchange (pack_route_kernel): inbox types / sender-local indices / per-sender counts
+  size_t off_ptype = 0, off_psrc = 0, off_rcnt = 0;
+  bool route_allowed = true, routed = false;
+  DevBuf<unsigned char> d_rel_all;  // [nranks][ncells] relevance masks of every rank
+  DevBuf<int> d_sendcnt, d_psrc;
+  DevBuf<PosQ> d_own;               // this rank's wrapped charges (all of them)
   std::string err;
   long long launches = 0;
 
@@ -85,6 +91,7 @@ struct conp_ctx {
   int one_electrode = 0;
   // electroneutrality polish of the epilogue (see charge_epilogue): on when the projection is
   bool neutral_polish = false, projected_here = false;
+  bool A_half_band = false;  // several GPUs: d_mat holds A's cyclic half band only until the blocks are assembled
   int n_left = 0;
   double sum_setz = 0;
   double build_ms = 0, invert_ms = 0;
@@ -244,20 +251,9 @@ void ensure_static_cells(conp_ctx *c) {
   c->d_nearmask.upload(mask, c->stream);
   c->d_nearcount.zero(1, c->stream);
   c->have_relevant = false;
-  if (c->nranks > 1 && c->have_pppm && !c->periodic[2] && getenv("CONP_SORT_ALL") == nullptr) {
-    std::vector<unsigned char> rel((size_t)c->grid_b.ncells, 0);
-    for (const PairRun &r : runs)
-      for (int cell = r.c0; cell < r.c1; ++cell) rel[cell] = 1;
-    int cz_lo = 0, cz_hi = 0;
-    slab_cell_layers(c, &cz_lo, &cz_hi);
-    const size_t layer = (size_t)c->grid_b.nc[1] * c->grid_b.nc[0];
-    if (c->pg.zs_n > 0) std::fill(rel.begin() + cz_lo * layer, rel.begin() + (cz_hi + 1) * layer, (unsigned char)1);
-    c->d_relevant.upload(rel, c->stream);
-    c->have_relevant = true;
-  }
+  std::vector<int> rs;
+  std::vector<int2> rr;
   if (c->have_pppm) {
-    std::vector<int> rs;
-    std::vector<int2> rr;
     c->splan.use_mma = c->spread_mode != 1;
     plan_pppm_spread_tiles(c->pg, c->grid_b, c->num_sms, rs, rr, c->splan);
     if (rr.empty()) rr.push_back(make_int2(0, 0));
@@ -271,6 +267,22 @@ void ensure_static_cells(conp_ctx *c) {
       fprintf(stderr, "[conp] rank %d spread tiles: %d x %d x %d tiles of %d x %d x %d (z,y,x), %zu cell runs, "
               "%zu B smem per warp, grid %d\n", c->rank, c->splan.ntz, c->splan.nty, c->splan.ntx, c->splan.tz,
               c->splan.ty, c->splan.tx, rr.size(), c->splan.smem, c->splan.grid);
+  }
+  // Several GPUs: the cells whose charges this rank reads at all -- within reach of its electrode rows (pair
+  // kernels), or in a candidate cell run of one of its spread tiles (its slab of PPPM planes).  Static.  The
+  // receiver-side filter of the all-gather path and the sender-side routing both use it.
+  if (c->nranks > 1 && getenv("CONP_SORT_ALL") == nullptr) {
+    std::vector<unsigned char> rel((size_t)c->grid_b.ncells, 0);
+    for (const PairRun &r : runs)
+      for (int cell = r.c0; cell < r.c1; ++cell) rel[cell] = 1;
+    if (c->have_pppm)
+      for (int k = 0; k < c->splan.ntiles && k + 1 < (int)rs.size(); ++k)
+        for (int r = rs[k]; r < rs[k + 1]; ++r)
+          for (int cell = rr[r].x; cell < rr[r].y; ++cell) rel[cell] = 1;
+    c->d_relevant.upload(rel, c->stream);
+    c->have_relevant = true;
+    c->d_rel_all.reserve((size_t)c->nranks * c->grid_b.ncells);
+    comm_allgather(c->comm, c->d_relevant.p, c->d_rel_all.p, (size_t)c->grid_b.ncells, c->stream);  // collective
   }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->static_cells = true;
@@ -318,6 +330,8 @@ void drop_p2p(conp_ctx *c) {
   if (!c->p2p) return;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->d_b.release(); c->d_sb.release(); c->d_uhat.release(); c->d_packed.release();
+  if (c->routed) { c->d_ptype.release(); c->d_psrc.release(); }
+  c->routed = false;
   p2p_destroy(c->p2p);
   c->p2p = nullptr;
   c->p2p_bytes = 0;
@@ -335,7 +349,8 @@ void ensure_p2p(conp_ctx *c) {
   const size_t st_bytes = up(sizeof(double) * std::max<size_t>(slice * c->nranks, 2));
   const size_t pk_bytes = up(sizeof(PosQ) * (size_t)std::max(c->m_slots, 1));
   const size_t pt_bytes = up(sizeof(double) * c->vlen * c->nranks);  // one partial S.b per rank
-  const size_t need = 2 * b_bytes + u_bytes + st_bytes + pk_bytes + pt_bytes;
+  const size_t ti_bytes = up(sizeof(int) * (size_t)std::max(c->m_slots, 1));  // inbox types / source indices
+  const size_t need = 2 * b_bytes + u_bytes + st_bytes + pk_bytes + pt_bytes + 2 * ti_bytes + 256;
   if (c->p2p && need == c->p2p_bytes) return;
   drop_p2p(c);
   // the views about to be attached may still own private memory from a single-context phase
@@ -348,11 +363,19 @@ void ensure_p2p(conp_ctx *c) {
   c->off_stage = c->off_uhat + u_bytes;
   c->off_packed = c->off_stage + st_bytes;
   c->off_parts = c->off_packed + pk_bytes;
+  c->off_ptype = c->off_parts + pt_bytes;
+  c->off_psrc = c->off_ptype + ti_bytes;
+  c->off_rcnt = c->off_psrc + ti_bytes;
   char *base = p2p_local(c->p2p);
   c->d_b.attach((double *)(base + c->off_b), c->vlen);
   c->d_sb.attach((double *)(base + c->off_sb), c->vlen);
   if (c->have_pppm) c->d_uhat.attach((cufftDoubleComplex *)(base + c->off_uhat), n_u / 2);
   c->d_packed.attach((PosQ *)(base + c->off_packed), (size_t)std::max(c->m_slots, 1));
+  c->routed = c->route_allowed;
+  if (c->routed) {
+    c->d_ptype.attach((int *)(base + c->off_ptype), (size_t)std::max(c->m_slots, 1));
+    c->d_psrc.attach((int *)(base + c->off_psrc), (size_t)std::max(c->m_slots, 1));
+  }
 }
 
 void stage_mark(conp_ctx *c, int i) {
@@ -406,8 +429,8 @@ bool use_ewald_gemm(const conp_ctx *c) {
 // operands and workspaces of the GEMM form (outside graph capture: allocates)
 void ensure_ewald_gemm(conp_ctx *c) {
   if (c->eg_valid) return;
-  // every rank sums its share of the charges (sfac_reduce, km_ewald.cpp:782-786)
-  ewald_gemm_plan(c->eg, c->ew, (c->m_total + c->nranks - 1) / c->nranks, c->r1 - c->r0, c->num_sms, c->stream);
+  // every rank sums its own charges (sfac_reduce, km_ewald.cpp:782-786)
+  ewald_gemm_plan(c->eg, c->ew, std::max(c->m_local, 1), c->r1 - c->r0, c->num_sms, c->stream);
   c->launches += ewald_gemm_electrodes(c->stream, c->eg, c->ew, c->r0, c->r1, c->d_etab.p);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->eg_valid = true;
@@ -456,10 +479,21 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   };
   const bool late_signal = fused && !c->signal_in_kernel;
   const PeerSync ps_pos = fused ? p2p_sync(c->p2p, 0) : PeerSync();
+  // routed position exchange: a charge goes only to the ranks whose relevance mask covers its cell
+  const bool routed = fused && c->routed && c->have_relevant;
   if (!multi) {
     c->launches += launch_pack_count(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, packed_local,
                                      ptype_local, c->d_cellof.p, c->d_slot.p, c->d_cellcount.p, c->scal(2),
                                      PeerSync(), 0, 0);
+  } else if (routed) {
+    CUDA_CHECK(cudaMemsetAsync(c->d_sendcnt.p, 0, sizeof(int) * c->nranks, s));
+    c->launches += launch_pack_route(s, g, c->m_local, x_dev, c->d_idx.p, c->d_qraw.p, c->d_typeraw.p, c->d_own.p,
+                                     c->rank, c->nranks, c->mpad, c->d_rel_all.p, p2p_sync(c->p2p, 0),
+                                     c->off_packed, c->off_ptype, c->off_psrc, c->d_sendcnt.p, c->scal(2));
+    // per-receiver counts, this rank's sum(q z) (padding slot of its inbox block on every rank), flags
+    c->launches += p2p_signal(c->p2p, 0, s,
+                              c->off_packed + sizeof(PosQ) * (size_t)(c->m_offsets[c->rank] + c->mpad - 1),
+                              c->scal(2), c->off_rcnt, c->d_sendcnt.p);
   } else {
     // every rank's positions go to every rank; the sum(q z) partial rides in the block's last (padding)
     // slot.  Types and charges are static between reneighbourings and were gathered in conp_post_neighbor.
@@ -480,9 +514,11 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
       comm_allgather(c->comm, packed_local, c->d_packed.p, sizeof(PosQ) * (size_t)c->mpad, s);
     }
     // PPPM mode: only the charges this rank can use (near its rows, or in its slab) are sorted
-    const unsigned char *relevant =
-        (kspace_mode == CONP_KSPACE_PPPM && c->have_relevant) ? c->d_relevant.p : nullptr;
-    c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, c->d_mcounts.p, c->d_packed.p, c->d_cellof.p,
+    // all-gather path: only the charges this rank can use are sorted (Ewald mode on that path sums the
+    // structure factors of the rank's own block, which is not sorted either)
+    const unsigned char *relevant = (!routed && c->have_relevant) ? c->d_relevant.p : nullptr;
+    const int *counts = routed ? (const int *)(p2p_local(c->p2p) + c->off_rcnt) : c->d_mcounts.p;
+    c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, counts, c->d_packed.p, c->d_cellof.p,
                                         c->d_slot.p, c->d_cellcount.p, relevant, ps_pos);
   }
   c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p, c->d_packed.p, c->mpad,
@@ -521,9 +557,12 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                               multi ? c->m_slots : c->m_total,
                                               multi ? c->d_cellstart.p + g.ncells : nullptr, c->d_brick.p,
                                               c->d_flag.p);
-    } else if (!multi || c->periodic[2]) {
+    } else if (!multi) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
                                         c->d_flag.p);
+    } else if (c->periodic[2]) {  // the slab's stencils wrap: every sorted (= relevant) charge is a candidate
+      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_cellstart.p, 0, g.ncells,
+                                        c->d_brick.p, c->d_flag.p);
     } else {
       int cz_lo = 0, cz_hi = 0;
       slab_cell_layers(c, &cz_lo, &cz_hi);
@@ -564,18 +603,18 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   } else {
     const EwaldHost &e = c->ew;
     const bool gemm = use_ewald_gemm(c);
-    // sincos_b + sfac_reduce (km_ewald.cpp:668-786): every rank holds all charges (sorted), sums the structure
-    // factors of its contiguous share of them and the partial S(k) are added across ranks
-    const int ja = (int)(((long long)c->m_total * c->rank) / c->nranks);
-    const int jb = (int)(((long long)c->m_total * (c->rank + 1)) / c->nranks);
-    const size_t T = (size_t)e.kxmax + e.kymax + e.kzmax + 3;
-    c->launches += launch_axis_tables(s, jb - ja, nullptr, nullptr, nullptr, c->d_sorted.p + ja, e.unitk, e.kxmax,
-                                      e.kymax, e.kzmax, c->d_jtab.p + (size_t)ja * T);
+    // sincos_b + sfac_reduce (km_ewald.cpp:668-786): every rank sums the structure factors of its share of the
+    // charges and the partial S(k) are added across ranks
+    // = its own charges (the block it packed itself; the sort order does not matter for a sum)
+    const PosQ *own = routed ? c->d_own.p : packed_local;
+    const int mo = c->m_local;
+    c->launches += launch_axis_tables(s, mo, nullptr, nullptr, nullptr, own, e.unitk, e.kxmax, e.kymax, e.kzmax,
+                                      c->d_jtab.p);
     if (gemm)
-      c->launches += ewald_gemm_sfac(s, c->eg, e, ja, jb, c->d_sorted.p, c->d_jtab.p, c->d_kz.p, c->d_sfac.p);
+      c->launches += ewald_gemm_sfac(s, c->eg, e, 0, mo, own, c->d_jtab.p, c->d_kz.p, c->d_sfac.p);
     else
-      c->launches += launch_ewald_sfac(s, jb - ja, c->d_sorted.p + ja, c->d_jtab.p + (size_t)ja * T, e.kxmax, e.kymax,
-                                       e.kzmax, e.kcount, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_sfac.p);
+      c->launches += launch_ewald_sfac(s, mo, own, c->d_jtab.p, e.kxmax, e.kymax, e.kzmax, e.kcount, c->d_kx.p,
+                                       c->d_ky.p, c->d_kz.p, c->d_sfac.p);
     if (multi) comm_allreduce_sum_f64(c->comm, c->d_sfac.p, 2 * (size_t)std::max(e.kcount, 1), s);
     stage_mark(c, 4);
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_pair, 0));  // join
@@ -855,6 +894,7 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     if (getenv("CONP_EWALD_GEMM")) c->eg_mode = atoi(getenv("CONP_EWALD_GEMM")) != 0 ? 1 : 0;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
+    c->route_allowed = getenv("CONP_ROUTE") == nullptr || atoi(getenv("CONP_ROUTE")) != 0;
     if (const char *e = getenv("CONP_SPREAD"))
       c->spread_mode = !strcmp(e, "atomic") ? 0 : !strcmp(e, "smem") ? 1 : !strcmp(e, "mma") ? 2 : -1;
     if (getenv("CONP_SPREAD_ATOMIC") != nullptr && atoi(getenv("CONP_SPREAD_ATOMIC")) != 0) c->spread_mode = 0;
@@ -1285,10 +1325,13 @@ int conp_build_A(conp_ctx *c) {
       c->launches += launch_ewald_panel(s, N, c->d_etab.p, e.kxmax, e.kymax, e.kzmax, k0, kc, (int)segs.size(),
                                         dsegs.p, c->d_kx.p, c->d_ky.p, c->d_kz.p, c->d_ug.p, panel.p, ld);
       c->launches += launch_gram_accumulate(s, nr, N, 2 * kc, panel.p + c->r0, panel.p, ld, c->d_mat.p, c->pitch,
-                                            c->nranks == 1);
+                                            c->r0);
       CUDA_CHECK(cudaStreamSynchronize(s));  // segs / dsegs reuse
     }
-    if (c->nranks == 1) c->launches += launch_gram_mirror(s, N, c->d_mat.p, c->pitch);  // the Gram is symmetric
+    // the Gram is symmetric and only its cyclic half band was computed: one GPU completes it now, several
+    // GPUs when the row blocks are assembled for the inversion (conp_invert_project)
+    if (c->nranks == 1) c->launches += launch_gram_mirror(s, N, c->d_mat.p, c->pitch);
+    c->A_half_band = c->nranks > 1;
     // ---- diagonal, self and slab terms -----------------------------------------
     const double diag_k = e.ug_tot - 2.0 / MY_PIS * c->g_ewald;  // km_ewald.cpp:632
     const double self_eta = std::sqrt(2.0) / MY_PIS * c->eta;    // fix_conp.cpp:796-800
@@ -1334,6 +1377,7 @@ int conp_load_matrix(conp_ctx *c, const double *full, int is_inverse) {
     c->sym = false;
     c->asym_rel = -1.0;
     c->projected_here = false;
+    c->A_half_band = false;
     c->d_fullS.release();
     if (is_inverse) {
       // a ready-made inverse: look at the whole matrix once to see whether the symmetric product applies.
@@ -1364,6 +1408,8 @@ int conp_load_matrix(conp_ctx *c, const double *full, int is_inverse) {
 int conp_get_matrix(conp_ctx *c, double *rows_out) {
   return guard(c, [&] {
     need(c->have_A, "conp_get_matrix: no matrix yet");
+    need(!c->A_half_band, "conp_get_matrix: on several GPUs the rows of A are complete only after "
+                          "conp_invert_project (matout: run on one rank)");
     const int N = c->N, nr = c->r1 - c->r0;
     if (nr > 0)
       CUDA_CHECK(cudaMemcpy2DAsync(rows_out, (size_t)N * sizeof(double), c->d_mat.p, c->pitch * sizeof(double),
@@ -1395,6 +1441,10 @@ int conp_invert_project(conp_ctx *c, int nullneutral, int zneutr, int one_electr
           offs[r] = (size_t)a * N * sizeof(double);
         }
         comm_allgatherv(c->comm, F.p + (size_t)c->r0 * N, F.p, bytes.data(), offs.data(), c->rank, c->nranks, s);
+        if (c->A_half_band) {  // rows built here hold the half band only (conp_build_A): mirror the rest
+          c->launches += launch_gram_mirror(s, N, F.p, N);
+          c->A_half_band = false;
+        }
       }
       // LU + solve against the identity (LAPACK dgetrf_/dgetri_ in the reference, fix_conp.cpp:947-949)
       cusolverDnParams_t params;
@@ -1571,7 +1621,9 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     c->d_stype.reserve(m); c->d_ssrc.reserve(m);
     c->d_cellof.reserve(m); c->d_slot.reserve(m);
     c->d_nearlist.reserve(m);
-    if (c->nranks > 1) {  // static per-charge data: types of every rank's block, once per reneighbouring
+    c->d_sendcnt.zero(std::max(c->nranks, 1), s);
+    c->d_own.reserve((size_t)std::max(c->m_local, 1));
+    if (c->nranks > 1 && !(c->p2p && c->routed)) {  // static per-charge data: types of every rank's block
       std::vector<int> ht(c->mpad, 0);
       for (int j = 0; j < c->m_local; ++j) ht[j] = type[c->h_idx[j]];
       int *own = c->d_ptype.p + c->m_offsets[c->rank];
@@ -1857,12 +1909,15 @@ int conp_post_force(conp_ctx *c, double qqrd2e, double *f_out, double *energies_
       g.rc = c->rc_f;
       for (int a = 0; a < 3; ++a) g.smax[a] = g.periodic[a] ? (int)std::ceil(g.rc / g.prd[a]) + 1 : 0;
       CUDA_CHECK(cudaMemsetAsync(c->d_nearcount.p, 0, sizeof(int), s));
+      const bool routed = c->p2p && c->routed && c->have_relevant;
+      const int *counts = routed ? (const int *)(p2p_local(c->p2p) + c->off_rcnt) : nullptr;
       c->launches += launch_near_list(s, c->grid_b, c->m_slots, c->d_packed.p, c->d_nearmask.p, c->d_nearlist.p,
-                                      c->d_nearcount.p);
+                                      c->d_nearcount.p, counts, c->mpad);
       c->launches += launch_pair_postforce(s, g, pair_tables(c, c->d_cuteff_b.p), qqrd2e, c->d_esorted.p,
                                            c->d_ecellstart.p, c->d_q.p, c->d_packed.p, c->d_ptype.p,
                                            c->d_nearlist.p, c->d_nearcount.p, c->m_slots, c->d_cutsq_listed.p,
-                                           c->d_fpacked.p, c->scal(4), c->num_sms);
+                                           c->d_fpacked.p, c->scal(4), c->num_sms,
+                                           routed ? c->d_psrc.p : nullptr, c->mpad);
     }
     if (c->nranks > 1) {
       comm_allreduce_sum_f64(c->comm, c->scal(4), 8, s);

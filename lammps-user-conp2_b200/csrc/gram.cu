@@ -51,9 +51,20 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 // (partial sums, added up by the consumer in a fixed order).  accumulate == 0 overwrites C.
 __global__ void __launch_bounds__(THREADS, 1)
 gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, const double *__restrict__ panel_a,
-            size_t lda, size_t ldb, double *__restrict__ Cmat, size_t pitch, size_t slice_stride, int lower_only,
-            int accumulate) {
-  if (lower_only && blockIdx.x > blockIdx.y) return;  // tile strictly above the diagonal: mirrored later
+            size_t lda, size_t ldb, double *__restrict__ Cmat, size_t pitch, size_t slice_stride, int band_n,
+            int band_row0, int accumulate) {
+  // Symmetric product (the Gram): only the tiles that touch the cyclic half band (j - i) mod N in [0, N/2] of
+  // their rows are computed -- the same number for every row, so row blocks of any rank are balanced; the
+  // other half is the mirror image (launch_gram_band_mirror, after the row blocks have been assembled).
+  if (band_n > 0) {
+    const int gi0 = band_row0 + blockIdx.y * BM, gj0 = blockIdx.x * BN;
+    const int dlo = gj0 - (gi0 + BM - 1), span = BM + BN - 2, H = band_n / 2;
+    if (span + 1 < band_n) {
+      int t = dlo % band_n;
+      t += t < 0 ? band_n : 0;
+      if (!(t <= H || t + span >= band_n)) return;
+    }
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GramSmem &sm = *reinterpret_cast<GramSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,21 +143,27 @@ gram_kernel(int nrows, int n, int kdim, const double *__restrict__ panel_r, cons
   }
 }
 
-// C[i][j] = C[j][i] for j > i (square matrix held whole on this GPU)
+// C[i][j] = C[j][i] for the elements outside the cyclic half band, (j - i) mod n > n/2 (square matrix held
+// whole on this GPU; their mirror images lie inside the band and were computed).  32 x 32 tiles through
+// shared memory so that both reads and writes are unit stride.
 __global__ void __launch_bounds__(256)
 mirror_kernel(int n, double *__restrict__ C, size_t pitch) {
   __shared__ double tile[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
-  if (bj < bi) return;  // handle (bi, bj) with bj >= bi: write the upper tile from the lower one
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int H = n / 2;
   for (int r = ty; r < 32; r += 8) {
-    const int i = bj * 32 + r, j = bi * 32 + tx;  // read lower tile element (i, j), i >= j region
+    const int i = bj * 32 + r, j = bi * 32 + tx;  // transposed tile (bj, bi)
     tile[r][tx] = (i < n && j < n) ? C[(size_t)i * pitch + j] : 0.0;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
-    const int i = bi * 32 + r, j = bj * 32 + tx;  // upper element (i, j) = lower (j, i)
-    if (i < n && j < n && j > i) C[(size_t)i * pitch + j] = tile[tx][r];
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < n && j < n) {
+      int d = j - i;
+      d += d < 0 ? n : 0;
+      if (d > H) C[(size_t)i * pitch + j] = tile[tx][r];
+    }
   }
 }
 
@@ -160,13 +177,13 @@ int launch_gram_mirror(cudaStream_t s, int n, double *C, size_t pitch) {
 }
 
 int launch_gram_accumulate(cudaStream_t s, int nrows, int n, int kdim, const double *panel_rows,
-                           const double *panel_all, size_t ld, double *C, size_t pitch, int lower_only) {
+                           const double *panel_all, size_t ld, double *C, size_t pitch, int row0) {
   if (nrows <= 0 || n <= 0 || kdim <= 0) return 0;
   if (kdim % BK) CONP_THROW(CONP_ERR_ARG, "gram: kdim must be a multiple of %d", BK);
   ensure_dynamic_smem(gram_kernel, sizeof(GramSmem));
   dim3 grid((n + BN - 1) / BN, (nrows + BM - 1) / BM);
-  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, ld, C, pitch, 0,
-                                                      lower_only, 1);
+  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(nrows, n, kdim, panel_rows, panel_all, ld, ld, C, pitch, 0, n,
+                                                      row0, 1);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -178,7 +195,7 @@ int launch_tn_gemm(cudaStream_t s, int m, int n, int kdim, const double *A, size
   if (pitch % 2) CONP_THROW(CONP_ERR_ARG, "tn_gemm: pitch must be even");
   ensure_dynamic_smem(gram_kernel, sizeof(GramSmem));
   dim3 grid((n + BN - 1) / BN, (m + BM - 1) / BM, std::max(ksplit, 1));
-  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(m, n, kdim, A, B, lda, ldb, C, pitch, slice_stride, 0,
+  gram_kernel<<<grid, THREADS, sizeof(GramSmem), s>>>(m, n, kdim, A, B, lda, ldb, C, pitch, slice_stride, 0, 0,
                                                       accumulate);
   CUDA_CHECK(cudaGetLastError());
   return 1;

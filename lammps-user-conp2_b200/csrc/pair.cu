@@ -157,6 +157,65 @@ pack_count_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int
   });
 }
 
+// Several GPUs, routed exchange: a charge only travels to the ranks that can use it.  rel_all[r][cell] says
+// whether rank r reads charges of that cell (cells within reach of its electrode rows, or feeding its slab
+// of PPPM planes -- static, exchanged once).  Every rank r has, in its arena, one inbox of mpad slots per
+// sender: the sender appends the charges r needs (position + charge, type, index in the sender's own list)
+// with warp-aggregated slot counters, and the p2p_signal kernel behind this one delivers the per-receiver
+// counts, the rank's sum(q z) and the flags.  `own` keeps all of this rank's wrapped charges (Ewald
+// structure factors are summed by the owner, km_ewald.cpp:668-786).
+__global__ void __launch_bounds__(256)
+pack_route_kernel(CellGrid g, int m, const double *__restrict__ x_raw, const int *__restrict__ idx,
+                  const double *__restrict__ q, const int *__restrict__ type, PosQ *__restrict__ own, int rank,
+                  int nranks, int mpad, const unsigned char *__restrict__ rel_all, char *const *__restrict__ arena,
+                  size_t off_packed, size_t off_ptype, size_t off_psrc, int *__restrict__ send_count,
+                  double *__restrict__ qz_sum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  double qz = 0.0;
+  PosQ p = {0.0, 0.0, 0.0, 0.0};
+  int cell = 0, ty = 0;
+  if (j < m) {
+    const int src = idx ? idx[j] : j;
+    const double xr = x_raw[3 * (size_t)src], yr = x_raw[3 * (size_t)src + 1], zr = x_raw[3 * (size_t)src + 2];
+    p.x = wrap_coord(g, 0, xr);
+    p.y = wrap_coord(g, 1, yr);
+    p.z = wrap_coord(g, 2, zr);
+    p.q = q[src];
+    ty = type[src];
+    own[j] = p;
+    qz = p.q * zr;  // raw z: km_ewald.cpp:839, fix_cond.cpp:103
+    cell = (cell_coord(g, 2, p.z) * g.nc[1] + cell_coord(g, 1, p.y)) * g.nc[0] + cell_coord(g, 0, p.x);
+  }
+  for (int r = 0; r < nranks; ++r) {
+    const bool need = j < m && rel_all[(size_t)r * g.ncells + cell] != 0;
+    const unsigned mk = __ballot_sync(0xffffffffu, need);
+    if (mk == 0u) continue;
+    int base = 0;
+    if (lane == __ffs(mk) - 1) base = atomicAdd(send_count + r, __popc(mk));
+    base = __shfl_sync(0xffffffffu, base, __ffs(mk) - 1);
+    if (need) {
+      const size_t slot = (size_t)rank * mpad + base + __popc(mk & lt);
+      char *a = arena[r] + P2P_CTRL_BYTES;
+      reinterpret_cast<PosQ *>(a + off_packed)[slot] = p;
+      reinterpret_cast<int *>(a + off_ptype)[slot] = ty;
+      reinterpret_cast<int *>(a + off_psrc)[slot] = j;
+    }
+  }
+  __shared__ double sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qz += __shfl_xor_sync(0xffffffffu, qz, o);
+  if (lane == 0) sh[threadIdx.x >> 5] = qz;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double v = sh[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0 && v != 0.0) atomicAdd(qz_sum, v);
+  }
+}
+
 // multi-GPU: the gathered charges sit in `nranks` blocks of `mpad` slots; block r holds
 // counts[r] charges, the rest is padding (the last slot carries that rank's sum(q z)).  With the fused
 // exchange (ps.arena != nullptr) the kernel first waits for every rank's block to have landed.
@@ -294,10 +353,10 @@ cell_scatter_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, const in
 // near list over the gathered charges: warp-aggregated append
 __global__ void __launch_bounds__(256)
 near_list_kernel(CellGrid g, int m, const PosQ *__restrict__ packed, const unsigned char *__restrict__ near_mask,
-                 int *__restrict__ near_list, int *__restrict__ near_count) {
+                 int *__restrict__ near_list, int *__restrict__ near_count, const int *__restrict__ counts, int mpad) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   bool near = false;
-  if (j < m) {
+  if (j < m && (!counts || j % mpad < counts[j / mpad])) {  // routed exchange: only the filled inbox slots
     const PosQ p = packed[j];
     const int cell = (cell_coord(g, 2, p.z) * g.nc[1] + cell_coord(g, 1, p.y)) * g.nc[0] + cell_coord(g, 0, p.x);
     near = near_mask[cell] != 0 && p.q != 0.0;
@@ -482,7 +541,7 @@ pair_postforce_kernel(CellGrid g, PairTables pt, double qqrd2e, const EPos *__re
                       const PosQ *__restrict__ packed, const int *__restrict__ packed_type,
                       const int *__restrict__ near_list, const int *__restrict__ near_count,
                       const double *__restrict__ cutsq_listed, double *__restrict__ f_packed,
-                      double *__restrict__ energies) {
+                      double *__restrict__ energies, const int *__restrict__ psrc, int mpad) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps_total = gridDim.x * PAIR_WARPS;
   const int nwork = __ldg(near_count);
@@ -530,9 +589,11 @@ pair_postforce_kernel(CellGrid g, PairTables pt, double qqrd2e, const EPos *__re
       fz += __shfl_xor_sync(0xffffffffu, fz, o);
     }
     if (lane == 0 && (fx != 0.0 || fy != 0.0 || fz != 0.0)) {
-      atomicAdd(f_packed + 3 * (size_t)j, fx);  // multi-GPU: each rank adds its own rows' share
-      atomicAdd(f_packed + 3 * (size_t)j + 1, fy);
-      atomicAdd(f_packed + 3 * (size_t)j + 2, fz);
+      // routed exchange: inbox slot j of sender block j / mpad is that sender's charge psrc[j]
+      const size_t fj = psrc ? (size_t)(j / mpad) * mpad + psrc[j] : (size_t)j;
+      atomicAdd(f_packed + 3 * fj, fx);  // multi-GPU: each rank adds its own rows' share
+      atomicAdd(f_packed + 3 * fj + 1, fy);
+      atomicAdd(f_packed + 3 * fj + 2, fz);
     }
   }
   double vals[7] = {ecoul, v0, v1, v2, v3, v4, v5};
@@ -755,10 +816,21 @@ int launch_cell_scatter(cudaStream_t s, const CellGrid &g, int m, const PosQ *pa
   return 1;
 }
 
+int launch_pack_route(cudaStream_t s, const CellGrid &g, int m, const double *x_raw, const int *idx, const double *q,
+                      const int *type, PosQ *own, int rank, int nranks, int mpad, const unsigned char *rel_all,
+                      const PeerSync &ps, size_t off_packed, size_t off_ptype, size_t off_psrc, int *send_count,
+                      double *qz_sum) {
+  pack_route_kernel<<<std::max((m + 255) / 256, 1), 256, 0, s>>>(g, m, x_raw, idx, q, type, own, rank, nranks, mpad,
+                                                                 rel_all, ps.arena, off_packed, off_ptype, off_psrc,
+                                                                 send_count, qz_sum);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 int launch_near_list(cudaStream_t s, const CellGrid &g, int m, const PosQ *packed, const unsigned char *near_mask,
-                     int *near_list, int *near_count) {
+                     int *near_list, int *near_count, const int *counts, int mpad) {
   if (m <= 0) return 0;
-  near_list_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, packed, near_mask, near_list, near_count);
+  near_list_kernel<<<(m + 255) / 256, 256, 0, s>>>(g, m, packed, near_mask, near_list, near_count, counts, mpad);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -811,12 +883,13 @@ int launch_pair_P(cudaStream_t s, const CellGrid &g, const PairTables &pt, const
 int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &pt, double qqrd2e,
                           const EPos *esorted, const int *cell_start, const double *q_ele, const PosQ *packed,
                           const int *packed_type, const int *near_list, const int *near_count, int max_near,
-                          const double *cutsq_listed, double *f_packed, double *energies, int num_sms) {
+                          const double *cutsq_listed, double *f_packed, double *energies, int num_sms,
+                          const int *psrc, int mpad) {
   if (max_near <= 0) return 0;
   int grid = std::min((max_near + PAIR_WARPS - 1) / PAIR_WARPS, num_sms * 8);
   pair_postforce_kernel<<<grid, PAIR_WARPS * 32, 0, s>>>(g, pt, qqrd2e, esorted, cell_start, q_ele, packed,
                                                          packed_type, near_list, near_count, cutsq_listed,
-                                                         f_packed, energies);
+                                                         f_packed, energies, psrc, mpad);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
