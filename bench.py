@@ -76,7 +76,7 @@ def config_dict(name, kspace, lmp, n_ele, kcount_a):
 
 # measured DRAM bytes per launch (ncu --set full, profiles/): (workload, kernel) -> read + written
 TRAFFIC = {("cfg5", "gemv"): 12.801121e9 + 6.872832e6, ("cfg4", "gemv"): 800.11392e6 + 3.297536e6,
-           ("cfg5", "symv"): 6.615392e9 + 13.343488e6, ("cfg4", "symv"): 406.715392e6 + 5.890816e6}
+           ("cfg5", "symv"): 6.615391e9 + 11.123200e6, ("cfg4", "symv"): 406.715392e6 + 5.890816e6}
 
 DEFAULT_WORKLOAD = "cfg5"  # BASELINE configs[4]: the configuration the 1/2/4/8-GPU metric is quoted on; fits one GPU
 

@@ -260,6 +260,10 @@ int conp_matvec(conp_ctx *ctx, const double *v, double *out);
 int conp_plan_symv(int n, int row0, int nrows, int num_sms, int max_strips, int *strips_out, int *nstrips_out,
                    int *slice_len_out);
 int conp_bench_dgemm_tflops(conp_ctx *ctx, int n, double *tflops_out);
+/* Host-only: the row partition of A and S (what fix_conp.cpp:816-823 does with elenum_list/displs): rank's
+ * rows [*row_begin, *row_end) of n_ele; every rank but the last ones owns *rows_per_rank rows (a multiple
+ * of 16).  conp_set_electrodes uses exactly this rule. */
+int conp_row_block(int n_ele, int nranks, int rank, int *row_begin, int *row_end, int *rows_per_rank);
 /* Host-only (no GPU needed): the tile decomposition of the owner-computes PPPM spread (replaces the scatter
  * loop of elyte_make_rho, pppm_conp.cpp:172-228) for a mesh / cell grid: geom_out[12] = {tz, ty, tx, ntz, nty,
  * ntx, halo_z, halo_y, halo_x, ncx, ncy, ncz}; run_start_out[ntiles + 1] and runs_out[2 * nruns] list, per

@@ -29,7 +29,7 @@ SYMBOLS = [
     "conp_get_density_region", "conp_mesh_potential", "conp_electrode_potential",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
-    "conp_matvec", "conp_plan_symv", "conp_plan_spread",
+    "conp_matvec", "conp_plan_symv", "conp_plan_spread", "conp_row_block",
 ]
 
 
@@ -81,6 +81,16 @@ def plan_spread(mesh, order, shift, boxlo, prd, periodic, slab_volfactor, rc, zi
     out = {k: int(v) for k, v in zip(keys, geom)}
     out.update(ntiles=nt.value, run_start=rs, runs=rr[:nr.value])
     return out
+
+
+def row_block(n_ele, nranks, rank):
+    """(row_begin, row_end, rows_per_rank) of the library's row partition (host-only entry point)."""
+    L = load_library()
+    a, b, r = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = L.conp_row_block(int(n_ele), int(nranks), int(rank), C.byref(a), C.byref(b), C.byref(r))
+    if rc:
+        raise RuntimeError(f"conp_row_block: status {rc}")
+    return a.value, b.value, r.value
 
 
 class ConpError(RuntimeError):
@@ -150,6 +160,7 @@ def load_library(path: str | None = None):
     L.conp_plan_spread.argtypes = [c_ip, C.c_int, C.c_double, c_dp, c_dp, c_ip, C.c_double, C.c_double, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_ip, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.conp_row_block.argtypes = [C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip]
     if path is None:
         _lib = L
     return L

@@ -377,7 +377,8 @@ struct SpreadPlan {
   // tensor-core kernel (spread_mma_kernel): in = allowed, out = chosen; per-charge stencil origins / weights
   int use_mma = 0;
   int4 *origin = nullptr;
-  double *weights = nullptr;
+  double *weights = nullptr;   // [3 order][wstride]
+  size_t wstride = 0;
 };
 void plan_pppm_spread_tiles(const PPPMGeom &g, const CellGrid &cells, int num_sms, std::vector<int> &run_start,
                             std::vector<int2> &runs, SpreadPlan &plan);

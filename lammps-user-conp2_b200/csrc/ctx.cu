@@ -1071,9 +1071,9 @@ int conp_set_electrodes(conp_ctx *c, int n_ele, const int *tag, const int *type,
         CONP_THROW(CONP_ERR_ARG, "conp_set_electrodes: atom type out of range");
     }
     // equal contiguous row blocks, multiple of 16 rows so every block start is 128-byte aligned
-    c->rpr = (int)round_up((size_t)(N + c->nranks - 1) / c->nranks, 16);
-    c->r0 = std::min(N, c->rank * c->rpr);
-    c->r1 = std::min(N, c->r0 + c->rpr);
+    int rpr_all = 0;
+    conp_row_block(N, c->nranks, c->rank, &c->r0, &c->r1, &rpr_all);
+    c->rpr = rpr_all;
     c->ncols_pad = (int)round_up(N, 16);
     c->pitch = c->ncols_pad;
     c->vlen = std::max((size_t)c->nranks * c->rpr, (size_t)c->ncols_pad) + 16;
@@ -1643,6 +1643,7 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
       c->d_sp_weights.reserve(mm * 3 * c->pg.order);
       c->splan.origin = c->d_sp_origin.p;
       c->splan.weights = c->d_sp_weights.p;
+      c->splan.wstride = mm;
     }
     c->d_cellcount.zero((size_t)c->grid_b.ncells + 8, s);
     c->d_cellstart.zero((size_t)c->grid_b.ncells + 8, s);
@@ -1819,6 +1820,9 @@ int conp_electrode_potential(conp_ctx *c, int pairflag, int kspaceflag, double e
       pt.pairmode = CONP_PAIR_ETA;  // the compute knows one Gaussian width only
       pt.eta = eta;
       const double rc = std::sqrt(mx);
+      if (c->nranks > 1 && rc > c->rc_b * (1.0 + 1e-12))
+        CONP_THROW(CONP_ERR_STATE, "conp_electrode_potential: on several GPUs the pair cut-off of the compute (%g) "
+                   "must not exceed the fix's (%g): charges beyond it are not exchanged", rc, c->rc_b);
       if (rc > 0.0 && nr > 0) {
         // electrolyte -> electrode: the step's cell-sorted charges, traversal lists rebuilt for this radius
         if (c->m_total > 0) {
@@ -2044,6 +2048,17 @@ int conp_plan_symv(int n, int row0, int nrows, int num_sms, int max_strips, int 
       strips_out[2 * s] = strips[s].x;
       strips_out[2 * s + 1] = strips[s].y;
     }
+  return CONP_OK;
+}
+
+int conp_row_block(int n_ele, int nranks, int rank, int *row_begin, int *row_end, int *rows_per_rank) {
+  if (n_ele < 0 || nranks < 1 || rank < 0 || rank >= nranks) return CONP_ERR_ARG;
+  // equal contiguous row blocks, multiple of 16 rows so every block start is 128-byte aligned
+  const int rpr = (int)round_up((size_t)(n_ele + nranks - 1) / nranks, 16);
+  const int r0 = std::min(n_ele, rank * rpr);
+  if (row_begin) *row_begin = r0;
+  if (row_end) *row_end = std::min(n_ele, r0 + rpr);
+  if (rows_per_rank) *rows_per_rank = rpr;
   return CONP_OK;
 }
 

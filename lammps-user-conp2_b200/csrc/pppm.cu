@@ -392,13 +392,14 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// origin[j] = (nx, ny, zi0, ok): mesh index of the stencil's first point along x and y (unwrapped), compact
-// input plane of its first plane, ok = 0 for q == 0 or an out-of-range charge; weights[j][3 P]
+// origin[j] = (nx, ny, zi0, ok): mesh index of the stencil's first point along x and y (wrapped), compact
+// input plane of its first plane, ok = 0 for q == 0 or an out-of-range charge; weights[3 P][wstride] (weight
+// k of charge j at k * wstride + j: coalesced stores here, one 8-byte gather per weight in the tile kernel)
 template <int P>
 __global__ void __launch_bounds__(256)
 stencil_prepass_kernel(PPPMGeom g, RhoCoeff rc, int m_bound, const int *__restrict__ count_ptr,
                        const PosQ *__restrict__ atoms, int4 *__restrict__ origin, double *__restrict__ weights,
-                       int *__restrict__ range_flag) {
+                       size_t wstride, int *__restrict__ range_flag) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = count_ptr ? min(m_bound, *count_ptr) : m_bound;
   if (j >= m) return;
@@ -423,12 +424,12 @@ stencil_prepass_kernel(PPPMGeom g, RhoCoeff rc, int m_bound, const int *__restri
         const double dy = ny + g.shiftone - fy;
         const double dz = nz + g.shiftone - fz;
         const double z0 = g.delvolinv * p.q;  // :205
-        double *w = weights + (size_t)j * (3 * P);
+        double *w = weights + j;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-          w[k] = z0 * rho1d_c<P>(rc, k, dz);
-          w[P + k] = rho1d_c<P>(rc, k, dy);
-          w[2 * P + k] = rho1d_c<P>(rc, k, dx);
+          w[(size_t)k * wstride] = z0 * rho1d_c<P>(rc, k, dz);
+          w[(size_t)(P + k) * wstride] = rho1d_c<P>(rc, k, dy);
+          w[(size_t)(2 * P + k) * wstride] = rho1d_c<P>(rc, k, dx);
         }
       }
     }
@@ -439,7 +440,7 @@ stencil_prepass_kernel(PPPMGeom g, RhoCoeff rc, int m_bound, const int *__restri
 template <int P, int TZ>
 __global__ void __launch_bounds__(32)
 spread_mma_kernel(PPPMGeom g, SpreadPlan sp, const int4 *__restrict__ origin, const double *__restrict__ weights,
-                  const int *__restrict__ cell_start, double *__restrict__ brick) {
+                  size_t wstride, const int *__restrict__ cell_start, double *__restrict__ brick) {
   constexpr int WS = (TZ + SM_TY + SM_TX) | 1;  // scratch row: zw[TZ] | wy[8] | wx[32], odd stride
   constexpr unsigned FULL = 0xffffffffu;
   __shared__ double wsc[32 * WS];
@@ -518,12 +519,13 @@ spread_mma_kernel(PPPMGeom g, SpreadPlan sp, const int4 *__restrict__ origin, co
         __syncwarp();
         if (hit) {
           const int r = __popc(hits & lt_mask);
-          const double *w = weights + (size_t)j * (3 * P);
+          const double *w = weights + j;
           double *row = wsc + r * WS;
           unsigned planes = 0u, blocks = 0u;
 #pragma unroll
           for (int k = 0; k < P; ++k) {
-            const double wz = w[k], wy = w[P + k], wx = w[2 * P + k];
+            const double wz = w[(size_t)k * wstride], wy = w[(size_t)(P + k) * wstride],
+                         wx = w[(size_t)(2 * P + k) * wstride];
             if ((unsigned)(rz + k) < (unsigned)ez) { row[rz + k] = wz; planes |= 1u << (rz + k); }
             if ((unsigned)(ry + k) < (unsigned)ey) row[TZ + ry + k] = wy;
             if ((unsigned)(rx + k) < (unsigned)ex) { row[TZ + SM_TY + rx + k] = wx; blocks |= 1u << ((rx + k) >> 3); }
@@ -1068,11 +1070,13 @@ int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan
 #define CONP_SPM_CASE(P_)                                                                                          \
   case P_:                                                                                                         \
     stencil_prepass_kernel<P_><<<(mb + 255) / 256, 256, 0, s>>>(g, rho_coeff, mb, count_ptr, atoms, plan.origin,  \
-                                                                plan.weights, range_flag);                        \
+                                                                plan.weights, plan.wstride, range_flag);          \
     if (plan.tz == 4)                                                                                              \
-      spread_mma_kernel<P_, 4><<<plan.grid_mma, 32, 0, s>>>(g, plan, plan.origin, plan.weights, cell_start, brick); \
+      spread_mma_kernel<P_, 4><<<plan.grid_mma, 32, 0, s>>>(g, plan, plan.origin, plan.weights, plan.wstride,     \
+                                                            cell_start, brick);                                   \
     else                                                                                                           \
-      spread_mma_kernel<P_, 8><<<plan.grid_mma, 32, 0, s>>>(g, plan, plan.origin, plan.weights, cell_start, brick); \
+      spread_mma_kernel<P_, 8><<<plan.grid_mma, 32, 0, s>>>(g, plan, plan.origin, plan.weights, plan.wstride,     \
+                                                            cell_start, brick);                                   \
     break;
     switch (g.order) {
       CONP_SPM_CASE(1) CONP_SPM_CASE(2) CONP_SPM_CASE(3) CONP_SPM_CASE(4) CONP_SPM_CASE(5) CONP_SPM_CASE(6)

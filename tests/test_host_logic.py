@@ -66,13 +66,21 @@ def test_rank_ownership_partition_is_disjoint_and_complete():
         assert np.array_equal(np.sort(allc), others) and len(set(allc.tolist())) == len(allc)
 
 
-def test_row_blocks_match_library_rule():
-    """Library rule (ctx.cu conp_set_electrodes): equal blocks, multiple of 16 rows."""
-    for n, world in ((192, 2), (10000, 8), (40000, 8), (833, 4), (5, 2)):
-        rpr = -(-(-(-n // world)) // 16) * 16
-        blocks = [(min(n, r * rpr), min(n, min(n, r * rpr) + rpr)) for r in range(world)]
+def test_row_blocks_of_the_library():
+    """conp_row_block (the rule conp_set_electrodes applies): contiguous blocks that tile [0, n), equal and a
+    multiple of 16 rows except at the end, also when n < 16 * world."""
+    from conp_b200 import abi
+    import __graft_entry__
+    import os
+    if not os.path.exists(abi.LIB_PATH):
+        __graft_entry__.build()
+    for n, world in ((192, 2), (10000, 8), (40000, 8), (833, 4), (5, 2), (40000, 1)):
+        blocks = [abi.row_block(n, world, r) for r in range(world)]
+        rpr = blocks[0][2]
+        assert rpr % 16 == 0 and rpr * world >= n and (rpr - 16) * world < n
         assert blocks[0][0] == 0 and blocks[-1][1] == n
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        assert all(b - a == rpr or b == n for a, b, _ in blocks)
 
 
 def test_matrix_file_formats(tmp_path):
