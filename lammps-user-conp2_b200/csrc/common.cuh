@@ -387,6 +387,19 @@ int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan
                              const int *cell_start, int m_bound /* upper bound of the sorted charges */,
                              const int *count_ptr /* device: their actual number, or nullptr */, double *brick,
                              int *range_flag);
+// z-sweep spread (pppm.cu): second, mesh-aligned sort of the charges + one warp per (column, z-segment)
+struct SweepPlan {
+  bool usable = false;
+  int ncolx = 0, ncoly = 0, pz_lo = 0, npz = 0, wrap_z = 0, nbins = 0, nitems = 0, grid = 0;
+  // device buffers (owned by the context)
+  int *bin_of = nullptr, *slot = nullptr, *bin_count = nullptr, *bin_start = nullptr, *counter = nullptr;
+  double *records = nullptr;  // [m][(3 order + 2) & ~1]: origin + weights of every charge, in bin order
+  const int4 *items = nullptr;
+};
+void plan_pppm_sweep(const PPPMGeom &g, int num_sms, std::vector<int4> &items, SweepPlan &plan);
+// atoms: the packed (unsorted) charges; valid: nullptr, or per slot a value < 0 for slots to skip
+int launch_pppm_spread_sweep(cudaStream_t s, const PPPMGeom &g, const SweepPlan &plan, const double *rho_coeff_host,
+                             const PosQ *atoms, int m_bound, const int *valid, double *brick, int *range_flag);
 int launch_pppm_green_mul(cudaStream_t s, size_t n, cufftDoubleComplex *work, const double *ghalf);
 // rhat: spectra of the rank's nzl input planes (compact planes zs_lo..); uhat: (partial) output-plane spectra
 // Launch plan of the z-convolution (built once per rank by plan_pppm_zconv): narrow column groups stage

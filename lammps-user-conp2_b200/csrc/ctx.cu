@@ -140,8 +140,13 @@ struct conp_ctx {
   DevBuf<int2> d_sp_runs;
   DevBuf<int4> d_sp_origin;
   DevBuf<double> d_sp_weights;
+  // z-sweep spread
+  SweepPlan swplan;
+  DevBuf<int> d_sw_binof, d_sw_slot, d_sw_count, d_sw_start;
+  DevBuf<double> d_sw_records;
+  DevBuf<int4> d_sw_items;
   bool spread_atomic = false;
-  int spread_mode = -1;  // CONP_SPREAD = atomic | smem | mma (default: by size, see conp_post_neighbor)
+  int spread_mode = -1;  // CONP_SPREAD = atomic | smem | mma | sweep (default: by size, see conp_post_neighbor)
   DevBuf<double> d_pw;
   DevBuf<cufftDoubleComplex> d_rhat, d_uhat, d_Kc;
   cufftHandle plan_f = 0, plan_b = 0;
@@ -259,10 +264,27 @@ void ensure_static_cells(conp_ctx *c) {
     if (rr.empty()) rr.push_back(make_int2(0, 0));
     c->d_sp_runstart.upload(rs, c->stream);
     c->d_sp_runs.upload(rr, c->stream);
-    c->d_sp_counter.zero(4, c->stream);
+    c->d_sp_counter.zero(8, c->stream);
     c->splan.run_start = c->d_sp_runstart.p;
     c->splan.runs = c->d_sp_runs.p;
     c->splan.counter = c->d_sp_counter.p;
+    {
+      std::vector<int4> items;
+      plan_pppm_sweep(c->pg, c->num_sms, items, c->swplan);
+      if (c->swplan.usable) {
+        c->d_sw_items.upload(items, c->stream);
+        c->d_sw_count.zero((size_t)c->swplan.nbins + 8, c->stream);
+        c->d_sw_start.zero((size_t)c->swplan.nbins + 8, c->stream);
+        c->swplan.items = c->d_sw_items.p;
+        c->swplan.bin_count = c->d_sw_count.p;
+        c->swplan.bin_start = c->d_sw_start.p;
+        c->swplan.counter = c->d_sp_counter.p + 1;
+        if (c->debug)
+          fprintf(stderr, "[conp] rank %d sweep spread: %d x %d columns, origin planes %d..+%d, %d bins, %d items, grid %d\n",
+                  c->rank, c->swplan.ncoly, c->swplan.ncolx, c->swplan.pz_lo, c->swplan.npz, c->swplan.nbins,
+                  c->swplan.nitems, c->swplan.grid);
+      }
+    }
     if (c->debug)
       fprintf(stderr, "[conp] rank %d spread tiles: %d x %d x %d tiles of %d x %d x %d (z,y,x), %zu cell runs, "
               "%zu B smem per warp, grid %d\n", c->rank, c->splan.ntz, c->splan.nty, c->splan.ntx, c->splan.tz,
@@ -521,14 +543,24 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     c->launches += launch_bin_positions(s, g, c->m_slots, c->mpad, counts, c->d_packed.p, c->d_cellof.p,
                                         c->d_slot.p, c->d_cellcount.p, relevant, ps_pos);
   }
-  c->launches += launch_cell_scan(s, g.ncells, c->d_cellcount.p, c->d_cellstart.p, c->d_packed.p, c->mpad,
+  // The z-sweep spread reads the packed charges itself (it has its own, mesh-aligned sort), so the physical
+  // cell sort then feeds only the real-space pair kernel and moves to the side stream with it.
+  const bool use_sweep = kspace_mode == CONP_KSPACE_PPPM && !c->spread_atomic && c->swplan.usable &&
+                         c->spread_mode != 1 && c->spread_mode != 2;
+  const bool sort_aside = fork && use_sweep;
+  cudaStream_t u = sort_aside ? t : s;
+  if (sort_aside) {
+    CUDA_CHECK(cudaEventRecord(c->ev_sorted, s));
+    CUDA_CHECK(cudaStreamWaitEvent(t, c->ev_sorted, 0));
+  }
+  c->launches += launch_cell_scan(u, g.ncells, c->d_cellcount.p, c->d_cellstart.p, c->d_packed.p, c->mpad,
                                   c->nranks, multi ? c->scal(2) : nullptr);
-  c->launches += launch_cell_scatter(s, g, c->m_slots, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
+  c->launches += launch_cell_scatter(u, g, c->m_slots, c->d_packed.p, c->d_ptype.p, c->d_cellof.p, c->d_slot.p,
                                      c->d_cellstart.p, c->d_sorted.p, c->d_stype.p, c->d_ssrc.p, c->d_sortedf.p);
   stage_mark(c, 2);
 
   // ---- real-space part of b (blist_coul_cal), beside the k-space chain -----------
-  if (fork) {
+  if (fork && !sort_aside) {
     CUDA_CHECK(cudaEventRecord(c->ev_sorted, s));
     CUDA_CHECK(cudaStreamWaitEvent(t, c->ev_sorted, 0));
   }
@@ -551,7 +583,12 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
     auto kmark = [&](int i) { if (c->stage_timing && c->debug) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
     kmark(0);
-    if (!c->spread_atomic) {
+    if (use_sweep) {
+      // all packed charges on one GPU; on several, the inbox slots bin_positions accepted (cell_of >= 0)
+      c->launches += launch_pppm_spread_sweep(s, pg, c->swplan, c->h_rho.data(), c->d_packed.p,
+                                              multi ? c->m_slots : c->m_total, multi ? c->d_cellof.p : nullptr,
+                                              c->d_brick.p, c->d_flag.p);
+    } else if (!c->spread_atomic) {
       // the sorted charges: all of them on one GPU, the relevant subset (count in cell_start[ncells]) on several
       c->launches += launch_pppm_spread_tiles(s, pg, c->splan, c->h_rho.data(), c->d_sorted.p, c->d_cellstart.p,
                                               multi ? c->m_slots : c->m_total,
@@ -896,7 +933,8 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
     c->route_allowed = getenv("CONP_ROUTE") == nullptr || atoi(getenv("CONP_ROUTE")) != 0;
     if (const char *e = getenv("CONP_SPREAD"))
-      c->spread_mode = !strcmp(e, "atomic") ? 0 : !strcmp(e, "smem") ? 1 : !strcmp(e, "mma") ? 2 : -1;
+      c->spread_mode = !strcmp(e, "atomic") ? 0 : !strcmp(e, "smem") ? 1 : !strcmp(e, "mma") ? 2 :
+                       !strcmp(e, "sweep") ? 3 : -1;
     if (getenv("CONP_SPREAD_ATOMIC") != nullptr && atoi(getenv("CONP_SPREAD_ATOMIC")) != 0) c->spread_mode = 0;
     c->d_scal.zero(16, c->stream);
     c->d_partials.zero(3 * 1024, c->stream);
@@ -1637,13 +1675,19 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
     // red.global kernel below (fewer fixed costs: no per-step stencil pass, no tile scan).
     c->spread_atomic = c->spread_mode == 0 ||
                        (c->spread_mode < 0 && (long long)c->m_total / c->nranks < 250000LL);
-    if (c->have_pppm && c->splan.use_mma) {  // per-charge stencil origins / weights of the tensor-core spread
+    if (c->have_pppm && (c->splan.use_mma || c->swplan.usable)) {  // per-charge stencil data of the tensor-core spreads
       const size_t mm = (size_t)std::max(c->m_slots, 1);
       c->d_sp_origin.reserve(mm);
       c->d_sp_weights.reserve(mm * 3 * c->pg.order);
       c->splan.origin = c->d_sp_origin.p;
       c->splan.weights = c->d_sp_weights.p;
       c->splan.wstride = mm;
+      c->d_sw_binof.reserve(mm);
+      c->d_sw_slot.reserve(mm);
+      c->d_sw_records.reserve(mm * (size_t)((3 * c->pg.order + 2) & ~1));
+      c->swplan.bin_of = c->d_sw_binof.p;
+      c->swplan.slot = c->d_sw_slot.p;
+      c->swplan.records = c->d_sw_records.p;
     }
     c->d_cellcount.zero((size_t)c->grid_b.ncells + 8, s);
     c->d_cellstart.zero((size_t)c->grid_b.ncells + 8, s);

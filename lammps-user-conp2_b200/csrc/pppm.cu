@@ -43,6 +43,12 @@ __device__ __forceinline__ int wrapi(int m, int n) {
   return m < 0 ? m + n : m;
 }
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
+}
+
 // LAMMPS PPPM::compute_rho1d for one axis (Horner in rho_coeff, same loop as
 // pppm_conp_intel.cpp:290-301); rc is [order][order] with k shifted by -nlower
 __device__ __forceinline__ double rho1d(const double *__restrict__ rc, int order, int k, double d) {
@@ -574,6 +580,319 @@ spread_mma_kernel(PPPMGeom g, SpreadPlan sp, const int4 *__restrict__ origin, co
   }
 }
 
+// ---------------------------------------------------------------------------
+// z-sweep form of the tensor-core spread (the default for large systems).
+//
+// What the tile kernels above pay for is finding and clipping the charges of a tile: the sort cells are
+// physical (rc/2 wide, shared with the pair kernels), so every tile re-reads several times the charges it
+// uses, and a 5-point stencil straddles a 4-8 point tile in most directions.  Here the charges get a second,
+// mesh-aligned counting sort per step -- key = (column, origin plane), a column being a footprint of 8 mesh
+// rows x 32 mesh columns, plane fastest -- and a warp sweeps one column upwards through z:
+//   * all charges whose stencil starts on plane p touch exactly the planes p .. p+order-1, so the warp keeps
+//     a window of `order` planes x 8 rows x 32 columns as accumulator fragments in registers; after the
+//     charges of origin plane p, plane p is complete: it is stored (once, plain stores) and its registers
+//     become plane p+order (the window rotates by renaming inside an unrolled loop, no register moves);
+//   * candidates of plane p are the four bins (this column and its -y, -x, -xy neighbours, whose stencils
+//     can reach over the border) of that plane: no scan of unrelated charges, no clipping in z at all;
+//   * the accumulation is the same block-sparse DMMA as in spread_mma_kernel (4 charges x 8 rows x 8 columns
+//     per mma.sync.m8n8k4.f64), always over all `order` planes.
+// Work items are (column, z-segment); a segment first runs the order-1 origin planes below it (warm-up).
+// mesh_bin_kernel / mesh_scatter_kernel do the sort: origin + bin, exclusive scan (cell_scan_kernel), then the
+// weights are computed once and written straight to their sorted place.
+// ---------------------------------------------------------------------------
+constexpr int SW_FY = 8, SW_FX = 32, SW_NXB = SW_FX / 8;
+
+struct SweepGeom {
+  int ncolx, ncoly;   // columns along x / y
+  int pz_lo, npz;     // origin planes binned: compact planes pz_lo .. pz_lo + npz - 1 (mod nz when periodic)
+  int wrap_z;         // the slab is the whole periodic mesh: origin planes wrap
+};
+
+// origin plane -> bin plane index, or -1
+__device__ __forceinline__ int sweep_plane(const SweepGeom &sg, int zi0, int nz) {
+  int t = zi0 - sg.pz_lo;
+  if (sg.wrap_z) { t += t < 0 ? nz : 0; t -= t >= nz ? nz : 0; }
+  return ((unsigned)t < (unsigned)sg.npz) ? t : -1;
+}
+
+template <int P>
+__device__ __forceinline__ bool stencil_origin(const PPPMGeom &g, const PosQ &p, int &ox, int &oy, int &zi0, double &dx,
+                                               double &dy, double &dz, int *range_flag) {
+  if (p.q == 0.0) return false;  // pppm_conp.cpp:161
+  const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
+  const double fy = (p.y - g.boxlo[1]) * g.delinv[1];
+  const double fz = (p.z - g.boxlo[2]) * g.delinv[2];
+  if (!(fabs(fx) < OFFSET / 2 && fabs(fy) < OFFSET / 2 && fabs(fz) < OFFSET / 2)) {
+    *range_flag = 1;  // "Out of range atoms - cannot compute PPPM", pppm_conp.cpp:167
+    return false;
+  }
+  const int nx = (int)(fx + g.shift) - OFFSET;  // :146-148
+  const int ny = (int)(fy + g.shift) - OFFSET;
+  const int nz = (int)(fz + g.shift) - OFFSET;
+  zi0 = wrapi(nz + g.nlower - g.zin_lo, g.nz);
+  if (g.nzi < g.nz && zi0 + P > g.nzi) {
+    *range_flag = 1;  // a plane outside what the box can reach: "Out of range atoms"
+    return false;
+  }
+  ox = wrapi(nx + g.nlower, g.nx);
+  oy = wrapi(ny + g.nlower, g.ny);
+  dx = nx + g.shiftone - fx;  // :199-201
+  dy = ny + g.shiftone - fy;
+  dz = nz + g.shiftone - fz;
+  return true;
+}
+
+template <int P>
+__global__ void __launch_bounds__(256)
+mesh_bin_kernel(PPPMGeom g, SweepGeom sg, int m, const int *__restrict__ valid, const PosQ *__restrict__ atoms,
+                int *__restrict__ bin_of, int *__restrict__ slot, int *__restrict__ bin_count,
+                int *__restrict__ range_flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  int ox, oy, zi0;
+  double dx, dy, dz;
+  int bin = -1;
+  // several GPUs: `valid` (the cell index bin_positions assigned, < 0 = empty or irrelevant inbox slot)
+  if ((!valid || valid[j] >= 0) && stencil_origin<P>(g, atoms[j], ox, oy, zi0, dx, dy, dz, range_flag)) {
+    const int t = sweep_plane(sg, zi0, g.nz);
+    if (t >= 0) bin = ((oy / SW_FY) * sg.ncolx + ox / SW_FX) * sg.npz + t;
+  }
+  bin_of[j] = bin;
+  if (bin >= 0) slot[j] = atomicAdd(bin_count + bin, 1);
+}
+
+// record of charge j at its sorted position d: SW_ND(P) doubles = one or two cache lines,
+//   [0] = (ox, oy) as two ints | [1 .. P] z weights x q/dV | [1+P .. 2P] y weights | [1+2P .. 3P] x weights
+template <int P>
+struct SweepRec {
+  static constexpr int ND = (3 * P + 2) & ~1;  // 1 + 3 P, rounded up to a multiple of 16 bytes
+};
+
+// ND/2 consecutive lanes per charge: lane k of the team computes and stores the record's doubles 2k, 2k+1 as one
+// 16-byte store, so a charge's 128-byte record leaves as one coalesced line
+template <int P>
+__global__ void __launch_bounds__(256)
+mesh_scatter_kernel(PPPMGeom g, RhoCoeff rc, int m, const PosQ *__restrict__ atoms, const int *__restrict__ bin_of,
+                    const int *__restrict__ slot, const int *__restrict__ bin_start, double *__restrict__ records) {
+  constexpr int ND = SweepRec<P>::ND, TEAM = ND / 2;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (int)(gid / TEAM), k2 = (int)(gid - (long long)j * TEAM);
+  if (j >= m) return;
+  const int bin = bin_of[j];
+  if (bin < 0) return;
+  const PosQ p = atoms[j];
+  int ox, oy, zi0, dummy = 0;
+  double dx, dy, dz;
+  stencil_origin<P>(g, p, ox, oy, zi0, dx, dy, dz, &dummy);
+  const size_t d = (size_t)bin_start[bin] + slot[j];
+  const double z0 = g.delvolinv * p.q;  // :205
+  double v[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int e = 2 * k2 + h;  // element of the record
+    if (e == 0) {
+      v[h] = __longlong_as_double(((long long)(unsigned)oy << 32) | (unsigned)ox);
+    } else if (e <= 3 * P) {
+      const int ax = (e - 1) / P, k = (e - 1) - ax * P;  // 0: z, 1: y, 2: x
+      const double dd = ax == 0 ? dz : (ax == 1 ? dy : dx);
+      double r = 0.0;
+#pragma unroll
+      for (int l = P - 1; l >= 0; --l) r = rc.c[l * P + k] + r * dd;  // constant-bank read with a run-time k
+      v[h] = ax == 0 ? z0 * r : r;
+    } else {
+      v[h] = 0.0;
+    }
+  }
+  reinterpret_cast<double2 *>(records + d * ND)[k2] = make_double2(v[0], v[1]);
+}
+
+constexpr int SW_MAXS = 64;  // plane-steps per work item (segment + warm-up), see plan_pppm_sweep
+
+template <int P>
+__global__ void __launch_bounds__(32, 12)
+spread_sweep_kernel(PPPMGeom g, SweepGeom sg, int nitems, const int4 *__restrict__ items, int *__restrict__ counter,
+                    const int *__restrict__ bin_start, const double *__restrict__ records,
+                    double *__restrict__ brick) {
+  constexpr int ND = SweepRec<P>::ND;
+  constexpr int STR = ND + 2;  // staging row stride: 16-byte aligned, rows spread over the banks
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ __align__(16) double stage[2][32 * STR];  // the records of one chunk of 32 candidates, double-buffered
+  __shared__ int order[32];                            // r-th overlapping candidate of the chunk -> its lane
+  __shared__ int rngb[4][SW_MAXS], rnge[4][SW_MAXS];   // per plane-step: record ranges of the four bins
+  __shared__ int stot[SW_MAXS];                        // ... and their total length
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int fy = lane >> 2, fa = lane & 3;
+  const int NX = g.nx, NY = g.ny, NZ = g.nz;
+
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(counter, 1);
+    it = __shfl_sync(FULL, it, 0);
+    if (it >= nitems) break;
+    const int4 item = items[it];  // column, first / end plane of the segment (slab-local t), unused
+    const int col = item.x, t_lo = item.y, t_hi = item.z;
+    const int cy = col / sg.ncolx, cx = col - cy * sg.ncolx;
+    const int y0 = cy * SW_FY, x0 = cx * SW_FX;
+    const int ey = min(SW_FY, NY - y0), ex = min(SW_FX, NX - x0);
+    // the four columns whose charges can reach this one (stencils run towards +y / +x, periodic mesh)
+    const int cym = cy == 0 ? sg.ncoly - 1 : cy - 1, cxm = cx == 0 ? sg.ncolx - 1 : cx - 1;
+    const int ccol[4] = {col, cy * sg.ncolx + cxm, cym * sg.ncolx + cx, cym * sg.ncolx + cxm};  // >= 2 columns per axis
+    const int ts = t_lo - (P - 1);  // origin plane of step 0 (warm-up: the planes below the segment)
+    const int ns = t_hi - ts;       // plane-steps; step s handles origin plane ts + s and completes that plane
+    __syncwarp();
+    for (int u = lane; u < 4 * ns; u += 32) {
+      const int c = u / ns, sidx = u - c * ns;
+      const int cc = c == 0 ? ccol[0] : c == 1 ? ccol[1] : c == 2 ? ccol[2] : ccol[3];
+      int zi = g.zs_lo + ts + sidx;  // compact plane of the step's origin plane
+      if (sg.wrap_z) { zi += zi < 0 ? NZ : 0; zi -= zi >= NZ ? NZ : 0; }
+      const int bp = zi >= 0 ? sweep_plane(sg, zi, NZ) : -1;
+      int b0 = 0, b1 = 0;
+      if (bp >= 0) {
+        const int b = cc * sg.npz + bp;
+        b0 = bin_start[b];
+        b1 = bin_start[b + 1];
+      }
+      rngb[c][sidx] = b0;
+      rnge[c][sidx] = b1;
+    }
+    __syncwarp();
+    for (int u = lane; u < ns; u += 32)
+      stot[u] = (rnge[0][u] - rngb[0][u]) + (rnge[1][u] - rngb[1][u]) + (rnge[2][u] - rngb[2][u]) +
+                (rnge[3][u] - rngb[3][u]);
+    __syncwarp();
+
+    double acc[P][SW_NXB][2];  // window: acc[n] = plane (current origin plane + n)
+#pragma unroll
+    for (int n = 0; n < P; ++n)
+#pragma unroll
+      for (int b = 0; b < SW_NXB; ++b) acc[n][b][0] = acc[n][b][1] = 0.0;
+
+    // candidates of step sidx: the four ranges back to back; total count
+    auto step_total = [&](int sidx) { return stot[sidx]; };
+    // first chunk position at or after (sidx, c0)
+    auto settle = [&](int &sidx, int &c0) {
+      while (sidx < ns && c0 >= step_total(sidx)) { ++sidx; c0 = 0; }
+    };
+    // start the copy of chunk (sidx, c0) into stage[buf]: lane l takes candidate c0 + l
+    auto issue = [&](int sidx, int c0, int buf) {
+      int q = c0 + lane;
+      long long j = -1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n = rnge[c][sidx] - rngb[c][sidx];
+        if (j < 0 && q >= 0 && q < n) j = rngb[c][sidx] + q;
+        q -= n;
+      }
+      if (j >= 0) {
+        const double *src = records + (size_t)j * ND;
+        double *dst = &stage[buf][lane * STR];
+#pragma unroll
+        for (int k = 0; k < ND / 2; ++k) cp_async<16>(dst + 2 * k, src + 2 * k);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // plane (origin plane of step `sidx`) is complete: one plain store per point, rotate the window
+    auto finish_step = [&](int sidx) {
+      const int t = ts + sidx;
+      if (t >= t_lo && fy < ey) {
+        double *dst = brick + ((size_t)t * NY + (y0 + fy)) * NX + x0;
+#pragma unroll
+        for (int b = 0; b < SW_NXB; ++b) {
+          const int cc = 8 * b + 2 * fa;
+          if (cc < ex) dst[cc] = acc[0][b][0];
+          if (cc + 1 < ex) dst[cc + 1] = acc[0][b][1];
+        }
+      }
+#pragma unroll
+      for (int n = 0; n + 1 < P; ++n)
+#pragma unroll
+        for (int b = 0; b < SW_NXB; ++b) { acc[n][b][0] = acc[n + 1][b][0]; acc[n][b][1] = acc[n + 1][b][1]; }
+#pragma unroll
+      for (int b = 0; b < SW_NXB; ++b) acc[P - 1][b][0] = acc[P - 1][b][1] = 0.0;
+    };
+
+    int s_cur = 0, c_cur = 0, buf = 0, s_done = 0;  // s_done: first step whose plane is not finished yet
+    settle(s_cur, c_cur);
+    if (s_cur < ns) issue(s_cur, c_cur, buf);
+    while (s_cur < ns) {
+      int s_nxt = s_cur, c_nxt = c_cur + 32;
+      settle(s_nxt, c_nxt);
+      if (s_nxt < ns) {  // the next chunk's records fly while this one is spread
+        issue(s_nxt, c_nxt, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();
+      while (s_done < s_cur) finish_step(s_done++);  // steps without candidates in between
+      const int nvalid = min(32, step_total(s_cur) - c_cur);
+      const double *st = stage[buf];
+      bool hit = false;
+      if (lane < nvalid) {
+        const long long oo = __double_as_longlong(st[lane * STR]);
+        int ry = (int)(oo >> 32) - y0, rx = (int)(oo & 0xffffffffll) - x0;
+        // (o - 0) mod n, then the last order-1 values are stencils that wrap in from below
+        ry += ry < 0 ? NY : 0; ry -= ry > NY - P ? NY : 0;
+        rx += rx < 0 ? NX : 0; rx -= rx > NX - P ? NX : 0;
+        hit = ry > -P && ry < ey && rx > -P && rx < ex;
+      }
+      const unsigned hits = __ballot_sync(FULL, hit);
+      const int nh = __popc(hits);
+      if (hit) order[__popc(hits & lt_mask)] = lane;
+      __syncwarp();
+      for (int g0 = 0; g0 < nh; g0 += 4) {
+        const int row = g0 + fa;
+        const bool have = row < nh;
+        const double *rec = st + (have ? order[row] : 0) * STR;
+        const long long oo = __double_as_longlong(rec[0]);
+        int ry = (int)(oo >> 32) - y0, rx = (int)(oo & 0xffffffffll) - x0;
+        ry += ry < 0 ? NY : 0; ry -= ry > NY - P ? NY : 0;
+        rx += rx < 0 ? NX : 0; rx -= rx > NX - P ? NX : 0;
+        // column blocks this charge reaches
+        const int c_lo = max(rx, 0), c_hi = min(rx + P - 1, SW_FX - 1);
+        unsigned bg = have ? (((1u << ((c_hi >> 3) + 1)) - 1u) & ~((1u << (c_lo >> 3)) - 1u)) : 0u;
+        bg |= __shfl_xor_sync(FULL, bg, 1);
+        bg |= __shfl_xor_sync(FULL, bg, 2);  // union over the 4 charges: identical in every lane
+        const int my = fy - ry;  // A fragment: row fy of the column, charge fa
+        const double ay = (have && (unsigned)my < (unsigned)P) ? rec[1 + P + my] : 0.0;
+        // B fragment of block b: column 8 b + fy, charge fa.  The usual block patterns of four neighbouring
+        // charges (one block, or two adjacent ones) get straight-line code: no predicate per DMMA.
+#define CONP_SW_BLOCKS(MASK)                                                                           \
+  {                                                                                                    \
+    double bx[SW_NXB];                                                                                 \
+    _Pragma("unroll") for (int b = 0; b < SW_NXB; ++b) {                                               \
+      bx[b] = 0.0;                                                                                     \
+      if ((MASK) & (1u << b)) {                                                                        \
+        const int lx = 8 * b + fy - rx;                                                                \
+        bx[b] = (have && (unsigned)lx < (unsigned)P) ? rec[1 + 2 * P + lx] : 0.0;                      \
+      }                                                                                                \
+    }                                                                                                  \
+    _Pragma("unroll") for (int n = 0; n < P; ++n) {                                                    \
+      const double a = ay * (have ? rec[1 + n] : 0.0);                                                 \
+      _Pragma("unroll") for (int b = 0; b < SW_NXB; ++b)                                               \
+        if ((MASK) & (1u << b)) dmma884(acc[n][b][0], acc[n][b][1], a, bx[b]);                         \
+    }                                                                                                  \
+  }
+        switch (bg) {
+          case 1u: CONP_SW_BLOCKS(1u) break;
+          case 2u: CONP_SW_BLOCKS(2u) break;
+          case 4u: CONP_SW_BLOCKS(4u) break;
+          case 8u: CONP_SW_BLOCKS(8u) break;
+          case 3u: CONP_SW_BLOCKS(3u) break;
+          case 6u: CONP_SW_BLOCKS(6u) break;
+          case 12u: CONP_SW_BLOCKS(12u) break;
+          default: CONP_SW_BLOCKS(bg) break;
+        }
+#undef CONP_SW_BLOCKS
+      }
+      __syncwarp();
+      s_cur = s_nxt; c_cur = c_nxt; buf ^= 1;
+    }
+    while (s_done < ns) finish_step(s_done++);
+  }
+}
+
 // z-convolution with the tabulated kernel, one launch for all (kx,ky) columns.
 //
 // For k_xy != 0 the kernel decays like the Ewald Gaussian / exp(-|k_xy| |dz|): krad[col] bounds the
@@ -594,12 +913,6 @@ spread_mma_kernel(PPPMGeom g, SpreadPlan sp, const int4 *__restrict__ origin, co
 //    the partial sums are combined with a fixed shuffle tree.
 constexpr int ZC_THREADS = 256;
 constexpr int ZC_COLS = 8;
-
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
-}
 
 template <bool REALK>
 __global__ void __launch_bounds__(ZC_THREADS)
@@ -1110,6 +1423,75 @@ int launch_pppm_spread_tiles(cudaStream_t s, const PPPMGeom &g, const SpreadPlan
 #undef CONP_SPT_CASE
   CUDA_CHECK(cudaGetLastError());
   return 1;
+}
+
+// z-sweep spread: columns of 8 x 32 mesh points, origin-plane bins, (column, segment) work items
+void plan_pppm_sweep(const PPPMGeom &g, int num_sms, std::vector<int4> &items, SweepPlan &plan) {
+  plan = SweepPlan();
+  items.clear();
+  const int P = g.order;
+  if (g.zs_n <= 0) return;
+  const int ncx = (g.nx + SW_FX - 1) / SW_FX, ncy = (g.ny + SW_FY - 1) / SW_FY;
+  // a stencil must not wrap inside a column nor jump over a narrow last column
+  if (ncx < 2 || ncy < 2 || g.nx - (ncx - 1) * SW_FX < P - 1 || g.ny - (ncy - 1) * SW_FY < P - 1) return;
+  if (g.nx <= SW_FX + P - 1 || g.ny <= SW_FY + P - 1) return;
+  plan.ncolx = ncx; plan.ncoly = ncy;
+  plan.wrap_z = g.nzi == g.nz;
+  if (plan.wrap_z) {  // periodic z: origin planes below the slab wrap around the ring
+    plan.pz_lo = g.zs_n == g.nz ? 0 : g.zs_lo - (P - 1);
+    plan.npz = g.zs_n == g.nz ? g.nz : g.zs_n + (P - 1);
+    if (plan.npz > g.nz) return;
+  } else {
+    plan.pz_lo = std::max(0, g.zs_lo - (P - 1));
+    plan.npz = g.zs_lo + g.zs_n - plan.pz_lo;
+  }
+  plan.nbins = ncx * ncy * plan.npz;
+  const int ncols = ncx * ncy;
+  const int per_sm = 12;  // register-limited (~165 per lane) one-warp CTAs per SM
+  const int target = num_sms * per_sm;
+  int nseg = std::max(1, std::min((target + ncols - 1) / ncols, std::max(1, g.zs_n / 16)));
+  nseg = std::max(nseg, (g.zs_n + (SW_MAXS - P) - 1) / (SW_MAXS - P));  // segment + warm-up <= SW_MAXS plane-steps
+  const int seg = (g.zs_n + nseg - 1) / nseg;
+  for (int t0 = 0; t0 < g.zs_n; t0 += seg)  // segment-major: neighbouring CTAs work on the same planes (L2 locality)
+    for (int c = 0; c < ncols; ++c) items.push_back(make_int4(c, t0, std::min(t0 + seg, g.zs_n), 0));
+  plan.nitems = (int)items.size();
+  plan.grid = std::min(plan.nitems, target);
+  plan.usable = true;
+}
+
+int launch_pppm_spread_sweep(cudaStream_t s, const PPPMGeom &g, const SweepPlan &sp, const double *rho_coeff_host,
+                             const PosQ *atoms, int m_bound, const int *valid, double *brick, int *range_flag) {
+  if (!sp.usable || g.zs_n <= 0) return 0;
+  if (m_bound <= 0) {
+    CUDA_CHECK(cudaMemsetAsync(brick, 0, sizeof(double) * (size_t)g.zs_n * g.ny * g.nx, s));
+    return 0;
+  }
+  RhoCoeff rc;
+  std::memset(&rc, 0, sizeof(rc));
+  std::memcpy(rc.c, rho_coeff_host, sizeof(double) * g.order * g.order);
+  SweepGeom sg;
+  sg.ncolx = sp.ncolx; sg.ncoly = sp.ncoly; sg.pz_lo = sp.pz_lo; sg.npz = sp.npz; sg.wrap_z = sp.wrap_z;
+  CUDA_CHECK(cudaMemsetAsync(sp.bin_count, 0, sizeof(int) * ((size_t)sp.nbins + 8), s));
+  CUDA_CHECK(cudaMemsetAsync(sp.counter, 0, sizeof(int), s));
+  const unsigned gb = (unsigned)((m_bound + 255) / 256);
+#define CONP_SWEEP_CASE(P_)                                                                                          \
+  case P_:                                                                                                           \
+    mesh_bin_kernel<P_><<<gb, 256, 0, s>>>(g, sg, m_bound, valid, atoms, sp.bin_of, sp.slot, sp.bin_count,          \
+                                           range_flag);                                                             \
+    launch_cell_scan(s, sp.nbins, sp.bin_count, sp.bin_start, nullptr, 1, 1, nullptr);                               \
+    mesh_scatter_kernel<P_><<<(unsigned)(((long long)m_bound * (((3 * P_ + 2) & ~1) / 2) + 255) / 256), 256, 0, s>>>( \
+        g, rc, m_bound, atoms, sp.bin_of, sp.slot, sp.bin_start, sp.records);                                       \
+    spread_sweep_kernel<P_><<<sp.grid, 32, 0, s>>>(g, sg, sp.nitems, sp.items, sp.counter, sp.bin_start, sp.records, \
+                                                   brick);                                                          \
+    break;
+  switch (g.order) {
+    CONP_SWEEP_CASE(1) CONP_SWEEP_CASE(2) CONP_SWEEP_CASE(3) CONP_SWEEP_CASE(4) CONP_SWEEP_CASE(5)
+    CONP_SWEEP_CASE(6) CONP_SWEEP_CASE(7)
+    default: CONP_THROW(CONP_ERR_ARG, "PPPM order %d not supported", g.order);
+  }
+#undef CONP_SWEEP_CASE
+  CUDA_CHECK(cudaGetLastError());
+  return 4;
 }
 
 int launch_region_gather(cudaStream_t s, const PPPMGeom &g, int which, const int lo[3], const int hi[3],

@@ -233,7 +233,7 @@ def test_unsymmetric_influence_function_takes_the_complex_kernel():
     fix.close()
 
 
-@pytest.mark.parametrize("kernel", ["atomic", "smem", "mma"])
+@pytest.mark.parametrize("kernel", ["atomic", "smem", "mma", "sweep"])
 @pytest.mark.parametrize("which", ["small_slab", "dilute_periodic", "dilute_slab_order7", "small_order4"])
 def test_all_spread_kernels_give_the_oracle_density(kernel, which, monkeypatch):
     """elyte_make_rho (pppm_conp.cpp:172-228) through each of the three spread kernels -- red.global,

@@ -32,6 +32,9 @@ def _worker(rank, world, uid_file, case_name, out_file):
     elif case_name == "dilute_cond":
         lmp, arg = dilute(2)
         arg[2], arg[6] = "cond", "0.02"
+    elif case_name == "small_pppm_sweep":   # the z-sweep tensor-core spread on each rank's slab of planes
+        os.environ["CONP_SPREAD"] = "sweep"
+        lmp, arg = synthetic("small", h=0.5, accuracy=1e-4)
     else:
         lmp, arg = synthetic("small", h=1.25, accuracy=1e-4)
     fix = make_fix(lmp, arg, device=rank, rank=rank, nranks=world, unique_id=uid)
@@ -45,14 +48,14 @@ def _worker(rank, world, uid_file, case_name, out_file):
     b, bk = fix.ctx.get_b()
     info = fix.ctx.info()
     extra = {}
-    if case_name == "small_pppm":  # bricks are sharded (electrolyte by z-slab, electrode by rows): gathered on demand
+    if case_name.startswith("small_pppm"):  # bricks are sharded (electrolyte by z-slab, electrode by rows): gathered on demand
         extra = dict(rho=fix.ctx.get_density(0), rho_e=fix.ctx.get_density(1), u=fix.ctx.get_potential_brick())
     np.savez(out_file % rank, q=q, q2=q2, scalar=fix.scalar_output, b=b, rows=[info.row_begin, info.row_end],
              eself=eself, ecoul=ecoul, **extra)
     fix.close()
 
 
-@pytest.mark.parametrize("case_name", ["dilute_ewald", "dilute_cond", "small_pppm"])
+@pytest.mark.parametrize("case_name", ["dilute_ewald", "dilute_cond", "small_pppm", "small_pppm_sweep"])
 def test_two_ranks_match_oracle(tmp_path, case_name):
     import torch
     if torch.cuda.device_count() < 2:
@@ -75,6 +78,8 @@ def test_two_ranks_match_oracle(tmp_path, case_name):
     elif case_name == "dilute_cond":
         lmp, arg = dilute(2)
         arg[2], arg[6] = "cond", "0.02"
+    elif case_name == "small_pppm_sweep":
+        lmp, arg = synthetic("small", h=0.5, accuracy=1e-4)
     else:
         lmp, arg = synthetic("small", h=1.25, accuracy=1e-4)
     ref = O.OracleFixConp(lmp, arg)
@@ -93,7 +98,7 @@ def test_two_ranks_match_oracle(tmp_path, case_name):
         assert np.abs(r["b"] - ref.bbb_all).max() <= 5e-12 * max(np.abs(ref.bbb_all).max(), 1.0)
         assert abs(float(r["scalar"]) - ref.scalar_output) <= 1e-9 * abs(ref.scalar_output) + 1e-12
     assert np.array_equal(res[0]["q2"], res[1]["q2"])  # replicated epilogue is bitwise identical
-    if case_name == "small_pppm":
+    if case_name.startswith("small_pppm"):
         for r in res:
             assert np.abs(r["rho"] - ref.elyte_density).max() <= 1e-12 * np.abs(ref.elyte_density).max()
             assert np.abs(r["rho_e"] - ref.ele_density).max() <= 1e-9 * np.abs(ref.ele_density).max() + 1e-15
