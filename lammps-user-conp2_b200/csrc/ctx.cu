@@ -1670,11 +1670,11 @@ int conp_post_neighbor(conp_ctx *c, int nlocal, const double *q, const int *type
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
     ensure_static_cells(c);
-    // Which spread: measured on a B200 (profiles/r02_spread_kernels.md) the three kernels are within ~25 % of
-    // each other; the owner-computes tensor-core kernel wins from a few 1e5 charges per GPU upward, the
-    // red.global kernel below (fewer fixed costs: no per-step stencil pass, no tile scan).
+    // Which spread: measured on a B200 (profiles/r02_spread_kernels.md) the owner-computes tensor-core kernels
+    // win from a few 1e5 charges per GPU upward (cfg5 on one GPU: 500 000), the red.global kernel below
+    // (cfg4; cfg5 on >= 2 GPUs): fewer fixed costs -- no second sort, no per-step stencil pass.
     c->spread_atomic = c->spread_mode == 0 ||
-                       (c->spread_mode < 0 && (long long)c->m_total / c->nranks < 250000LL);
+                       (c->spread_mode < 0 && (long long)c->m_total / c->nranks < 300000LL);
     if (c->have_pppm && (c->splan.use_mma || c->swplan.usable)) {  // per-charge stencil data of the tensor-core spreads
       const size_t mm = (size_t)std::max(c->m_slots, 1);
       c->d_sp_origin.reserve(mm);

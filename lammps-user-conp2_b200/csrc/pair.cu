@@ -694,8 +694,19 @@ void build_pair_runs(const CellGrid &g, int begin, int end, const double *xyz, s
               if (!g.periodic[1] && (cy == 0 || cy == g.nc[1] - 1)) dy = 0.0;
               if (dy * dy + dz * dz > rc2) continue;
               const int base = (cz * g.nc[1] + cy) * g.nc[0];
+              // this row of cells is at least (dy, dz) away: along x only the chord of the cut-off sphere
+              int rlx = lx, rhx = hx;
+              if (g.periodic[0]) {  // (a non-periodic x keeps its clamped edge cells: they hold far-away atoms too)
+                const double xr = std::sqrt(std::max(rc2 - dy * dy - dz * dz, 0.0));
+                const int tlx = (int)std::floor((xi - shx - xr - g.lo[0]) * g.cinv[0]);
+                const int thx = (int)std::floor((xi - shx + xr - g.lo[0]) * g.cinv[0]);
+                if (thx < 0 || tlx > g.nc[0] - 1) continue;
+                rlx = std::max(lx, std::max(0, tlx));
+                rhx = std::min(hx, std::min(thx, g.nc[0] - 1));
+                if (rlx > rhx) continue;
+              }
               PairRun run;
-              run.c0 = base + lx; run.c1 = base + hx + 1;
+              run.c0 = base + rlx; run.c1 = base + rhx + 1;
               run.sx = (short)sx; run.sy = (short)sy; run.sz = (short)sz; run.pad = 0;
               const size_t first = (size_t)run_start[i - begin];
               if (runs.size() > first && runs.back().c1 == run.c0 && runs.back().sx == run.sx &&

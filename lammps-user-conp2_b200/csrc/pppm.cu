@@ -668,15 +668,12 @@ struct SweepRec {
   static constexpr int ND = (3 * P + 2) & ~1;  // 1 + 3 P, rounded up to a multiple of 16 bytes
 };
 
-// ND/2 consecutive lanes per charge: lane k of the team computes and stores the record's doubles 2k, 2k+1 as one
-// 16-byte store, so a charge's 128-byte record leaves as one coalesced line
 template <int P>
 __global__ void __launch_bounds__(256)
 mesh_scatter_kernel(PPPMGeom g, RhoCoeff rc, int m, const PosQ *__restrict__ atoms, const int *__restrict__ bin_of,
                     const int *__restrict__ slot, const int *__restrict__ bin_start, double *__restrict__ records) {
-  constexpr int ND = SweepRec<P>::ND, TEAM = ND / 2;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = (int)(gid / TEAM), k2 = (int)(gid - (long long)j * TEAM);
+  constexpr int ND = SweepRec<P>::ND;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   const int bin = bin_of[j];
   if (bin < 0) return;
@@ -686,24 +683,18 @@ mesh_scatter_kernel(PPPMGeom g, RhoCoeff rc, int m, const PosQ *__restrict__ ato
   stencil_origin<P>(g, p, ox, oy, zi0, dx, dy, dz, &dummy);
   const size_t d = (size_t)bin_start[bin] + slot[j];
   const double z0 = g.delvolinv * p.q;  // :205
-  double v[2];
+  double r[ND];
+  r[0] = __longlong_as_double(((long long)(unsigned)oy << 32) | (unsigned)ox);
+  r[ND - 1] = 0.0;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int e = 2 * k2 + h;  // element of the record
-    if (e == 0) {
-      v[h] = __longlong_as_double(((long long)(unsigned)oy << 32) | (unsigned)ox);
-    } else if (e <= 3 * P) {
-      const int ax = (e - 1) / P, k = (e - 1) - ax * P;  // 0: z, 1: y, 2: x
-      const double dd = ax == 0 ? dz : (ax == 1 ? dy : dx);
-      double r = 0.0;
-#pragma unroll
-      for (int l = P - 1; l >= 0; --l) r = rc.c[l * P + k] + r * dd;  // constant-bank read with a run-time k
-      v[h] = ax == 0 ? z0 * r : r;
-    } else {
-      v[h] = 0.0;
-    }
+  for (int k = 0; k < P; ++k) {
+    r[1 + k] = z0 * rho1d_c<P>(rc, k, dz);
+    r[1 + P + k] = rho1d_c<P>(rc, k, dy);
+    r[1 + 2 * P + k] = rho1d_c<P>(rc, k, dx);
   }
-  reinterpret_cast<double2 *>(records + d * ND)[k2] = make_double2(v[0], v[1]);
+  double2 *dst = reinterpret_cast<double2 *>(records + d * ND);  // one 128-byte line per charge (order 5)
+#pragma unroll
+  for (int k = 0; k < ND / 2; ++k) dst[k] = make_double2(r[2 * k], r[2 * k + 1]);
 }
 
 constexpr int SW_MAXS = 64;  // plane-steps per work item (segment + warm-up), see plan_pppm_sweep
@@ -1479,8 +1470,8 @@ int launch_pppm_spread_sweep(cudaStream_t s, const PPPMGeom &g, const SweepPlan 
     mesh_bin_kernel<P_><<<gb, 256, 0, s>>>(g, sg, m_bound, valid, atoms, sp.bin_of, sp.slot, sp.bin_count,          \
                                            range_flag);                                                             \
     launch_cell_scan(s, sp.nbins, sp.bin_count, sp.bin_start, nullptr, 1, 1, nullptr);                               \
-    mesh_scatter_kernel<P_><<<(unsigned)(((long long)m_bound * (((3 * P_ + 2) & ~1) / 2) + 255) / 256), 256, 0, s>>>( \
-        g, rc, m_bound, atoms, sp.bin_of, sp.slot, sp.bin_start, sp.records);                                       \
+    mesh_scatter_kernel<P_><<<gb, 256, 0, s>>>(g, rc, m_bound, atoms, sp.bin_of, sp.slot, sp.bin_start,             \
+                                               sp.records);                                                         \
     spread_sweep_kernel<P_><<<sp.grid, 32, 0, s>>>(g, sg, sp.nitems, sp.items, sp.counter, sp.bin_start, sp.records, \
                                                    brick);                                                          \
     break;
