@@ -359,8 +359,12 @@ int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &p
 // pppm.cu ------------------------------------------------------------------
 // spreads the sorted charges of cells [cell_lo, cell_hi) (all of them if cell_start == nullptr) onto the
 // rank's slab of input planes; m_bound = upper bound of the number of charges in that range
+// inbox_counts != nullptr: the charges are read unsorted, as they arrived -- sender r's block of the inbox starts at
+// slot r * mpad and holds inbox_counts[r] charges; `valid` (optional) < 0 marks slots this rank does not read
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
-                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag);
+                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag,
+                       const int *inbox_counts = nullptr, int nsenders = 0, int mpad = 0, const int *valid = nullptr);
+int launch_fill_zero(cudaStream_t s, double *p, size_t n);
 // Owner-computes form of the same spread (no atomics): the rank's slab of input planes is cut into tiles of
 // tz x ty x tx mesh points, one warp owns one tile at a time in its private shared memory and stores every
 // mesh point exactly once (also the zeros: no memset of the brick).  plan_pppm_spread_tiles works out, per

@@ -173,7 +173,13 @@ struct conp_ctx {
   bool debug = false;             // CONP_DEBUG: extra timers and plan printouts on stderr
   bool signal_in_kernel = false;  // CONP_SIGNAL_IN_KERNEL=1: producers raise the flags themselves (per-block fences)
   bool uhat_nccl = false;       // CONP_UHAT_NCCL=1: NCCL all-reduce for the spectra even on the peer-to-peer path
+  bool spread_unsorted = true;  // CONP_SPREAD_UNSORTED=0: the red.global spread reads the cell-sorted charges
   bool stage_timing = false;
+  // CONP_TRACE=1 (debugging): one-thread kernels between the stages of the captured step add up %globaltimer
+  // offsets from the step's start -- the only way to see the critical path inside a graph replay, where the
+  // eager per-stage events (launch-rate bound for kernels of a few us) say little.  Each stamp costs ~2 us.
+  bool trace = false;
+  DevBuf<unsigned long long> d_trace;  // [0] start of the current step, [1 + i] sum of offsets of mark i, [40] steps
   double stage_ms[NSTAGE] = {0, 0, 0, 0, 0, 0, 0, 0};
   int stage_n = 0;
 
@@ -400,8 +406,20 @@ void ensure_p2p(conp_ctx *c) {
   }
 }
 
+__global__ void stamp_kernel(unsigned long long *tr, int i) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (i == 0) { tr[0] = t; tr[40]++; }
+  tr[1 + i] += t - tr[0];
+}
+
+void trace_mark(conp_ctx *c, int i) {
+  if (c->trace && !c->stage_timing) stamp_kernel<<<1, 1, 0, c->stream>>>(c->d_trace.p, i);
+}
+
 void stage_mark(conp_ctx *c, int i) {
   if (c->stage_timing) CUDA_CHECK(cudaEventRecord(c->sev[i], c->stream));
+  trace_mark(c, i);
 }
 
 // q-side matvec out = S.b.  `out` is a full-length (vlen) vector: this rank's rows on return of the
@@ -478,10 +496,10 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     CUDA_CHECK(cudaStreamWaitEvent(t, c->ev_begin, 0));
   }
   if (kspace_mode == CONP_KSPACE_PPPM) {  // clears of the step's bricks, off the critical path
-    if (c->spread_atomic)  // the tile kernel stores every point of the brick itself
-      CUDA_CHECK(cudaMemsetAsync(c->d_brick.p, 0, sizeof(double) * (size_t)std::max(c->pg.zs_n, 1) * c->plane, t));
+    if (c->spread_atomic)  // the owner-computes kernels store every point of the brick themselves
+      c->launches += launch_fill_zero(t, c->d_brick.p, (size_t)std::max(c->pg.zs_n, 1) * c->plane);
     CUDA_CHECK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), t));
-    CUDA_CHECK(cudaMemsetAsync(c->d_ebrick.p, 0, sizeof(double) * (size_t)c->pg.nzo * c->plane, t));
+    c->launches += launch_fill_zero(t, c->d_ebrick.p, (size_t)c->pg.nzo * c->plane);
     if (fork) CUDA_CHECK(cudaEventRecord(c->ev_cleared, t));
   }
   // ---- counting sort of the point charges: pack (+histogram, sum q z), scan, scatter ----
@@ -547,7 +565,10 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   // cell sort then feeds only the real-space pair kernel and moves to the side stream with it.
   const bool use_sweep = kspace_mode == CONP_KSPACE_PPPM && !c->spread_atomic && c->swplan.usable &&
                          c->spread_mode != 1 && c->spread_mode != 2;
-  const bool sort_aside = fork && use_sweep;
+  // red.global spread: it reads the packed charges / the inbox as they arrived (unsorted; red.global does not
+  // care: cfg4 +1.7 %), so here too the sort is only the pair kernel's business.  CONP_SPREAD_UNSORTED=0: sorted.
+  const bool spread_inbox = kspace_mode == CONP_KSPACE_PPPM && c->spread_atomic && c->spread_unsorted;
+  const bool sort_aside = fork && (use_sweep || spread_inbox);
   cudaStream_t u = sort_aside ? t : s;
   if (sort_aside) {
     CUDA_CHECK(cudaEventRecord(c->ev_sorted, s));
@@ -581,7 +602,10 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   if (kspace_mode == CONP_KSPACE_PPPM) {
     const PPPMGeom &pg = c->pg;
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_cleared, 0));
-    auto kmark = [&](int i) { if (c->stage_timing && c->debug) CUDA_CHECK(cudaEventRecord(c->kev[i], s)); };
+    auto kmark = [&](int i) {
+      if (c->stage_timing && c->debug) CUDA_CHECK(cudaEventRecord(c->kev[i], s));
+      trace_mark(c, 10 + i);
+    };
     kmark(0);
     if (use_sweep) {
       // all packed charges on one GPU; on several, the inbox slots bin_positions accepted (cell_of >= 0)
@@ -595,8 +619,16 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                               multi ? c->d_cellstart.p + g.ncells : nullptr, c->d_brick.p,
                                               c->d_flag.p);
     } else if (!multi) {
-      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, nullptr, 0, 0, c->d_brick.p,
-                                        c->d_flag.p);
+      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, spread_inbox ? c->d_packed.p : c->d_sorted.p,
+                                        nullptr, 0, 0, c->d_brick.p, c->d_flag.p);
+    } else if (spread_inbox) {
+      // what arrived: this rank's slab charges plus the pair kernel's halo (the kernel skips planes outside the
+      // slab).  Grid for the uniform share + 50 %; the kernel grid-strides beyond it.
+      const int *counts = routed ? (const int *)(p2p_local(c->p2p) + c->off_rcnt) : c->d_mcounts.p;
+      const long long bound = (long long)c->m_total / c->nranks * 3 / 2 + 1024;
+      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, (int)std::min<long long>(bound, c->m_slots), c->d_packed.p,
+                                        nullptr, 0, 0, c->d_brick.p, c->d_flag.p, counts, c->nranks, c->mpad,
+                                        c->d_cellof.p);
     } else if (c->periodic[2]) {  // the slab's stencils wrap: every sorted (= relevant) charge is a candidate
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_cellstart.p, 0, g.ncells,
                                         c->d_brick.p, c->d_flag.p);
@@ -928,6 +960,12 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     for (auto &ev : c->sev) CUDA_CHECK(cudaEventCreate(&ev));
     for (auto &ev : c->kev) CUDA_CHECK(cudaEventCreate(&ev));
     c->debug = getenv("CONP_DEBUG") != nullptr;
+    c->spread_unsorted = getenv("CONP_SPREAD_UNSORTED") == nullptr || atoi(getenv("CONP_SPREAD_UNSORTED")) != 0;
+    c->trace = getenv("CONP_TRACE") != nullptr && atoi(getenv("CONP_TRACE")) != 0;
+    if (c->trace) {
+      c->d_trace.reserve(48);
+      CUDA_CHECK(cudaMemset(c->d_trace.p, 0, sizeof(unsigned long long) * 48));
+    }
     if (getenv("CONP_EWALD_GEMM")) c->eg_mode = atoi(getenv("CONP_EWALD_GEMM")) != 0 ? 1 : 0;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
@@ -2036,6 +2074,21 @@ int conp_stage_times(conp_ctx *c, int enable, double *out8) {
   if (n && c->debug)
     fprintf(stderr, "[conp] rank %d k-space stage (ms): spread %.4f fft %.4f zconv %.4f all-reduce %.4f ifft %.4f\n",
             c->rank, c->kev_ms[0] / n, c->kev_ms[1] / n, c->kev_ms[2] / n, c->kev_ms[3] / n, c->kev_ms[4] / n);
+  if (c->trace) {  // the graph replays so far: mean offset of every mark from the step's start
+    unsigned long long h[48];
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpy(h, c->d_trace.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[40]) {
+      static const char *name[16] = {"begin", "packed", "binned", "pair", "kspace", "gathered", "b-exchanged",
+                                     "matvec", "epilogue", "", "k:begin", "k:spread", "k:fft", "k:zconv",
+                                     "k:all-reduce", "k:ifft"};
+      fprintf(stderr, "[conp] rank %d graph timeline over %llu steps (us after begin):", c->rank, h[40]);
+      for (int i = 0; i < 16; ++i)
+        if (name[i][0] && (i == 0 || h[1 + i])) fprintf(stderr, " %s %.1f", name[i], 1e-3 * (double)h[1 + i] / (double)h[40]);
+      fprintf(stderr, "\n");
+    }
+    CUDA_CHECK(cudaMemset(c->d_trace.p, 0, sizeof(h)));
+  }
   c->stage_timing = enable != 0;
   for (auto &v : c->kev_ms) v = 0;
   for (auto &v : c->stage_ms) v = 0;

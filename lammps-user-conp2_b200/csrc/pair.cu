@@ -57,9 +57,28 @@ __device__ __forceinline__ double ferfcr_sqrt(double a2_r2) {
 
 enum { MODE_B = 0, MODE_A = 1, MODE_P = 2 };  // MODE_P: MODE_A's pairs, summed with the partners' charges
 
+// erfcr_sqrt(g^2 r^2) g - erfcr_sqrt(eta^2 r^2) eta (the two lines above, Gaussian electrode charges) with the
+// shared work done once: one reciprocal square root gives r and 1/r, one reciprocal gives both rational
+// arguments t = 1/(1 + p a r).  Same formula, a few ulp apart from evaluating the two terms separately; this is
+// the per-step pair kernel's inner loop (~7e6 pairs per update at cfg5).
+__device__ __forceinline__ double dudq_two_gauss(double g_ewald, double eta, double rsq) {
+  const double rinv = rsqrt(rsq), r = rsq * rinv;
+  const double ag = g_ewald * r, ae = eta * r;
+  const double u = fma(EWALD_P, ag, 1.0), v = fma(EWALD_P, ae, 1.0);
+  const double w = 1.0 / (u * v);
+  const double tg = v * w, te = u * w;
+  const double ag2 = ag * ag, ae2 = ae * ae;
+  const double eg = ag2 < ERFC_MAX * ERFC_MAX ? exp(-ag2) : 0.0;
+  const double ee = ae2 < ERFC_MAX * ERFC_MAX ? exp(-ae2) : 0.0;
+  const double pg = tg * (A1 + tg * (A2 + tg * (A3 + tg * (A4 + tg * A5))));
+  const double pe = te * (A1 + te * (A2 + te * (A3 + te * (A4 + te * A5))));
+  return (pg * eg - pe * ee) * rinv;
+}
+
 // dudq of fix_conp.cpp:1263-1264 / 1335-1336; (it, jt) = (electrode type, partner type)
 template <int MODE>
 __device__ __forceinline__ double dudq_pair(const PairTables &pt, double rsq, int it, int jt) {
+  if (MODE == MODE_B && pt.pairmode != CONP_PAIR_EHGO) return dudq_two_gauss(pt.g_ewald, pt.eta, rsq);
   double v = erfcr_sqrt(pt.g_ewald * pt.g_ewald * rsq) * pt.g_ewald;
   if (pt.pairmode == CONP_PAIR_EHGO) {  // fix_conp.cpp:1561-1566
     const int ij = it * (pt.ntypes + 1) + jt;
@@ -858,6 +877,8 @@ int launch_pair_b(cudaStream_t s, const CellGrid &g, const PairTables &pt, int r
   const double extent = std::max(std::max(g.prd[0], g.prd[1]), g.prd[2]) + 2.0 * g.rc;
   const double slack = 2.0 * (2.0 * std::sqrt(3.0) * g.rc * 4.0 * extent * 1.1920929e-7) + 1e-4 * g.rc * g.rc;
   const float cutmax_f = (float)(g.rc * g.rc + slack);
+  // (Capping the blocks per SM with unused dynamic shared memory, to leave room for the k-space chain's blocks
+  // beside this kernel, was measured: 2 or 3 blocks per SM cost 3-6 % of the step at cfg4 and on two GPUs.)
   pair_kernel<MODE_B><<<(n + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, 0, s>>>(
       g, pt, row_begin, row_end, ex, ey, ez, etype, cell_start, run_start, runs, sorted, sorted_type, sorted_f,
       cutmax_f, nullptr, nullptr, b_real, 0);

@@ -57,28 +57,56 @@ __device__ __forceinline__ double rho1d(const double *__restrict__ rc, int order
   return r;
 }
 
+// Clears of the step's bricks.  (A cudaMemsetAsync node inside the captured step ran at ~0.4 TB/s -- 45 MB of
+// slab brick held the spread back by ~50 us on two GPUs; this streams at HBM store speed.)
+__global__ void __launch_bounds__(256)
+fill_zero_kernel(double *__restrict__ p, size_t n) {
+  const size_t head = ((reinterpret_cast<uintptr_t>(p) & 15) && n) ? 1 : 0;  // up to the first 16-byte boundary
+  const size_t n2 = (n - head) / 2;
+  double2 *p2 = reinterpret_cast<double2 *>(p + head);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    p2[i] = make_double2(0.0, 0.0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (head) p[0] = 0.0;
+    if ((n - head) & 1) p[n - 1] = 0.0;
+  }
+}
+
 // one thread per (atom, z-plane n, y-row m); the thread adds its `order`
 // x-consecutive mesh points with red.global.add.f64.  (A point-per-thread
 // mapping that puts the `order` x-neighbours in adjacent lanes was measured 3x
 // slower: same-sector atomics of one warp instruction serialise in L2.)
 __global__ void __launch_bounds__(256)
 spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, const PosQ *__restrict__ atoms,
-              const int *__restrict__ cell_start, int cell_lo, int cell_hi, double *__restrict__ brick,
+              const int *__restrict__ cell_start, int cell_lo, int cell_hi, const int *__restrict__ inbox_counts,
+              int nsenders, int mpad, const int *__restrict__ valid, double *__restrict__ brick,
               int *__restrict__ range_flag) {
   __shared__ double rc[MAXORDER * MAXORDER];
+  __shared__ int cnt_end[17];  // inbox mode: running totals of the per-sender counts
   const int order = g.order;
   for (int t = threadIdx.x; t < order * order; t += blockDim.x) rc[t] = rho_coeff[t];
+  if (inbox_counts && threadIdx.x == 0) {
+    int tot = 0;
+    for (int r = 0; r < nsenders; ++r) { tot += min(inbox_counts[r], mpad); cnt_end[r] = tot; }
+  }
   __syncthreads();
-  // charges of the cell range (multi-GPU: the cells whose stencils can reach this rank's slab)
-  const int jb = cell_start ? cell_start[cell_lo] : 0;
-  const int je = cell_start ? cell_start[cell_hi] : m_atoms;
+  // charges of the cell range (multi-GPU: the cells whose stencils can reach this rank's slab), or, inbox mode,
+  // the unsorted charges as they arrived: sender r's block starts at slot r * mpad and holds inbox_counts[r]
+  const int jb = inbox_counts ? 0 : (cell_start ? cell_start[cell_lo] : 0);
+  const int je = inbox_counts ? cnt_end[nsenders - 1] : (cell_start ? cell_start[cell_hi] : m_atoms);
   const int per_atom = order * order;
   const long long work = (long long)(je - jb) * per_atom;
   for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < work;
        gid += (long long)gridDim.x * blockDim.x) {
-    const int j = jb + (int)(gid / per_atom);
+    int j = jb + (int)(gid / per_atom);
     const int nm = (int)(gid % per_atom);
     const int n = nm / order, m = nm - n * order;
+    if (inbox_counts) {
+      int r = 0;
+      while (j >= cnt_end[r]) ++r;
+      j = r * mpad + j - (r ? cnt_end[r - 1] : 0);
+      if (valid && valid[j] < 0) continue;  // not in a cell this rank reads
+    }
     const PosQ p = atoms[j];
     if (p.q == 0.0) continue;  // pppm_conp.cpp:161
     const double fx = (p.x - g.boxlo[0]) * g.delinv[0];
@@ -1229,8 +1257,17 @@ add_bricks_kernel(size_t n, const double *__restrict__ a, const double *__restri
 
 }  // namespace
 
+int launch_fill_zero(cudaStream_t s, double *p, size_t n) {
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)std::min<size_t>((n / 2 + 255) / 256 + 1, (size_t)148 * 8);
+  fill_zero_kernel<<<grid, 256, 0, s>>>(p, n);
+  CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
-                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag) {
+                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag,
+                       const int *inbox_counts, int nsenders, int mpad, const int *valid) {
   if (m_bound <= 0 || g.zs_n <= 0) return 0;
   const long long threads = (long long)m_bound * g.order * g.order;
   const unsigned grid = (unsigned)((threads + 255) / 256);
@@ -1245,7 +1282,8 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
     if (per_sm > 0 && per_sm < 8) smem = ((size_t)(227 * 1024) / per_sm - 1024) & ~(size_t)127;
   }
   if (smem > 0) ensure_dynamic_smem(spread_kernel, smem);
-  spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, brick, range_flag);
+  spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, inbox_counts,
+                                        nsenders, mpad, valid, brick, range_flag);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }
