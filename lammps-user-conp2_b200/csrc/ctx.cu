@@ -2082,10 +2082,13 @@ int conp_stage_times(conp_ctx *c, int enable, double *out8) {
       static const char *name[16] = {"begin", "packed", "binned", "pair", "kspace", "gathered", "b-exchanged",
                                      "matvec", "epilogue", "", "k:begin", "k:spread", "k:fft", "k:zconv",
                                      "k:all-reduce", "k:ifft"};
-      fprintf(stderr, "[conp] rank %d graph timeline over %llu steps (us after begin):", c->rank, h[40]);
-      for (int i = 0; i < 16; ++i)
-        if (name[i][0] && (i == 0 || h[1 + i])) fprintf(stderr, " %s %.1f", name[i], 1e-3 * (double)h[1 + i] / (double)h[40]);
-      fprintf(stderr, "\n");
+      char line[1024];
+      int len = snprintf(line, sizeof(line), "[conp] rank %d graph timeline over %llu steps (us after begin):", c->rank,
+                         h[40]);
+      for (int i = 0; i < 16 && len < (int)sizeof(line) - 40; ++i)
+        if (name[i][0] && (i == 0 || h[1 + i]))
+          len += snprintf(line + len, sizeof(line) - len, " %s %.1f", name[i], 1e-3 * (double)h[1 + i] / (double)h[40]);
+      fprintf(stderr, "%s\n", line);  // one write: the ranks' lines must not interleave
     }
     CUDA_CHECK(cudaMemset(c->d_trace.p, 0, sizeof(h)));
   }

@@ -499,32 +499,71 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
       acc = fma(__ldg(q_ele + wq.i[e]), dudq_pair<MODE_A>(pt, wq.rsq[e], it, wq.t[e]), acc);
     }
   };
+  // The runs of a row are walked as one flat sequence of chunks of 32 candidates.  Dependent loads are what this
+  // kernel waits for (run -> cell_start -> candidates; ncu: 45 % occupancy, stalls on the load chain), so lane l
+  // fetches run l's descriptor and target range up front (two load latencies for up to 32 runs instead of two
+  // per run) and the candidates of the next chunk are requested before the current chunk is processed.
+  constexpr unsigned FULL = 0xffffffffu;
   const int r0 = run_start[i - row_begin], r1 = run_start[i - row_begin + 1];
-  for (int r = r0; r < r1; ++r) {
-    const PairRun run = runs[r];
-    const double shx = run.sx * g.prd[0], shy = run.sy * g.prd[1], shz = run.sz * g.prd[2];
-    const float fxi = (float)(xi - shx - g.lo[0]), fyi = (float)(yi - shy - g.lo[1]), fzi = (float)(zi - shz - g.lo[2]);
-    const int jb = __ldg(cell_start + run.c0), je = __ldg(cell_start + run.c1);
-    for (int j0 = jb; j0 < je; j0 += 32) {
+  for (int rb = r0; rb < r1; rb += 32) {
+    const int nrun = min(32, r1 - rb);
+    int4 mr = make_int4(0, 0, 0, 0);  // c0, c1, sx | sy << 16, sz
+    int my_jb = 0, my_je = 0;
+    if (lane < nrun) {
+      mr = __ldg(reinterpret_cast<const int4 *>(runs + rb + lane));
+      my_jb = __ldg(cell_start + mr.x);
+      my_je = __ldg(cell_start + mr.y);
+    }
+    // (q, j0): chunk [j0, j0 + 32) of run q; je, sa, sb: the run's end and packed image shifts.  All warp-uniform.
+    auto advance = [&](int &q, int &j0, int &je, int &sa, int &sb) {
+      j0 += 32;
+      while (j0 >= je) {
+        if (++q >= nrun) return false;
+        j0 = __shfl_sync(FULL, my_jb, q);
+        je = __shfl_sync(FULL, my_je, q);
+        sa = __shfl_sync(FULL, mr.z, q);
+        sb = __shfl_sync(FULL, mr.w, q);
+      }
+      return true;
+    };
+    float4 cur_f = make_float4(0.f, 0.f, 0.f, 0.f), nxt_f = cur_f;
+    EPos cur_e = {}, nxt_e = {};
+    auto fetch = [&](int j0, int je, float4 &pf, EPos &pe) {
+      const int k = j0 + lane;
+      if (k < je) {
+        if (MODE == MODE_B) pf = sorted_f[k];
+        else pe = esorted[k];
+      }
+    };
+    int q = -1, j0 = 0, je = 0, sa = 0, sb = 0;
+    bool have = advance(q, j0, je, sa, sb);
+    if (have) fetch(j0, je, cur_f, cur_e);
+    while (have) {
+      int nq = q, nj0 = j0, nje = je, nsa = sa, nsb = sb;
+      const bool more = advance(nq, nj0, nje, nsa, nsb);
+      if (more) fetch(nj0, nje, nxt_f, nxt_e);
+      // ---- the current chunk ----
+      const int isx = (short)(sa & 0xffff), isy = (short)(sa >> 16), isz = (short)(sb & 0xffff);
+      const double shx = isx * g.prd[0], shy = isy * g.prd[1], shz = isz * g.prd[2];
       const int k = j0 + lane;
       bool pass = false;
       double rsq = 0.0;
       int jt = 0, jidx = 0;
       if (k < je) {
         if (MODE == MODE_B) {
-          const float4 pf = sorted_f[k];
-          const float fx = fxi - pf.x, fy = fyi - pf.y, fz = fzi - pf.z;
+          const float fxi = (float)(xi - shx - g.lo[0]), fyi = (float)(yi - shy - g.lo[1]),
+                      fzi = (float)(zi - shz - g.lo[2]);
+          const float fx = fxi - cur_f.x, fy = fyi - cur_f.y, fz = fzi - cur_f.z;
           pass = fx * fx + fy * fy + fz * fz < cutmax_f;
         } else {
-          const EPos e = esorted[k];
-          jt = e.type; jidx = e.idx;
-          const double dx = xi - (e.x + shx), dy = yi - (e.y + shy), dz = zi - (e.z + shz);
+          jt = cur_e.type; jidx = cur_e.idx;
+          const double dx = xi - (cur_e.x + shx), dy = yi - (cur_e.y + shy), dz = zi - (cur_e.z + shz);
           rsq = dx * dx + dy * dy + dz * dz;
           pass = rsq < __ldg(cut_row + jt);
-          if (jidx == i && run.sx == 0 && run.sy == 0 && run.sz == 0) pass = false;
+          if (jidx == i && isx == 0 && isy == 0 && isz == 0) pass = false;
         }
       }
-      const unsigned mask = __ballot_sync(0xffffffffu, pass);
+      const unsigned mask = __ballot_sync(FULL, pass);
       if (pass) {
         const int pos = qn + __popc(mask & lt_mask);
         if (MODE == MODE_B) {
@@ -540,6 +579,9 @@ pair_kernel(CellGrid g, PairTables pt, int row_begin, int row_end, const double 
         qn -= 32;
         __syncwarp();
       }
+      cur_f = nxt_f; cur_e = nxt_e;
+      q = nq; j0 = nj0; je = nje; sa = nsa; sb = nsb;
+      have = more;
     }
   }
   __syncwarp();
