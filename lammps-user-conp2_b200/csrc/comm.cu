@@ -439,6 +439,8 @@ PeerSync p2p_sync(PeerArena *a, int chan) {
   return ps;
 }
 
+size_t p2p_arena_offset(size_t payload_off) { return arena_off(payload_off); }
+
 int p2p_signal(PeerArena *a, int chan, cudaStream_t s, size_t value_off, const double *value, size_t count_off,
                const int *counts) {
   p2p_signal_kernel<<<1, 32, 0, s>>>(p2p_sync(a, chan), value ? arena_off(value_off) : 0, value,
@@ -447,11 +449,13 @@ int p2p_signal(PeerArena *a, int chan, cudaStream_t s, size_t value_off, const d
   return 1;
 }
 
-int p2p_allreduce_pull_f64(PeerArena *a, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t s) {
+int p2p_allreduce_pull_f64(PeerArena *a, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t s,
+                           int raise_ready) {
   const size_t slice = (n + a->nranks - 1) / a->nranks;
   const unsigned grid = (unsigned)std::min<size_t>(296, std::max<size_t>(1, (slice + 255) / 256));
-  p2p_pull_reduce_bcast_kernel<<<grid, 256, 0, s>>>(p2p_sync(a, chan_ready), p2p_sync(a, chan_done), arena_off(off), n,
-                                                    slice);
+  PeerSync ready = p2p_sync(a, chan_ready);
+  ready.raise_first = raise_ready;
+  p2p_pull_reduce_bcast_kernel<<<grid, 256, 0, s>>>(ready, p2p_sync(a, chan_done), arena_off(off), n, slice);
   CUDA_CHECK(cudaGetLastError());
   return 1 + p2p_wait(a, chan_done, s);
 }

@@ -232,7 +232,10 @@ int p2p_wait(PeerArena *, int chan, cudaStream_t);
 int p2p_allreduce_f64(PeerArena *, size_t off, size_t n, size_t stage_off, int chan, cudaStream_t);
 // same sum for a vector whose producer kernel raised `chan_ready` itself (peer_block_signal): pull the
 // partial slices over NVLink, store the total everywhere, wait on `chan_done`
-int p2p_allreduce_pull_f64(PeerArena *, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t);
+// raise_ready: the producer only stored; the pull kernel raises this rank's `chan_ready` flags itself
+int p2p_allreduce_pull_f64(PeerArena *, size_t off, size_t n, int chan_ready, int chan_done, cudaStream_t,
+                           int raise_ready = 0);
+size_t p2p_arena_offset(size_t payload_off);  // payload offset -> byte offset from the arena base
 int p2p_error(PeerArena *);  // non-zero after a wait timed out
 // argument for kernels that do their own exchange (peer.cuh); a null arena gives the no-op value
 PeerSync p2p_sync(PeerArena *, int chan);
@@ -362,8 +365,8 @@ int launch_pair_postforce(cudaStream_t s, const CellGrid &g, const PairTables &p
 // inbox_counts != nullptr: the charges are read unsorted, as they arrived -- sender r's block of the inbox starts at
 // slot r * mpad and holds inbox_counts[r] charges; `valid` (optional) < 0 marks slots this rank does not read
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
-                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag,
-                       const int *inbox_counts = nullptr, int nsenders = 0, int mpad = 0, const int *valid = nullptr);
+                       double *brick, int *range_flag, const int *inbox_counts = nullptr, int nsenders = 0,
+                       int mpad = 0, const int *valid = nullptr);
 int launch_fill_zero(cudaStream_t s, double *p, size_t n);
 // Owner-computes form of the same spread (no atomics): the rank's slab of input planes is cut into tiles of
 // tz x ty x tx mesh points, one warp owns one tile at a time in its private shared memory and stores every

@@ -133,8 +133,7 @@ struct conp_ctx {
   DevBuf<int> d_part2grid, d_widx, d_poff, d_flag, d_zmap, d_zout, d_krad, d_zc_wide, d_zc_aout;
   DevBuf<ZconvGroup> d_zc_narrow;
   ZconvPlan zplan;
-  // owner-computes spread (pppm.cu): tiles of the slab + candidate cell runs; CONP_SPREAD_ATOMIC=1 selects
-  // the red.global kernel of round 1 instead (A/B runs)
+  // owner-computes spread (pppm.cu): tiles of the slab + candidate cell runs (CONP_SPREAD selects the kernel)
   SpreadPlan splan;
   DevBuf<int> d_sp_runstart, d_sp_counter;
   DevBuf<int2> d_sp_runs;
@@ -172,6 +171,7 @@ struct conp_ctx {
   double kev_ms[5] = {0, 0, 0, 0, 0};
   bool debug = false;             // CONP_DEBUG: extra timers and plan printouts on stderr
   bool signal_in_kernel = false;  // CONP_SIGNAL_IN_KERNEL=1: producers raise the flags themselves (per-block fences)
+  bool fused_signal = true;     // CONP_FUSED_SIGNAL=0: stand-alone one-block signal kernels behind the producers
   bool uhat_nccl = false;       // CONP_UHAT_NCCL=1: NCCL all-reduce for the spectra even on the peer-to-peer path
   bool spread_unsorted = true;  // CONP_SPREAD_UNSORTED=0: the red.global spread reads the cell-sorted charges
   bool stage_timing = false;
@@ -227,18 +227,6 @@ double slab_pref(const conp_ctx *c) {
   if (!c->slabflag) return 0.0;
   const double volume = c->prd[0] * c->prd[1] * c->prd[2] * c->slab_volfactor;
   return 4.0 * MY_PI / volume;  // km_ewald.cpp:839, pppm_conp.cpp:307
-}
-
-// z-layers of cells (z-major order => one contiguous range of sorted charges) whose stencils can reach
-// this rank's slab of input planes
-void slab_cell_layers(const conp_ctx *c, int *cz_lo_out, int *cz_hi_out) {
-  const PPPMGeom &pg = c->pg;
-  const CellGrid &g = c->grid_b;
-  const double zlo = c->boxlo[2] + (pg.zin_lo + pg.zs_lo - pg.order - 1) / pg.delinv[2];
-  const double zhi = c->boxlo[2] + (pg.zin_lo + pg.zs_lo + pg.zs_n + pg.order + 1) / pg.delinv[2];
-  int cz_lo = (int)std::floor((zlo - g.lo[2]) * g.cinv[2]) - 1, cz_hi = (int)std::floor((zhi - g.lo[2]) * g.cinv[2]) + 1;
-  *cz_lo_out = std::max(0, std::min(cz_lo, g.nc[2] - 1));
-  *cz_hi_out = std::max(0, std::min(cz_hi, g.nc[2] - 1));
 }
 
 // electrodes never move: sort this rank's rows into the cell grid once and mark
@@ -518,7 +506,10 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     return ps;
   };
   const bool late_signal = fused && !c->signal_in_kernel;
-  const PeerSync ps_pos = fused ? p2p_sync(c->p2p, 0) : PeerSync();
+  // ... or, by default, from block 0 of the consuming kernel (PeerSync::raise_first): one launch less per exchange
+  const bool raise_in_consumer = late_signal && c->fused_signal;
+  PeerSync ps_pos = fused ? p2p_sync(c->p2p, 0) : PeerSync();
+  const size_t off_qz = c->off_packed + sizeof(PosQ) * (size_t)(c->m_offsets[c->rank] + c->mpad - 1);
   // routed position exchange: a charge goes only to the ranks whose relevance mask covers its cell
   const bool routed = fused && c->routed && c->have_relevant;
   if (!multi) {
@@ -531,9 +522,13 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                      c->rank, c->nranks, c->mpad, c->d_rel_all.p, p2p_sync(c->p2p, 0),
                                      c->off_packed, c->off_ptype, c->off_psrc, c->d_sendcnt.p, c->scal(2));
     // per-receiver counts, this rank's sum(q z) (padding slot of its inbox block on every rank), flags
-    c->launches += p2p_signal(c->p2p, 0, s,
-                              c->off_packed + sizeof(PosQ) * (size_t)(c->m_offsets[c->rank] + c->mpad - 1),
-                              c->scal(2), c->off_rcnt, c->d_sendcnt.p);
+    if (raise_in_consumer) {
+      ps_pos.raise_first = 1;
+      ps_pos.value_off = p2p_arena_offset(off_qz); ps_pos.value = c->scal(2);
+      ps_pos.count_off = p2p_arena_offset(c->off_rcnt); ps_pos.counts = c->d_sendcnt.p;
+    } else {
+      c->launches += p2p_signal(c->p2p, 0, s, off_qz, c->scal(2), c->off_rcnt, c->d_sendcnt.p);
+    }
   } else {
     // every rank's positions go to every rank; the sum(q z) partial rides in the block's last (padding)
     // slot.  Types and charges are static between reneighbourings and were gathered in conp_post_neighbor.
@@ -541,10 +536,12 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                      ptype_local, nullptr, nullptr, nullptr, c->scal(2),
                                      fused ? producer(0) : PeerSync(),
                                      c->off_packed + sizeof(PosQ) * (size_t)c->m_offsets[c->rank], c->mpad);
-    if (late_signal)  // + this rank's sum(q z) into the block's padding slot on every rank
-      c->launches += p2p_signal(c->p2p, 0, s,
-                                c->off_packed + sizeof(PosQ) * (size_t)(c->m_offsets[c->rank] + c->mpad - 1),
-                                c->scal(2));
+    if (raise_in_consumer) {  // + this rank's sum(q z) into the block's padding slot on every rank
+      ps_pos.raise_first = 1;
+      ps_pos.value_off = p2p_arena_offset(off_qz); ps_pos.value = c->scal(2);
+    } else if (late_signal) {
+      c->launches += p2p_signal(c->p2p, 0, s, off_qz, c->scal(2));
+    }
   }
   stage_mark(c, 1);
   if (multi) {
@@ -566,8 +563,9 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
   const bool use_sweep = kspace_mode == CONP_KSPACE_PPPM && !c->spread_atomic && c->swplan.usable &&
                          c->spread_mode != 1 && c->spread_mode != 2;
   // red.global spread: it reads the packed charges / the inbox as they arrived (unsorted; red.global does not
-  // care: cfg4 +1.7 %), so here too the sort is only the pair kernel's business.  CONP_SPREAD_UNSORTED=0: sorted.
-  const bool spread_inbox = kspace_mode == CONP_KSPACE_PPPM && c->spread_atomic && c->spread_unsorted;
+  // care: cfg4 +1.7 %), so here too the sort is only the pair kernel's business.  CONP_SPREAD_UNSORTED=0: sorted
+  // (one GPU only).
+  const bool spread_inbox = kspace_mode == CONP_KSPACE_PPPM && c->spread_atomic && (multi || c->spread_unsorted);
   const bool sort_aside = fork && (use_sweep || spread_inbox);
   cudaStream_t u = sort_aside ? t : s;
   if (sort_aside) {
@@ -620,27 +618,14 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
                                               c->d_flag.p);
     } else if (!multi) {
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, spread_inbox ? c->d_packed.p : c->d_sorted.p,
-                                        nullptr, 0, 0, c->d_brick.p, c->d_flag.p);
-    } else if (spread_inbox) {
+                                        c->d_brick.p, c->d_flag.p);
+    } else {
       // what arrived: this rank's slab charges plus the pair kernel's halo (the kernel skips planes outside the
       // slab).  Grid for the uniform share + 50 %; the kernel grid-strides beyond it.
       const int *counts = routed ? (const int *)(p2p_local(c->p2p) + c->off_rcnt) : c->d_mcounts.p;
       const long long bound = (long long)c->m_total / c->nranks * 3 / 2 + 1024;
       c->launches += launch_pppm_spread(s, pg, c->d_rho.p, (int)std::min<long long>(bound, c->m_slots), c->d_packed.p,
-                                        nullptr, 0, 0, c->d_brick.p, c->d_flag.p, counts, c->nranks, c->mpad,
-                                        c->d_cellof.p);
-    } else if (c->periodic[2]) {  // the slab's stencils wrap: every sorted (= relevant) charge is a candidate
-      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, c->m_total, c->d_sorted.p, c->d_cellstart.p, 0, g.ncells,
-                                        c->d_brick.p, c->d_flag.p);
-    } else {
-      int cz_lo = 0, cz_hi = 0;
-      slab_cell_layers(c, &cz_lo, &cz_hi);
-      const int cell_lo = cz_lo * g.nc[1] * g.nc[0], cell_hi = (cz_hi + 1) * g.nc[1] * g.nc[0];
-      // upper bound of the charges in the range: uniform share + 50 %, the kernel grid-strides beyond it
-      const long long bound = (long long)c->m_total * (cz_hi - cz_lo + 1) / g.nc[2] * 3 / 2 + 1024;
-      c->launches += launch_pppm_spread(s, pg, c->d_rho.p, (int)std::min<long long>(bound, c->m_total),
-                                        c->d_sorted.p, c->d_cellstart.p, cell_lo, cell_hi, c->d_brick.p,
-                                        c->d_flag.p);
+                                        c->d_brick.p, c->d_flag.p, counts, c->nranks, c->mpad, c->d_cellof.p);
     }
     kmark(1);
     if (pg.zs_n > 0) CUFFT_CHECK(cufftExecD2Z(c->plan_f, c->d_brick.p, c->d_rhat.p));
@@ -649,13 +634,14 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     c->launches += launch_pppm_zconv(s, (int)c->ncol, pg.nz, pg.zs_n, pg.zs_lo, pg.nzo, c->d_krad.p, c->zplan,
                                      c->d_rhat.p, c->k_real ? c->d_Kr.p : nullptr, c->d_Kc.p, c->d_uhat.p,
                                      uhat_p2p ? producer(1) : PeerSync());
-    if (uhat_p2p && late_signal) c->launches += p2p_signal(c->p2p, 1, s);
+    if (uhat_p2p && late_signal && !raise_in_consumer) c->launches += p2p_signal(c->p2p, 1, s);
     kmark(3);
     // every rank holds the partial sum over its slab: one small all-reduce completes the spectra (zconv has
     // announced its partial; the owner of a slice pulls it from every rank, sums, and stores it everywhere)
     if (multi) {
       if (uhat_p2p)
-        c->launches += p2p_allreduce_pull_f64(c->p2p, c->off_uhat, 2 * (size_t)pg.nzo * c->ncol, 1, 2, s);
+        c->launches += p2p_allreduce_pull_f64(c->p2p, c->off_uhat, 2 * (size_t)pg.nzo * c->ncol, 1, 2, s,
+                                              raise_in_consumer ? 1 : 0);
       else
         comm_allreduce_sum_f64(c->comm, (double *)c->d_uhat.p, 2 * (size_t)pg.nzo * c->ncol, s);
     }
@@ -668,7 +654,9 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     c->launches += launch_pppm_gather_b(s, c->pg, c->r0, c->r1, c->d_poff.p, c->d_pw.p, c->d_ubrick.p,
                                         c->d_ez.p, c->scal(2), spref, c->d_breal.p, c->d_bk.p, c->d_b.p,
                                         fused_b ? producer(3) : PeerSync(), c->off_b);
-    if (fused_b && late_signal) c->launches += p2p_signal(c->p2p, 3, s);
+    // (the symmetric matvec's consumers wait for b themselves and can raise the flags first; the stand-alone
+    // wait kernel of the general GEMV path cannot)
+    if (fused_b && late_signal && !(raise_in_consumer && fused && c->sym)) c->launches += p2p_signal(c->p2p, 3, s);
   } else {
     const EwaldHost &e = c->ew;
     const bool gemm = use_ewald_gemm(c);
@@ -720,12 +708,14 @@ void enqueue_step(conp_ctx *c, int kspace_mode, int variant) {
     c->launches += enqueue_matvec(c, s, c->d_b.p, c->d_sb.p, &ep);
     stage_mark(c, 7);
   } else if (fused_mv) {
+    PeerSync wait_b = p2p_sync(c->p2p, 3), wait_parts = p2p_sync(c->p2p, 4);
+    wait_b.raise_first = (raise_in_consumer && fused_b) ? 1 : 0;  // Ewald mode: p2p_push has signalled already
+    wait_parts.raise_first = raise_in_consumer ? 1 : 0;
     c->launches += launch_symv(s, c->d_mat.p, c->pitch, c->N, c->r0, nr, c->d_b.p, c->sy, c->d_rowpart.p,
-                               c->d_colpart.p, c->d_sb.p, (int)c->vlen, nullptr, p2p_sync(c->p2p, 3), producer(4),
-                               c->off_parts);
-    if (late_signal) c->launches += p2p_signal(c->p2p, 4, s);
+                               c->d_colpart.p, c->d_sb.p, (int)c->vlen, nullptr, wait_b, producer(4), c->off_parts);
+    if (late_signal && !raise_in_consumer) c->launches += p2p_signal(c->p2p, 4, s);
     stage_mark(c, 7);
-    c->launches += launch_update_charge_sum(s, make_epilogue(c, variant, false), p2p_sync(c->p2p, 4),
+    c->launches += launch_update_charge_sum(s, make_epilogue(c, variant, false), wait_parts,
                                             (const double *)(p2p_local(c->p2p) + c->off_parts), (int)c->vlen,
                                             c->d_sb.p);
   } else {
@@ -968,12 +958,12 @@ int conp_create(conp_ctx **out, int device, int rank, int nranks, const void *un
     }
     if (getenv("CONP_EWALD_GEMM")) c->eg_mode = atoi(getenv("CONP_EWALD_GEMM")) != 0 ? 1 : 0;
     c->signal_in_kernel = getenv("CONP_SIGNAL_IN_KERNEL") != nullptr && atoi(getenv("CONP_SIGNAL_IN_KERNEL")) != 0;
+    c->fused_signal = getenv("CONP_FUSED_SIGNAL") == nullptr || atoi(getenv("CONP_FUSED_SIGNAL")) != 0;
     c->uhat_nccl = getenv("CONP_UHAT_NCCL") != nullptr && atoi(getenv("CONP_UHAT_NCCL")) != 0;
     c->route_allowed = getenv("CONP_ROUTE") == nullptr || atoi(getenv("CONP_ROUTE")) != 0;
     if (const char *e = getenv("CONP_SPREAD"))
       c->spread_mode = !strcmp(e, "atomic") ? 0 : !strcmp(e, "smem") ? 1 : !strcmp(e, "mma") ? 2 :
                        !strcmp(e, "sweep") ? 3 : -1;
-    if (getenv("CONP_SPREAD_ATOMIC") != nullptr && atoi(getenv("CONP_SPREAD_ATOMIC")) != 0) c->spread_mode = 0;
     c->d_scal.zero(16, c->stream);
     c->d_partials.zero(3 * 1024, c->stream);
     c->d_counter.zero(1, c->stream);

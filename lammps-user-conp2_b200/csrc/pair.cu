@@ -248,7 +248,12 @@ bin_positions_kernel(CellGrid g, int m, int mpad, const int *__restrict__ counts
   }
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
-  if (j % mpad >= counts[j / mpad]) {
+  // (raise_first with counts: this rank's own entry of the delivered counts is written by block 0 of this very
+  // kernel -- read it from the source instead)
+  const int sender = j / mpad;
+  const int cnt = (ps.arena && ps.raise_first && ps.counts && sender == ps.rank) ? __ldcg(ps.counts + sender)
+                                                                                   : counts[sender];
+  if (j % mpad >= cnt) {
     cell_of[j] = -1;
     return;
   }

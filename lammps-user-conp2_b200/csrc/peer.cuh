@@ -35,6 +35,15 @@ struct PeerSync {
   // a one-block p2p_signal kernel raises them after the kernel boundary (cheaper for grids of many
   // small blocks: measured ~20 us of fences per kernel at ~1000 blocks)
   int signal_in_kernel = 1;
+  // consumer side: 1 = this rank's flags of the channel have not been raised yet (the producer kernel before
+  // this one only stored); block (0,0) of the consumer raises them in peer_block_wait before it starts to
+  // poll -- the kernel boundary has completed the producer's stores, and no stand-alone signal kernel is needed
+  int raise_first = 0;
+  // payload that only exists once the whole producer grid is done, delivered with the flags (raise_first):
+  // *value -> byte offset value_off of every rank's arena; counts[r] -> slot `rank` at count_off of rank r's
+  size_t value_off = 0, count_off = 0;
+  const double *value = nullptr;
+  const int *counts = nullptr;
 };
 
 __device__ __forceinline__ unsigned long long peer_ld_acquire(const unsigned long long *p) {
@@ -96,6 +105,16 @@ __device__ __forceinline__ void peer_block_wait(const PeerSync &ps) {
   ArenaCtl *mine = reinterpret_cast<ArenaCtl *>(ps.arena[ps.rank]);
   const unsigned long long e = mine->epoch[ps.chan] + 1ull;
   const int r = threadIdx.x;
+  if (ps.raise_first && blockIdx.x == 0 && blockIdx.y == 0 && r < ps.nranks) {
+    // (blocks are dispatched in index order, so block (0,0) of every rank runs even if the later blocks of
+    // the grid fill the GPU with pollers)
+    if (ps.value) *reinterpret_cast<double *>(ps.arena[r] + ps.value_off) = __ldcg(ps.value);
+    if (ps.counts) reinterpret_cast<int *>(ps.arena[r] + ps.count_off)[ps.rank] = __ldcg(ps.counts + r);
+    if (r != ps.rank) {
+      __threadfence_system();
+      peer_st_release(&reinterpret_cast<ArenaCtl *>(ps.arena[r])->flags[ps.chan][ps.rank], e);
+    }
+  }
   if (r < ps.nranks && r != ps.rank) {
     const long long t0 = clock64();
     while (peer_ld_acquire(&mine->flags[ps.chan][r]) < e) {

@@ -78,9 +78,8 @@ fill_zero_kernel(double *__restrict__ p, size_t n) {
 // slower: same-sector atomics of one warp instruction serialise in L2.)
 __global__ void __launch_bounds__(256)
 spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, const PosQ *__restrict__ atoms,
-              const int *__restrict__ cell_start, int cell_lo, int cell_hi, const int *__restrict__ inbox_counts,
-              int nsenders, int mpad, const int *__restrict__ valid, double *__restrict__ brick,
-              int *__restrict__ range_flag) {
+              const int *__restrict__ inbox_counts, int nsenders, int mpad, const int *__restrict__ valid,
+              double *__restrict__ brick, int *__restrict__ range_flag) {
   __shared__ double rc[MAXORDER * MAXORDER];
   __shared__ int cnt_end[17];  // inbox mode: running totals of the per-sender counts
   const int order = g.order;
@@ -90,10 +89,10 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
     for (int r = 0; r < nsenders; ++r) { tot += min(inbox_counts[r], mpad); cnt_end[r] = tot; }
   }
   __syncthreads();
-  // charges of the cell range (multi-GPU: the cells whose stencils can reach this rank's slab), or, inbox mode,
-  // the unsorted charges as they arrived: sender r's block starts at slot r * mpad and holds inbox_counts[r]
-  const int jb = inbox_counts ? 0 : (cell_start ? cell_start[cell_lo] : 0);
-  const int je = inbox_counts ? cnt_end[nsenders - 1] : (cell_start ? cell_start[cell_hi] : m_atoms);
+  // one GPU: atoms[0 .. m_atoms); several (inbox mode): the charges as they arrived, sender r's block starts at
+  // slot r * mpad and holds inbox_counts[r] (planes outside this rank's slab are skipped below)
+  const int jb = 0;
+  const int je = inbox_counts ? cnt_end[nsenders - 1] : m_atoms;
   const int per_atom = order * order;
   const long long work = (long long)(je - jb) * per_atom;
   for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < work;
@@ -1266,8 +1265,8 @@ int launch_fill_zero(cudaStream_t s, double *p, size_t n) {
 }
 
 int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coeff, int m_bound, const PosQ *atoms,
-                       const int *cell_start, int cell_lo, int cell_hi, double *brick, int *range_flag,
-                       const int *inbox_counts, int nsenders, int mpad, const int *valid) {
+                       double *brick, int *range_flag, const int *inbox_counts, int nsenders, int mpad,
+                       const int *valid) {
   if (m_bound <= 0 || g.zs_n <= 0) return 0;
   const long long threads = (long long)m_bound * g.order * g.order;
   const unsigned grid = (unsigned)((threads + 255) / 256);
@@ -1282,8 +1281,8 @@ int launch_pppm_spread(cudaStream_t s, const PPPMGeom &g, const double *rho_coef
     if (per_sm > 0 && per_sm < 8) smem = ((size_t)(227 * 1024) / per_sm - 1024) & ~(size_t)127;
   }
   if (smem > 0) ensure_dynamic_smem(spread_kernel, smem);
-  spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, cell_start, cell_lo, cell_hi, inbox_counts,
-                                        nsenders, mpad, valid, brick, range_flag);
+  spread_kernel<<<grid, 256, smem, s>>>(g, rho_coeff, m_bound, atoms, inbox_counts, nsenders, mpad, valid, brick,
+                                        range_flag);
   CUDA_CHECK(cudaGetLastError());
   return 1;
 }

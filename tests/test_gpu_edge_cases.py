@@ -233,13 +233,16 @@ def test_unsymmetric_influence_function_takes_the_complex_kernel():
     fix.close()
 
 
-@pytest.mark.parametrize("kernel", ["atomic", "smem", "mma", "sweep"])
+@pytest.mark.parametrize("kernel", ["atomic", "atomic_sorted", "smem", "mma", "sweep"])
 @pytest.mark.parametrize("which", ["small_slab", "dilute_periodic", "dilute_slab_order7", "small_order4"])
 def test_all_spread_kernels_give_the_oracle_density(kernel, which, monkeypatch):
-    """elyte_make_rho (pppm_conp.cpp:172-228) through each of the three spread kernels -- red.global,
-    shared-memory tiles (whole-axis tiles with halo on the small meshes), FP64 tensor-core tiles -- against
-    the oracle's brick, incl. even / high orders, periodic z and charges straddling every tile border."""
-    monkeypatch.setenv("CONP_SPREAD", kernel)
+    """elyte_make_rho (pppm_conp.cpp:172-228) through each of the spread kernels -- red.global (reading the
+    charges as packed, the default, or cell-sorted), shared-memory tiles (whole-axis tiles with halo on the small
+    meshes), FP64 tensor-core tiles, FP64 tensor-core z-sweep -- against the oracle's brick, incl. even / high
+    orders, periodic z and charges straddling every tile border."""
+    monkeypatch.setenv("CONP_SPREAD", kernel.split("_")[0])
+    if kernel == "atomic_sorted":
+        monkeypatch.setenv("CONP_SPREAD_UNSORTED", "0")
 
     def case():
         if which == "small_slab":
