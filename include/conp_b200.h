@@ -273,6 +273,15 @@ int conp_plan_spread(const int mesh[3], int order, double shift, const double bo
                      const int periodic[3], double slab_volfactor, double rc, int zin_lo, int nzi, int zs_lo,
                      int zs_n, int num_sms, int *geom_out, int *run_start_out, int max_tiles, int *runs_out,
                      int max_runs, int *ntiles_out, int *nruns_out);
+/* Host-only: the static candidate list of the real-space pair kernels (replaces the half neighbour list walked by
+ * blist_coul_cal / alist_coul_cal, fix_conp.cpp:1225-1365) for n fixed points (the electrode atoms) and search
+ * radius rc: sort-cell grid nc_out[3] (cells rc/2 wide, x fastest), and per point the x-contiguous runs of cells,
+ * seen through a periodic image shift, that the cut-off sphere can reach: run_start_out[n + 1] and
+ * runs_out[5 * nruns] = {c0, c1, sx, sy, sz} (cells [c0, c1), image shift in box lengths).  Points of a
+ * non-periodic axis outside the box are binned into the edge cells. */
+int conp_plan_pair_runs(const double boxlo[3], const double prd[3], const int periodic[3], double rc, int n,
+                        const double *xyz, int *nc_out, int *run_start_out, int *runs_out, int max_runs,
+                        int *nruns_out);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ SYMBOLS = [
     "conp_get_density_region", "conp_mesh_potential", "conp_electrode_potential",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
-    "conp_matvec", "conp_plan_symv", "conp_plan_spread", "conp_row_block",
+    "conp_matvec", "conp_plan_symv", "conp_plan_spread", "conp_row_block", "conp_plan_pair_runs",
 ]
 
 
@@ -81,6 +81,25 @@ def plan_spread(mesh, order, shift, boxlo, prd, periodic, slab_volfactor, rc, zi
     out = {k: int(v) for k, v in zip(keys, geom)}
     out.update(ntiles=nt.value, run_start=rs, runs=rr[:nr.value])
     return out
+
+
+def plan_pair_runs(boxlo, prd, periodic, rc, xyz):
+    """Static candidate list of the pair kernels (host-only entry point): (nc[3], run_start[n+1], runs[nruns,5])
+    with runs = (c0, c1, sx, sy, sz)."""
+    L = load_library()
+    lo, pr, pe = f64(boxlo), f64(prd), i32(periodic)
+    x = f64(np.ascontiguousarray(xyz).reshape(-1))
+    n = x.size // 3
+    nc = np.zeros(3, dtype=np.int32)
+    nr = C.c_int(0)
+    st = L.conp_plan_pair_runs(_dp(lo), _dp(pr), _ip(pe), float(rc), n, _dp(x), _ip(nc), None, None, 0, C.byref(nr))
+    if st:
+        raise RuntimeError(f"conp_plan_pair_runs: status {st}")
+    rs = np.zeros(n + 1, dtype=np.int32)
+    rr = np.zeros((max(nr.value, 1), 5), dtype=np.int32)
+    L.conp_plan_pair_runs(_dp(lo), _dp(pr), _ip(pe), float(rc), n, _dp(x), _ip(nc), _ip(rs), _ip(rr), nr.value,
+                          C.byref(nr))
+    return nc, rs, rr[:nr.value]
 
 
 def row_block(n_ele, nranks, rank):
@@ -161,6 +180,8 @@ def load_library(path: str | None = None):
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_ip, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.conp_row_block.argtypes = [C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip]
+    L.conp_plan_pair_runs.argtypes = [c_dp, c_dp, c_ip, C.c_double, C.c_int, c_dp, c_ip, c_ip, c_ip, C.c_int,
+                                      C.POINTER(C.c_int)]
     if path is None:
         _lib = L
     return L

@@ -2183,6 +2183,27 @@ int conp_plan_spread(const int mesh[3], int order, double shift, const double bo
   return CONP_OK;
 }
 
+int conp_plan_pair_runs(const double boxlo[3], const double prd[3], const int periodic[3], double rc, int n,
+                        const double *xyz, int *nc_out, int *run_start_out, int *runs_out, int max_runs,
+                        int *nruns_out) {
+  if (!boxlo || !prd || !periodic || !nc_out || !nruns_out || n < 0 || (n > 0 && !xyz) || !(rc > 0.0))
+    return CONP_ERR_ARG;
+  const CellGrid g = make_cell_grid(boxlo, prd, periodic, rc);
+  std::vector<int> rs;
+  std::vector<PairRun> rr;
+  build_pair_runs(g, 0, n, xyz, rs, rr);
+  for (int a = 0; a < 3; ++a) nc_out[a] = g.nc[a];
+  *nruns_out = (int)rr.size();
+  if (run_start_out)
+    for (int i = 0; i <= n; ++i) run_start_out[i] = rs[i];
+  if (runs_out)
+    for (int i = 0; i < (int)rr.size() && i < max_runs; ++i) {
+      int *o = runs_out + 5 * (size_t)i;
+      o[0] = rr[i].c0; o[1] = rr[i].c1; o[2] = rr[i].sx; o[3] = rr[i].sy; o[4] = rr[i].sz;
+    }
+  return CONP_OK;
+}
+
 int conp_bench_dgemm_tflops(conp_ctx *c, int n, double *tflops_out) {
   return guard(c, [&] {
     DevBuf<double> A, B, C;
