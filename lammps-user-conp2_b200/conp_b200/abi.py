@@ -271,6 +271,7 @@ class Context:
         m, r, g = i32(mesh), f64(rho_coeff), f64(greensfn)
         self._ck(self.L.conp_pppm_setup(self.h, _ip(m), int(order), _dp(r), _dp(g), float(shift), float(shiftone)))
         self.ngrid = int(np.prod(m))
+        self.mesh = tuple(int(v) for v in m)
 
     def build_A(self):
         self._ck(self.L.conp_build_A(self.h))
@@ -342,11 +343,15 @@ class Context:
         self._ck(self.L.conp_get_density(self.h, int(which), _dp(out)))
         return out
 
-    def get_density_region(self, which, lo, hi):
-        """Density on the sub-brick lo..hi (inclusive mesh indices x, y, z); returns [nz][ny][nx]."""
+    def get_density_region(self, which, lo, hi, out=None):
+        """Density on the sub-brick lo..hi (inclusive mesh indices x, y, z); returns [nz][ny][nx].  `out`: a
+        caller-owned C-contiguous float64 array of that shape (e.g. pinned memory, like a registered LAMMPS brick)."""
         lo_, hi_ = i32(lo), i32(hi)
         shape = tuple(int(hi_[a] - lo_[a] + 1) for a in (2, 1, 0))
-        out = np.zeros(shape)
+        if out is None:
+            out = np.zeros(shape)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("get_density_region: out must be a C-contiguous float64 array of the region's shape")
         self._ck(self.L.conp_get_density_region(self.h, int(which), _ip(lo_), _ip(hi_), _dp(out)))
         return out
 

@@ -96,6 +96,35 @@ def test_cfg4_matches_oracle_with_gpu_built_matrix(cfg4):
     _oracle_step_with_gpu_matrix(cfg4, "cfg4")
 
 
+def test_density_region_handoff_is_a_slice_of_the_brick_and_fast(cfg4):
+    """Force-pass hand-off (PPPMCONP::make_rho, pppm_conp.cpp:428-450): a rank's sub-brick of elyte + electrode
+    density comes from conp_get_density_region -- no allocation, no full-mesh transfer.  It must equal the same
+    slice of the full brick, and at this size cost well under a step (device side, incl. the copy to the host)."""
+    import torch
+    ctx = cfg4.ctx
+    cfg4.pre_force()
+    nx, ny, nz = ctx.mesh
+    full = ctx.get_density(2).reshape(nz, ny, nx)
+    assert np.abs(full).max() > 0.0
+    # the brick a rank of a 2 x 2 x 2 processor grid would own, and one that crosses the planes holding charge
+    for lo, hi in (((0, 0, 0), (nx // 2 - 1, ny // 2 - 1, nz // 2 - 1)),
+                   ((nx // 2, ny // 2, nz // 4), (nx - 1, ny - 1, nz // 4 + nz // 8))):
+        reg = ctx.get_density_region(2, lo, hi)
+        want = full[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+        assert reg.shape == want.shape and np.array_equal(reg, want)
+    # the brick of one rank of a 2 x 2 x 4 processor grid, into page-locked host memory (3.5 MB)
+    lo, hi = (0, 0, nz // 4), (nx // 2 - 1, ny // 2 - 1, nz // 4 + nz // 4 - 1)
+    shape = (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+    out = torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    ctx.get_density_region(2, lo, hi, out=out)  # warm: sizes the staging buffer
+    ctx.timer_record(0)
+    ctx.get_density_region(2, lo, hi, out=out)
+    ctx.timer_record(1)
+    ctx.sync()
+    assert np.array_equal(out, full[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1])
+    assert ctx.timer_elapsed_ms(0, 1) < 0.3
+
+
 def test_cfg5_headline_size_matches_oracle():
     """BASELINE configs[4] (40 000 electrode atoms / 500 000 charges): the configuration bench.py is
     quoted on.  Full setup on the GPU (Gram + inversion, ~90 s), then one jittered update against the oracle."""
