@@ -243,7 +243,8 @@ def gather_matrix_to_rank0(ctx, info, N, rank, world):
     mine = ctx.get_matrix()
     if world == 1:
         return mine
-    rows = torch.tensor([info.row_begin, info.row_end], dtype=torch.int64, device="cuda")
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"  # (gloo: the CPU test of this plumbing)
+    rows = torch.tensor([info.row_begin, info.row_end], dtype=torch.int64, device=dev)
     allrows = [torch.zeros_like(rows) for _ in range(world)]
     dist.all_gather(allrows, rows)
     allrows = [tuple(int(v) for v in t.cpu()) for t in allrows]
@@ -254,12 +255,12 @@ def gather_matrix_to_rank0(ctx, info, N, rank, world):
         for r in range(1, world):
             a, b = allrows[r]
             if b > a:
-                buf = torch.empty((b - a, N), dtype=torch.float64, device="cuda")
+                buf = torch.empty((b - a, N), dtype=torch.float64, device=dev)
                 dist.recv(buf, src=r)
                 S[a:b] = buf.cpu().numpy()
                 del buf
     elif info.row_end > info.row_begin:
-        dist.send(torch.from_numpy(mine).cuda(), dst=0)
+        dist.send(torch.from_numpy(np.ascontiguousarray(mine)).to(dev), dst=0)
     return S
 
 

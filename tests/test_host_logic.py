@@ -148,6 +148,48 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gather_worker(rank, world, port, q):
+    """bench.py's parity leg at N > 1: the row blocks of S (conp_row_block's partition) are assembled on rank 0
+    and every rank slices the same global jittered position sets."""
+    import sys
+    import types
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    from conp_b200 import abi
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 200
+    S = np.arange(n * n, dtype=np.float64).reshape(n, n)
+    a, b, _ = abi.row_block(n, world, rank)
+    ctx = types.SimpleNamespace(get_matrix=lambda: S[a:b].copy())
+    info = types.SimpleNamespace(row_begin=a, row_end=b)
+    full = bench.gather_matrix_to_rank0(ctx, info, n, rank, world)
+    x = np.linspace(0.0, 1.0, 30).reshape(10, 3)
+    sets = bench.jitter_sets(x, 3, seed=1234)
+    ok = (full is None) if rank else bool(np.array_equal(full, S))
+    q.put((rank, ok, (a, b), [s_.tobytes() for s_ in sets]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_matrix_gather_and_position_sets():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)                                   # rank 0 holds the whole S, the others nothing
+    assert res[0][2][0] == 0 and res[0][2][1] == res[1][2][0] and res[1][2][1] == 200  # contiguous row blocks
+    assert res[0][3] == res[1][3]                                   # every rank solves the same systems
+
+
 def test_gloo_world2_rank_plumbing():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
