@@ -279,6 +279,18 @@ int conp_plan_spread(const int mesh[3], int order, double shift, const double bo
  * seen through a periodic image shift, that the cut-off sphere can reach: run_start_out[n + 1] and
  * runs_out[5 * nruns] = {c0, c1, sx, sy, sz} (cells [c0, c1), image shift in box lengths).  Points of a
  * non-periodic axis outside the box are binned into the edge cells. */
+/* Host-only: the work plan of the windowed z-convolution that replaces the z-part of the FFT -> greensfn -> FFT
+ * chain of elyte_poisson (pppm_conp.cpp:230-267).  krad[ncol] = per (kx,ky) column the circular distance beyond
+ * which the tabulated kernel is dropped; zout[nzo] = mesh planes the electrode stencils read; the rank's slab of
+ * input planes is compact planes [zs_lo, zs_lo + nzl) of the nzi planes that can hold charge (mesh plane =
+ * zin_lo + compact plane, mod nz).  Columns are handled in groups of 8: a "narrow" group stages the slab planes
+ * within its radius of an output plane in shared memory, the other columns ("wide") read all planes.
+ * groups_out[32 * ngroups] = {c0, rblock, nint, np, lo[8], hi[8], base[8], pad[4]} per narrow group,
+ * wide_out[nwide] the wide columns, aout_out[nzo] the output planes in compact coordinates,
+ * caps_out[2] = {rcap, npcap} (largest radius / staged planes the narrow path is sized for). */
+int conp_plan_zconv(int ncol, int nz, int nzi, int zs_lo, int nzl, int zin_lo, const int *krad, int nzo,
+                    const int *zout, int real_kernel, int *groups_out, int max_groups, int *wide_out, int max_wide,
+                    int *aout_out, int *caps_out, int *ngroups_out, int *nwide_out);
 int conp_plan_pair_runs(const double boxlo[3], const double prd[3], const int periodic[3], double rc, int n,
                         const double *xyz, int *nc_out, int *run_start_out, int *runs_out, int max_runs,
                         int *nruns_out);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "conp_get_density_region", "conp_mesh_potential", "conp_electrode_potential",
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
-    "conp_matvec", "conp_plan_symv", "conp_plan_spread", "conp_row_block", "conp_plan_pair_runs",
+    "conp_matvec", "conp_plan_symv", "conp_plan_spread", "conp_row_block", "conp_plan_pair_runs", "conp_plan_zconv",
 ]
 
 
@@ -81,6 +81,32 @@ def plan_spread(mesh, order, shift, boxlo, prd, periodic, slab_volfactor, rc, zi
     out = {k: int(v) for k, v in zip(keys, geom)}
     out.update(ntiles=nt.value, run_start=rs, runs=rr[:nr.value])
     return out
+
+
+def plan_zconv(ncol, nz, nzi, zs_lo, nzl, zin_lo, krad, zout, real_kernel=True):
+    """Work plan of the windowed z-convolution (host-only entry point): dict with the narrow groups (c0, rblock,
+    intervals [(lo, hi, base)], np), the wide columns, the output planes in compact coordinates, rcap and npcap."""
+    L = load_library()
+    kr, zo = i32(krad), i32(zout)
+    ng, nw = C.c_int(0), C.c_int(0)
+    caps = np.zeros(2, dtype=np.int32)
+    args = (int(ncol), int(nz), int(nzi), int(zs_lo), int(nzl), int(zin_lo), _ip(kr), int(zo.size), _ip(zo),
+            int(bool(real_kernel)))
+    st = L.conp_plan_zconv(*args, None, 0, None, 0, None, _ip(caps), C.byref(ng), C.byref(nw))
+    if st:
+        raise RuntimeError(f"conp_plan_zconv: status {st}")
+    groups = np.zeros((max(ng.value, 1), 32), dtype=np.int32)
+    wide = np.zeros(max(nw.value, 1), dtype=np.int32)
+    aout = np.zeros(max(zo.size, 1), dtype=np.int32)
+    L.conp_plan_zconv(*args, _ip(groups), ng.value, _ip(wide), nw.value, _ip(aout), _ip(caps), C.byref(ng),
+                      C.byref(nw))
+    out = []
+    for g in groups[:ng.value]:
+        nint = int(g[2])
+        out.append(dict(c0=int(g[0]), rblock=int(g[1]), np=int(g[3]),
+                        intervals=[(int(g[4 + i]), int(g[12 + i]), int(g[20 + i])) for i in range(nint)]))
+    return dict(narrow=out, wide=wide[:nw.value].copy(), aout=aout[:zo.size].copy(), rcap=int(caps[0]),
+                npcap=int(caps[1]))
 
 
 def plan_pair_runs(boxlo, prd, periodic, rc, xyz):
@@ -180,6 +206,8 @@ def load_library(path: str | None = None):
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_ip, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.conp_row_block.argtypes = [C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip]
+    L.conp_plan_zconv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int, c_ip, C.c_int,
+                                  c_ip, C.c_int, c_ip, C.c_int, c_ip, c_ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.conp_plan_pair_runs.argtypes = [c_dp, c_dp, c_ip, C.c_double, C.c_int, c_dp, c_ip, c_ip, c_ip, C.c_int,
                                       C.POINTER(C.c_int)]
     if path is None:

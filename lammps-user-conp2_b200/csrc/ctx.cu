@@ -2183,6 +2183,30 @@ int conp_plan_spread(const int mesh[3], int order, double shift, const double bo
   return CONP_OK;
 }
 
+int conp_plan_zconv(int ncol, int nz, int nzi, int zs_lo, int nzl, int zin_lo, const int *krad, int nzo,
+                    const int *zout, int real_kernel, int *groups_out, int max_groups, int *wide_out, int max_wide,
+                    int *aout_out, int *caps_out, int *ngroups_out, int *nwide_out) {
+  if (ncol <= 0 || nz <= 0 || nzi <= 0 || nzi > nz || zs_lo < 0 || nzl < 0 || zs_lo + nzl > nzi || !krad || nzo < 0 ||
+      (nzo > 0 && !zout) || !caps_out || !ngroups_out || !nwide_out)
+    return CONP_ERR_ARG;
+  static_assert(sizeof(ZconvGroup) == 32 * sizeof(int), "ZconvGroup is handed out as 32 ints");
+  std::vector<ZconvGroup> narrow;
+  std::vector<int> wide, aout;
+  ZconvPlan plan;
+  plan_pppm_zconv(std::vector<int>(krad, krad + ncol), ncol, nz, nzi, zs_lo, nzl, zin_lo,
+                  std::vector<int>(zout, zout + nzo), real_kernel != 0, narrow, wide, aout, plan);
+  *ngroups_out = (int)narrow.size();
+  *nwide_out = (int)wide.size();
+  caps_out[0] = plan.rcap; caps_out[1] = plan.npcap;
+  if (groups_out)
+    std::memcpy(groups_out, narrow.data(), sizeof(ZconvGroup) * std::min<size_t>(narrow.size(), (size_t)std::max(max_groups, 0)));
+  if (wide_out)
+    std::memcpy(wide_out, wide.data(), sizeof(int) * std::min<size_t>(wide.size(), (size_t)std::max(max_wide, 0)));
+  if (aout_out)
+    for (int i = 0; i < nzo; ++i) aout_out[i] = aout[i];
+  return CONP_OK;
+}
+
 int conp_plan_pair_runs(const double boxlo[3], const double prd[3], const int periodic[3], double rc, int n,
                         const double *xyz, int *nc_out, int *run_start_out, int *runs_out, int max_runs,
                         int *nruns_out) {
