@@ -279,6 +279,13 @@ int conp_plan_spread(const int mesh[3], int order, double shift, const double bo
  * seen through a periodic image shift, that the cut-off sphere can reach: run_start_out[n + 1] and
  * runs_out[5 * nruns] = {c0, c1, sx, sy, sz} (cells [c0, c1), image shift in box lengths).  Points of a
  * non-periodic axis outside the box are binned into the edge cells. */
+/* Host-only: the work plan of the z-sweep PPPM spread (the second, mesh-aligned sort + sliding window of planes
+ * that replaces the scatter loop of elyte_make_rho, pppm_conp.cpp:172-228, at large charge counts) for a rank's
+ * slab [zs_lo, zs_lo + zs_n) of the nzi compact planes: geom_out[8] = {usable, columns along x, columns along y
+ * (a column = 8 rows x 32 mesh columns), first binned origin plane, number of binned origin planes, origin planes
+ * wrap (periodic z), bins, grid size}; items_out[3 * nitems] = {column, first, end slab plane of the segment}. */
+int conp_plan_sweep(const int mesh[3], int order, int nzi, int zs_lo, int zs_n, int num_sms, int *geom_out,
+                    int *items_out, int max_items, int *nitems_out);
 /* Host-only: the work plan of the windowed z-convolution that replaces the z-part of the FFT -> greensfn -> FFT
  * chain of elyte_poisson (pppm_conp.cpp:230-267).  krad[ncol] = per (kx,ky) column the circular distance beyond
  * which the tabulated kernel is dropped; zout[nzo] = mesh planes the electrode stencils read; the rank's slab of

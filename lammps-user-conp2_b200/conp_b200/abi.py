@@ -30,6 +30,7 @@ SYMBOLS = [
     "conp_get_potential_brick", "conp_post_force", "conp_stream", "conp_sync", "conp_timer_record",
     "conp_timer_elapsed_ms", "conp_stage_times", "conp_bench_gemv", "conp_bench_dgemm_tflops",
     "conp_matvec", "conp_plan_symv", "conp_plan_spread", "conp_row_block", "conp_plan_pair_runs", "conp_plan_zconv",
+    "conp_plan_sweep",
 ]
 
 
@@ -80,6 +81,24 @@ def plan_spread(mesh, order, shift, boxlo, prd, periodic, slab_volfactor, rc, zi
     keys = ("tz", "ty", "tx", "ntz", "nty", "ntx", "halo_z", "halo_y", "halo_x", "ncx", "ncy", "ncz")
     out = {k: int(v) for k, v in zip(keys, geom)}
     out.update(ntiles=nt.value, run_start=rs, runs=rr[:nr.value])
+    return out
+
+
+def plan_sweep(mesh, order, nzi, zs_lo, zs_n, num_sms=148):
+    """Work plan of the z-sweep spread (host-only entry point)."""
+    L = load_library()
+    m = i32(mesh)
+    geom = np.zeros(8, dtype=np.int32)
+    n = C.c_int(0)
+    args = (_ip(m), int(order), int(nzi), int(zs_lo), int(zs_n), int(num_sms))
+    st = L.conp_plan_sweep(*args, _ip(geom), None, 0, C.byref(n))
+    if st:
+        raise RuntimeError(f"conp_plan_sweep: status {st}")
+    items = np.zeros((max(n.value, 1), 3), dtype=np.int32)
+    L.conp_plan_sweep(*args, _ip(geom), _ip(items), n.value, C.byref(n))
+    keys = ("usable", "ncolx", "ncoly", "pz_lo", "npz", "wrap_z", "nbins", "grid")
+    out = {k: int(v) for k, v in zip(keys, geom)}
+    out["items"] = items[:n.value]
     return out
 
 
@@ -206,6 +225,8 @@ def load_library(path: str | None = None):
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_ip, C.c_int,
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.conp_row_block.argtypes = [C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip]
+    L.conp_plan_sweep.argtypes = [c_ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, C.c_int,
+                                  C.POINTER(C.c_int)]
     L.conp_plan_zconv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int, c_ip, C.c_int,
                                   c_ip, C.c_int, c_ip, C.c_int, c_ip, c_ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.conp_plan_pair_runs.argtypes = [c_dp, c_dp, c_ip, C.c_double, C.c_int, c_dp, c_ip, c_ip, c_ip, C.c_int,

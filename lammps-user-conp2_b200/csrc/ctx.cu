@@ -2183,6 +2183,28 @@ int conp_plan_spread(const int mesh[3], int order, double shift, const double bo
   return CONP_OK;
 }
 
+int conp_plan_sweep(const int mesh[3], int order, int nzi, int zs_lo, int zs_n, int num_sms, int *geom_out,
+                    int *items_out, int max_items, int *nitems_out) {
+  if (!mesh || !geom_out || !nitems_out || order < 1 || order > 7 || nzi < 0 || nzi > mesh[2] || zs_lo < 0 ||
+      zs_n < 0 || zs_lo + zs_n > nzi || num_sms < 1)
+    return CONP_ERR_ARG;
+  PPPMGeom g;
+  std::memset(&g, 0, sizeof(g));
+  g.nx = mesh[0]; g.ny = mesh[1]; g.nz = mesh[2]; g.order = order;
+  g.nzi = nzi; g.zs_lo = zs_lo; g.zs_n = zs_n;
+  std::vector<int4> items;
+  SweepPlan sp;
+  plan_pppm_sweep(g, num_sms, items, sp);
+  const int geom[8] = {sp.usable ? 1 : 0, sp.ncolx, sp.ncoly, sp.pz_lo, sp.npz, sp.wrap_z, sp.nbins, sp.grid};
+  std::memcpy(geom_out, geom, sizeof(geom));
+  *nitems_out = (int)items.size();
+  if (items_out)
+    for (int i = 0; i < (int)items.size() && i < max_items; ++i) {
+      items_out[3 * i] = items[i].x; items_out[3 * i + 1] = items[i].y; items_out[3 * i + 2] = items[i].z;
+    }
+  return CONP_OK;
+}
+
 int conp_plan_zconv(int ncol, int nz, int nzi, int zs_lo, int nzl, int zin_lo, const int *krad, int nzo,
                     const int *zout, int real_kernel, int *groups_out, int max_groups, int *wide_out, int max_wide,
                     int *aout_out, int *caps_out, int *ngroups_out, int *nwide_out) {

@@ -104,3 +104,57 @@ def test_dilute_reference_meshes():
 @pytest.mark.parametrize("rank", [0, 1, 2, 3])
 def test_rank_slab_of_four(rank):
     _check((64, 108, 300), 5, (61.5, 106.5, 100.0), (1, 1, 0), 3.0, 12.0, nranks=4, rank=rank, seed=10 + rank)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# z-sweep spread (plan_pppm_sweep through conp_plan_sweep): columns of 8 rows x 32 mesh columns, swept upward in
+# segments of planes with a window of `order` planes; charges are binned by (column, origin plane)
+# ---------------------------------------------------------------------------------------------------------------
+SW_FY, SW_FX, SW_MAXS = 8, 32, 64
+
+
+@pytest.mark.parametrize("mesh,order,nzi", [((125, 216, 1215), 5, 414), ((64, 108, 1000), 5, 350),
+                                            ((54, 48, 288), 5, 288), ((40, 48, 900), 4, 300),
+                                            ((54, 48, 864), 7, 288)])
+@pytest.mark.parametrize("nranks", [1, 2, 8])
+def test_sweep_plan_covers_every_plane_once_and_bins_every_origin(mesh, order, nzi, nranks):
+    from conp_b200 import abi
+    nx, ny, nz = mesh
+    per = -(-nzi // nranks)
+    for rank in range(nranks):
+        zs_lo = min(rank * per, nzi)
+        zs_n = max(0, min(per, nzi - zs_lo))
+        p = abi.plan_sweep(mesh, order, nzi, zs_lo, zs_n)
+        if zs_n == 0:
+            assert not p["usable"]
+            continue
+        assert p["usable"] == 1
+        ncx, ncy = -(-nx // SW_FX), -(-ny // SW_FY)
+        assert (p["ncolx"], p["ncoly"]) == (ncx, ncy) and p["nbins"] == ncx * ncy * p["npz"]
+        # every (column, slab plane) belongs to exactly one work item; a segment plus its warm-up fits the kernel
+        cover = np.zeros((ncx * ncy, zs_n), dtype=np.int32)
+        for col, t0, t1 in p["items"]:
+            assert 0 <= t0 < t1 <= zs_n and (t1 - t0) + (order - 1) <= SW_MAXS
+            cover[col, t0:t1] += 1
+        assert np.all(cover == 1)
+        assert 1 <= p["grid"] <= min(len(p["items"]), 148 * 12)
+        # every origin plane whose stencil (planes o .. o + order - 1) touches the slab has a bin
+        wrap = nzi == nz
+        assert p["wrap_z"] == int(wrap)
+        for o in range(-(order - 1), nzi):
+            planes = [(o + k) % nz if wrap else o + k for k in range(order)]
+            if not wrap and (o < 0 or o + order > nzi):
+                continue                                     # "Out of range atoms": rejected before binning
+            if any(zs_lo <= z < zs_lo + zs_n for z in planes):
+                t = (o % nz if wrap else o) - p["pz_lo"]
+                if wrap:
+                    t %= nz
+                assert 0 <= t < p["npz"], (o, p["pz_lo"], p["npz"])
+
+
+@pytest.mark.parametrize("mesh,order", [((36, 48, 100), 5),     # one column + a stencil would wrap inside it
+                                        ((66, 48, 100), 5),     # last column (2 wide) narrower than order - 1
+                                        ((64, 12, 100), 5)])    # too few rows
+def test_sweep_plan_refuses_meshes_whose_stencils_would_wrap_inside_a_column(mesh, order):
+    from conp_b200 import abi
+    assert not abi.plan_sweep(mesh, order, 100, 0, 100)["usable"]
