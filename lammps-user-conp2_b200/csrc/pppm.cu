@@ -142,7 +142,7 @@ spread_kernel(PPPMGeom g, const double *__restrict__ rho_coeff, int m_atoms, con
 }
 
 // ---------------------------------------------------------------------------
-// Owner-computes spread (the per-step default): no atomics, every mesh point stored exactly once.
+// Owner-computes spread, tile form (CONP_SPREAD=smem): no atomics, every mesh point stored exactly once.
 //
 // The rank's slab of input planes is cut into tiles of tz x ty x tx points.  One warp (= one CTA) owns a
 // tile at a time, accumulated in its private shared memory: a warp never shares a tile, so plain
